@@ -1,0 +1,93 @@
+"""ctypes binding of ``libbayescard_b200.so`` (the C ABI declared in ``include/bayescard_b200.h``).
+
+No torch types cross this boundary: callers pass raw addresses (``tensor.data_ptr()``,
+``ndarray.ctypes.data``) and a raw ``cudaStream_t``.  There is no fallback of any kind: if the
+shared library is missing, :func:`lib` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbayescard_b200.so")
+SPEC_CACHE_DIR = os.path.join(_HERE, "_spec_cache")
+
+BC_OK = 0
+DESC_RANGE_U8, DESC_RANGE_U16, DESC_DENSE_F32 = 0, 1, 2
+KERNEL_AUTO, KERNEL_GENERIC, KERNEL_SPEC, KERNEL_GEMM = 0, 1, 2, 3
+
+_lib = None
+
+
+class BayesCardError(RuntimeError):
+    pass
+
+
+def build(verbose: bool = False) -> str:
+    """Compile the extension in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    script = os.path.join(_HERE, "csrc", "build.sh")
+    res = subprocess.run(["bash", script], capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout)
+        print(res.stderr)
+    if res.returncode != 0:
+        raise BayesCardError("building libbayescard_b200.so failed")
+    global _lib
+    _lib = None
+    return LIB_PATH
+
+
+_SIGS = {
+    # name: (restype, argtypes)
+    "bc_model_create": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "bc_model_destroy": (None, [C.c_void_p]),
+    "bc_model_n_nodes": (C.c_int, [C.c_void_p]),
+    "bc_model_device": (C.c_int, [C.c_void_p]),
+    "bc_model_dense_width": (C.c_int64, [C.c_void_p]),
+    "bc_model_dense_offset": (C.c_int64, [C.c_void_p, C.c_int]),
+    "bc_model_desc_stride": (C.c_int64, [C.c_void_p, C.c_int]),
+    "bc_model_flops_dense": (C.c_int64, [C.c_void_p]),
+    "bc_model_specialize": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "bc_model_has_spec": (C.c_int, [C.c_void_p]),
+    "bc_model_spec_source": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "bc_model_spec_hash": (C.c_uint64, [C.c_void_p]),
+    "bc_model_load_cubin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "bc_query_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                 C.c_void_p]),
+    "bc_query_batch_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
+    "bc_gen_range_queries": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_size_t, C.c_int, C.c_int, C.c_void_p,
+                                       C.c_void_p]),
+    "bc_gen_range_queries_host": (C.c_int, [C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_size_t, C.c_int,
+                                            C.c_int, C.c_void_p]),
+    "bc_measure_fp32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "bc_launch_count": (C.c_uint64, []),
+    "bc_last_error": (C.c_char_p, []),
+    "bc_version": (C.c_char_p, []),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGS)
+
+
+def lib():
+    """The loaded library.  Raises if the CUDA extension has not been built -- no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise BayesCardError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(bayescard_b200 has no CPU fallback)")
+        h = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(h, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = h
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != BC_OK:
+        raise BayesCardError(f"bayescard_b200 error {rc}: {lib().bc_last_error().decode('utf-8', 'replace')}")

@@ -1,0 +1,12 @@
+#!/bin/bash
+# Build libbayescard_b200.so in-tree for sm_100a (the .so is git-ignored but travels with gpurun).
+set -euo pipefail
+cd "$(dirname "$0")"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+OUT=../libbayescard_b200.so
+SRCS="bc_api.cu k1_generic.cu spec_jit.cu spec_codegen.cc"
+$NVCC -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xptxas -v \
+      -Xcompiler -fPIC,-O2,-Wall,-fvisibility=hidden -shared -cudart static \
+      -x cu $SRCS -o $OUT -ldl 2> build.log || { cat build.log; exit 1; }
+grep -E "error|warning: v|Used [0-9]+ registers|spill" build.log | grep -v "0 bytes spill" | head -40 || true
+echo "built $OUT"

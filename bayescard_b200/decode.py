@@ -1,0 +1,306 @@
+"""Predicate compiler: raw predicates -> (bins, weights) -> packed per-query descriptors.
+
+Stage 1 (:meth:`PredicateCompiler.decode`) has the semantics of ``Bayescard_BN.query_decoding``
+(reference ``Models/Bayescard_BN.py:279-325``) with its helpers ``realign`` (``:53-72``),
+``continuous_range_map`` (``:180-239``), ``apply_encoding_to_value`` / ``apply_ndistinct_to_value``
+(``Models/BN_single_model.py:98-139``), quirks included:
+
+* an unknown scalar, a column without an encoding or an empty value list make the whole query
+  undecodable (``(None, None)``, estimate 0); unknown members of a value LIST are silently dropped;
+* several values falling into one bin add their ``n_in_bin`` fractions, capped at 1;
+* a ``(lo, hi)`` tuple on a categorical column enumerates the ORIGINAL values inside the range, minus
+  the column's null value;
+* continuous ranges are clamped to the column domain, a point ``x`` becomes ``[x-eps, x+eps]`` (times the
+  hard-coded ``n_distinct_mapping`` multiplier), and the bin walk stops expanding on one side as soon
+  as the other side reaches the edge of the domain.
+
+Unlike the reference nothing is mutated: ``decode`` returns fresh dicts.
+
+Stage 2 (:meth:`PredicateCompiler.pack`) writes descriptors for the CUDA kernels: the compact
+``RANGE_U8`` row when every predicate of a query is a contiguous bin interval with unit weights
+(89 % / 83 % of the shipped DMV / Census predicates), the dense fp32 weight row otherwise; fan-out
+columns of ``expectation`` become a bitmask (a predicate on the same column clears the bit, because the
+reference tests the predicate first: ``Pgmpy/inference/ExactInference.py:209,:238``).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib as L
+from .loader import TreeModel
+
+Decoded = Tuple[Optional[Dict[str, List[int]]], Optional[Dict[str, np.ndarray]]]
+
+
+class _Column:
+    """Per-column lookup tables built once per model."""
+
+    __slots__ = ("name", "kind", "enc", "pair", "num_vals", "num_bins", "num_wts", "null", "has_null",
+                 "edges", "domain", "nd_map", "card")
+
+    def __init__(self, tm: TreeModel, name: str):
+        self.name = name
+        self.kind = tm.attr_type.get(name)
+        self.enc = tm.encoding.get(name) if name in tm.encoding else None
+        self.card = int(tm.card[tm.index_of(name)]) if name in tm._index else None
+        nib = tm.n_in_bin.get(name) if name in tm.n_in_bin else None
+        has_nib = name in tm.n_in_bin
+        # value -> (bin, weight)
+        self.pair = {}
+        if self.enc is not None:
+            for val, b in self.enc.items():
+                w = 1
+                if has_nib and nib is not None and b in nib:
+                    t = nib[b]
+                    if isinstance(t, int):
+                        w = 1 / t
+                    elif val in t:
+                        w = t[val]
+                self.pair[val] = (b, w)
+        nv = tm.null_values
+        self.has_null = not (nv is None or len(nv) == 0 or name not in nv)
+        self.null = nv[name] if self.has_null else None
+        # numeric categorical columns: arrays in encoding (dict) order for vectorised range lookups
+        self.num_vals = self.num_bins = self.num_wts = None
+        if self.enc is not None and len(self.enc) and all(
+                isinstance(k, (int, float)) and not isinstance(k, bool) for k in self.enc):
+            keys = list(self.enc.keys())
+            self.num_vals = np.asarray(keys, dtype=np.float64)
+            self.num_bins = np.asarray([self.pair[k][0] for k in keys], dtype=np.int64)
+            self.num_wts = np.asarray([self.pair[k][1] for k in keys], dtype=np.float64)
+        self.edges = tm.mapping.get(name) if name in tm.mapping else None
+        self.domain = tm.domain.get(name)
+        self.nd_map = tm.n_distinct_mapping.get(name) if name in tm.n_distinct_mapping else None
+
+
+def _merge(bins: Sequence, wts: Sequence) -> Tuple[List[int], np.ndarray]:
+    """realign: drop None, first-occurrence order, duplicate bins add up capped at 1."""
+    pos: Dict[int, int] = {}
+    out_b: List[int] = []
+    out_w: List[float] = []
+    for b, w in zip(bins, wts):
+        if b is None:
+            continue
+        j = pos.get(b)
+        if j is None:
+            pos[b] = len(out_b)
+            out_b.append(int(b))
+            out_w.append(w)
+        else:
+            out_w[j] = min(out_w[j] + w, 1)
+    return out_b, np.asarray(out_w, dtype=np.float64)
+
+
+class PredicateCompiler:
+    def __init__(self, tm: TreeModel):
+        self.tm = tm
+        self.cols: Dict[str, _Column] = {n: _Column(tm, n) for n in tm.node_names}
+
+    # ------------------------------------------------------------------ stage 1
+    def _continuous(self, col: _Column, lo: float, hi: float) -> Tuple[List[int], np.ndarray]:
+        edges = col.edges
+        n = len(edges)
+
+        def cover(k: int) -> float:
+            tl, tr = edges[k]
+            if lo >= tr or hi <= tl:
+                return 0
+            if hi > tr:
+                return 1 if lo < tl else (tr - lo) / (tr - tl)
+            return (hi - lo) / (tr - tl) if lo > tl else (hi - tl) / (tr - tl)
+
+        # bisection for any bin overlapping [lo, hi]; same probe sequence as the reference
+        i, j = 0, n
+        while i != j:
+            mid = int(i + (j - i) / 2)
+            tl, tr = edges[mid]
+            if lo >= tr:
+                if i == mid:  # the reference recurses forever here; cannot happen for lo inside the domain
+                    break
+                i = mid
+            elif hi <= tl:
+                j = mid
+            else:
+                i = j = mid
+        down, up = i, i + 1
+        more_down = more_up = True
+        bins: List[int] = []
+        cov: List[float] = []
+        while down >= 0 and up < n and (more_down or more_up):
+            if more_down:
+                c = cover(down)
+                if c != 0:
+                    bins.append(down)
+                    cov.append(c)
+                    down -= 1
+                else:
+                    more_down = False
+            if more_up:
+                c = cover(up)
+                if c != 0:
+                    bins.append(up)
+                    cov.append(c)
+                    up += 1
+                else:
+                    more_up = False
+        return bins, np.asarray(cov, dtype=np.float64)
+
+    def decode(self, query: dict, coverage: Optional[dict] = None, epsilon: float = 0.5) -> Decoded:
+        bins_out: Dict[str, List[int]] = {}
+        wts_out: Dict[str, np.ndarray] = {}
+        for attr, val in query.items():
+            col = self.cols.get(attr)
+            if col is None or col.kind is None:
+                raise KeyError(attr)
+            if col.kind == "continuous":
+                if coverage is not None:
+                    bins_out[attr] = list(val) if isinstance(val, (list, tuple, np.ndarray)) else [val]
+                    wts_out[attr] = np.asarray(coverage[attr], dtype=np.float64)
+                    continue
+                mult = None
+                if type(val) == tuple:
+                    lo = max(col.domain[0], val[0])
+                    hi = min(col.domain[1], val[1])
+                else:
+                    lo, hi = val - epsilon, val + epsilon
+                    if col.nd_map is not None and val in col.nd_map:
+                        mult = col.nd_map[val]
+                if lo > hi:
+                    return None, None
+                b, w = self._continuous(col, lo, hi)
+                if mult is not None:
+                    w = w * mult
+                bins_out[attr], wts_out[attr] = b, w
+            elif type(val) == tuple:
+                lo, hi = val[0], val[1]
+                if col.num_vals is not None and isinstance(lo, (int, float)) and isinstance(hi, (int, float)):
+                    keep = (col.num_vals >= lo) & (col.num_vals <= hi)
+                    if col.has_null:
+                        keep &= col.num_vals != col.null
+                    sel_b, sel_w = col.num_bins[keep], col.num_wts[keep]
+                else:
+                    sel_b, sel_w = [], []
+                    for v, (b, w) in col.pair.items():
+                        if col.has_null and v == col.null:
+                            continue
+                        if lo <= v <= hi:
+                            sel_b.append(b)
+                            sel_w.append(w)
+                if len(sel_b) == 0:
+                    return None, None
+                bins_out[attr], wts_out[attr] = _merge(sel_b, sel_w)
+            else:
+                if col.enc is None:
+                    return None, None
+                if type(val) == list:
+                    if len(val) == 0:
+                        return None, None
+                    pairs = [col.pair.get(v, (None, 1)) for v in val]
+                    bins_out[attr], wts_out[attr] = _merge([p[0] for p in pairs], [p[1] for p in pairs])
+                else:
+                    p = col.pair.get(val)
+                    if p is None:
+                        return None, None
+                    bins_out[attr], wts_out[attr] = [int(p[0])], np.asarray([p[1]], dtype=np.float64)
+        return bins_out, wts_out
+
+    # ------------------------------------------------------------------ stage 2
+    def _is_unit_range(self, b: Sequence[int], w: np.ndarray) -> Optional[Tuple[int, int]]:
+        if len(b) == 0:
+            return (1, 0)  # selects nothing
+        lo, hi = min(b), max(b)
+        if hi - lo + 1 != len(b) or len(set(b)) != len(b):
+            return None
+        w = np.asarray(w, dtype=np.float64).reshape(-1)
+        if w.size == 1 and len(b) > 1:
+            return (lo, hi) if w[0] == 1 else None
+        return (lo, hi) if np.all(w == 1) else None
+
+    def pack(self, decoded: Sequence[Tuple[Dict[str, Sequence[int]], Dict[str, np.ndarray]]],
+             fanouts: Optional[Sequence[Sequence[str]]] = None, force_dense: bool = False):
+        """Pack already decoded queries.
+
+        Returns ``(range_idx, range_desc, dense_idx, dense_desc, mask)``: indices of the queries that
+        went to the ``RANGE_U8`` / ``DENSE_F32`` batch, the two descriptor arrays and the fan-out
+        bitmask rows (``None`` when no query has fan-out columns), all in input order within a batch.
+        Columns outside the root component are ignored, as the reference's Steiner walk never sees them.
+        """
+        tm = self.tm
+        n = tm.n_nodes
+        nq = len(decoded)
+        stride = -(-2 * n // 4) * 4
+        width = int(sum(-(-int(c) // 4) * 4 for c in tm.card))
+        off = np.concatenate([[0], np.cumsum([-(-int(c) // 4) * 4 for c in tm.card])[:-1]]).astype(np.int64)
+        allow_range = (not force_dense) and int(tm.card.max()) <= 256
+        base_row = np.zeros(stride, dtype=np.uint8)
+        base_row[1:2 * n:2] = np.minimum(tm.card - 1, 255).astype(np.uint8)
+        words = (n + 31) // 32
+        mask = np.zeros((nq, words), dtype=np.uint32) if fanouts is not None else None
+        kinds = np.zeros(nq, dtype=np.int8)  # 0 = range, 1 = dense
+        range_rows: List[np.ndarray] = []
+        dense_rows: List[np.ndarray] = []
+        for qi, (bins, wts) in enumerate(decoded):
+            ranges = {}
+            ok = allow_range
+            for attr, b in bins.items():
+                v = tm._index.get(attr)
+                if v is None:
+                    continue
+                bl = list(b) if isinstance(b, (list, tuple, np.ndarray)) else [b]
+                r = self._is_unit_range(bl, wts[attr]) if ok else None
+                if r is None:
+                    ok = False
+                    break
+                ranges[v] = r
+            if fanouts is not None:
+                for attr in fanouts[qi]:
+                    v = tm._index.get(attr)
+                    if v is None or attr in bins or tm.fan_vector(v) is None:
+                        continue
+                    mask[qi, v >> 5] |= np.uint32(1 << (v & 31))
+            if ok:
+                row = base_row.copy()
+                for v, (lo, hi) in ranges.items():
+                    row[2 * v], row[2 * v + 1] = lo, hi
+                range_rows.append(row)
+            else:
+                kinds[qi] = 1
+                row = np.zeros(width, dtype=np.float32)
+                for v in range(n):
+                    row[off[v]: off[v] + int(tm.card[v])] = 1.0
+                for attr, b in bins.items():
+                    v = tm._index.get(attr)
+                    if v is None:
+                        continue
+                    bl = list(b) if isinstance(b, (list, tuple, np.ndarray)) else [b]
+                    w = np.asarray(wts[attr], dtype=np.float64).reshape(-1)
+                    seg = np.zeros(int(tm.card[v]), dtype=np.float64)
+                    if len(bl):
+                        if w.size == 1 and len(bl) > 1:
+                            w = np.full(len(bl), w[0])
+                        np.add.at(seg, np.asarray(bl, dtype=np.int64), w)
+                    row[off[v]: off[v] + int(tm.card[v])] = seg
+                dense_rows.append(row)
+        range_idx = np.nonzero(kinds == 0)[0]
+        dense_idx = np.nonzero(kinds == 1)[0]
+        range_desc = np.stack(range_rows) if range_rows else np.zeros((0, stride), dtype=np.uint8)
+        dense_desc = np.stack(dense_rows) if dense_rows else np.zeros((0, width), dtype=np.float32)
+        return range_idx, range_desc, dense_idx, dense_desc, mask
+
+    def pack_ranges(self, lo: np.ndarray, hi: np.ndarray) -> np.ndarray:
+        """Vectorised RANGE_U8 packing of ``[B, n_nodes]`` bin bounds (topological node order)."""
+        n = self.tm.n_nodes
+        stride = -(-2 * n // 4) * 4
+        out = np.zeros((lo.shape[0], stride), dtype=np.uint8)
+        out[:, 0:2 * n:2] = lo
+        out[:, 1:2 * n:2] = hi
+        return out
+
+
+def unpack_ranges(tm: TreeModel, desc: np.ndarray):
+    """Inverse of :meth:`PredicateCompiler.pack_ranges`: ``(lo, hi)`` int arrays ``[B, n_nodes]``."""
+    n = tm.n_nodes
+    d = np.asarray(desc, dtype=np.uint8).reshape(-1, -(-2 * n // 4) * 4)
+    return d[:, 0:2 * n:2].astype(np.int64), d[:, 1:2 * n:2].astype(np.int64)

@@ -1,0 +1,198 @@
+"""Device-side model handle: a :class:`~bayescard_b200.loader.TreeModel` uploaded through the C ABI.
+
+``DeviceModel`` owns one ``bc_model*`` (one GPU).  ``ShardedModel`` replicates the CPT arena on several
+GPUs and splits a query batch into contiguous ranges, one host thread + stream set per device, no
+collective on the data path.  PyTorch is not needed here; callers that hold
+torch tensors pass ``tensor.data_ptr()`` and ``torch.cuda.current_stream().cuda_stream``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+from .loader import TreeModel
+
+
+class DeviceModel:
+    def __init__(self, tm: TreeModel, device: int = 0, specialize: bool = True, cache_dir: Optional[str] = None):
+        self.tm = tm
+        self.device = device
+        lib = L.lib()
+        arena, off, stride = tm.pack_arena()
+        fan, foff = tm.pack_fanouts()
+        parent = np.ascontiguousarray(tm.parent, dtype=np.int32)
+        card = np.ascontiguousarray(tm.card, dtype=np.int32)
+        h = C.c_void_p()
+        L.check(lib.bc_model_create(device, tm.n_nodes, parent.ctypes.data, card.ctypes.data, off.ctypes.data,
+                                    stride.ctypes.data, arena.ctypes.data, arena.size, foff.ctypes.data,
+                                    fan.ctypes.data, fan.size, C.byref(h)))
+        self._h = h
+        self.n_nodes = tm.n_nodes
+        self.mask_words = (tm.n_nodes + 31) // 32
+        self.dense_width = int(lib.bc_model_dense_width(h))
+        self.dense_offset = np.array([lib.bc_model_dense_offset(h, v) for v in range(tm.n_nodes)], dtype=np.int64)
+        self.flops_dense = int(lib.bc_model_flops_dense(h))
+        self.max_card = int(card.max())
+        self.spec_error: Optional[str] = None
+        if specialize and device >= 0:
+            try:
+                self.specialize(cache_dir)
+            except L.BayesCardError as e:  # generic CUDA kernel keeps serving; remembered for diagnostics
+                self.spec_error = str(e)
+
+    # ------------------------------------------------------------------ lifecycle
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            L.lib().bc_model_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ specialised kernel
+    def specialize(self, cache_dir: Optional[str] = None) -> None:
+        cache_dir = L.SPEC_CACHE_DIR if cache_dir is None else cache_dir
+        if cache_dir:
+            os.makedirs(cache_dir, exist_ok=True)
+        L.check(L.lib().bc_model_specialize(self._h, cache_dir.encode() if cache_dir else None))
+
+    @property
+    def has_spec(self) -> bool:
+        return bool(L.lib().bc_model_has_spec(self._h))
+
+    def spec_source(self) -> str:
+        lib = L.lib()
+        n = lib.bc_model_spec_source(self._h, None, 0)
+        if n < 0:
+            L.check(int(n))
+        buf = C.create_string_buffer(int(n))
+        lib.bc_model_spec_source(self._h, buf, int(n))
+        return buf.value.decode()
+
+    def spec_hash(self) -> int:
+        return int(L.lib().bc_model_spec_hash(self._h))
+
+    def spec_ffma(self) -> int:
+        """FFMA instructions the generated kernel executes per query (exact zeros are skipped)."""
+        for line in self.spec_source().splitlines()[:4]:
+            if "BC_SPEC_FFMA=" in line:
+                return int(line.split("BC_SPEC_FFMA=")[1].split()[0])
+        raise L.BayesCardError("generated source has no BC_SPEC_FFMA header")
+
+    # ------------------------------------------------------------------ geometry
+    def desc_stride(self, fmt: int) -> int:
+        s = int(L.lib().bc_model_desc_stride(self._h, fmt))
+        if s <= 0:
+            raise L.BayesCardError(f"unknown descriptor format {fmt}")
+        return s
+
+    # ------------------------------------------------------------------ launches
+    def run_device(self, desc_ptr: int, n: int, fmt: int, out_ptr: int, mask_ptr: int = 0,
+                   kernel: int = L.KERNEL_AUTO, stream: int = 0) -> None:
+        """One stream-ordered launch on DEVICE buffers (raw addresses)."""
+        L.check(L.lib().bc_query_batch(self._h, desc_ptr, n, fmt, mask_ptr or None, out_ptr, kernel, stream or None))
+
+    def run_host(self, desc: np.ndarray, fmt: int, mask: Optional[np.ndarray] = None,
+                 kernel: int = L.KERNEL_AUTO, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Host buffers in, host fp32 probabilities out (H2D / kernel / D2H pipelined in the library)."""
+        stride = self.desc_stride(fmt)
+        desc = np.ascontiguousarray(desc)
+        n = desc.nbytes // stride
+        if desc.nbytes != n * stride:
+            raise ValueError(f"descriptor buffer of {desc.nbytes} B is not a multiple of the row stride {stride}")
+        if mask is not None:
+            mask = np.ascontiguousarray(mask, dtype=np.uint32)
+            if mask.size != n * self.mask_words:
+                raise ValueError("fan-out mask has the wrong size")
+        if out is None:
+            out = np.empty(n, dtype=np.float32)
+        L.check(L.lib().bc_query_batch_host(self._h, desc.ctypes.data, n, fmt,
+                                            mask.ctypes.data if mask is not None else None, out.ctypes.data, kernel))
+        return out
+
+    def gen_range_queries_device(self, seed: int, first: int, n: int, kmin: int, kmax: int, desc_ptr: int,
+                                 stream: int = 0) -> None:
+        L.check(L.lib().bc_gen_range_queries(self._h, seed, first, n, kmin, kmax, desc_ptr, stream or None))
+
+    def gen_range_queries_host(self, seed: int, first: int, n: int, kmin: int, kmax: int) -> np.ndarray:
+        card = np.ascontiguousarray(self.tm.card, dtype=np.int32)
+        stride = self.desc_stride(L.DESC_RANGE_U8)
+        out = np.zeros((n, stride), dtype=np.uint8)
+        L.check(L.lib().bc_gen_range_queries_host(self.n_nodes, card.ctypes.data, seed, first, n, kmin, kmax,
+                                                  out.ctypes.data))
+        return out
+
+
+def gen_range_queries_host(tm: TreeModel, seed: int, first: int, n: int, kmin: int, kmax: int) -> np.ndarray:
+    """Host twin of the on-device generator (no GPU needed)."""
+    card = np.ascontiguousarray(tm.card, dtype=np.int32)
+    stride = -(-2 * tm.n_nodes // 4) * 4
+    out = np.zeros((n, stride), dtype=np.uint8)
+    L.check(L.lib().bc_gen_range_queries_host(tm.n_nodes, card.ctypes.data, seed, first, n, kmin, kmax,
+                                              out.ctypes.data))
+    return out
+
+
+def measure_fp32_peak(device: int = 0):
+    t, c = C.c_double(), C.c_double()
+    L.check(L.lib().bc_measure_fp32_peak(device, C.byref(t), C.byref(c)))
+    return t.value, c.value
+
+
+def launch_count() -> int:
+    return int(L.lib().bc_launch_count())
+
+
+class ShardedModel:
+    """The model replicated on several GPUs of one process; batches are split contiguously."""
+
+    def __init__(self, tm: TreeModel, devices: Sequence[int], specialize: bool = True):
+        self.tm = tm
+        self.replicas: List[DeviceModel] = [DeviceModel(tm, d, specialize=specialize) for d in devices]
+
+    @staticmethod
+    def split(n: int, parts: int):
+        """Equal contiguous ranges, remainder to the last."""
+        base = n // parts
+        bounds = [i * base for i in range(parts)] + [n]
+        return [(bounds[i], bounds[i + 1]) for i in range(parts)]
+
+    def run_host(self, desc: np.ndarray, fmt: int, mask: Optional[np.ndarray] = None,
+                 kernel: int = L.KERNEL_AUTO) -> np.ndarray:
+        r0 = self.replicas[0]
+        stride = r0.desc_stride(fmt)
+        desc = np.ascontiguousarray(desc).reshape(-1)
+        n = desc.nbytes // stride
+        rows = desc.view(np.uint8).reshape(n, stride)
+        out = np.empty(n, dtype=np.float32)
+        errs: List[BaseException] = []
+
+        def work(rep: DeviceModel, a: int, b: int):
+            try:
+                if b > a:
+                    rep.run_host(rows[a:b], fmt, None if mask is None else mask.reshape(n, -1)[a:b], kernel,
+                                 out=out[a:b])
+            except BaseException as e:  # noqa: BLE001
+                errs.append(e)
+
+        threads = [threading.Thread(target=work, args=(rep, a, b))
+                   for rep, (a, b) in zip(self.replicas, self.split(n, len(self.replicas)))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errs:
+            raise errs[0]
+        return out
+
+    def close(self):
+        for r in self.replicas:
+            r.close()

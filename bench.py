@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""bench.py -- queries/sec of exact tree inference (BASELINE.json metric) on N B200s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch of synthetic range-predicate queries:
+BASELINE.json configs[1], "Census Chow-Liu BN, batch of 1M synthetic multi-column range queries"
+(seeded counter-based generator, k ~ U{1..14} constrained columns).  With N > 1
+every rank runs the same per-GPU batch on its own replica of the CPT arena (weak scaling; the path
+has no exchange step, so no collective runs inside the timed region -- NCCL is used for the barrier
+and the max-over-ranks reduction only).
+
+  value      whole-job q/s, descriptors already resident in HBM, CUDA events around K steps
+  e2e        same metric through the host-buffer C-ABI call (bc_query_batch_host): pinned host
+             descriptors -> H2D -> kernel -> D2H of the fp32 results, all inside the timed region
+  roofline   dominant kernel vs the FP32 FFMA peak measured in this same run (the kernel keeps the
+             CPTs in the instruction stream, so HBM is not its bound; the HBM view is reported too)
+  cpu_baseline  the oracle port of the reference algorithm (numpy fp64, per query, as the reference
+             loops) timed on this host on a bounded sample -- a reported baseline, not the target
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "queries/sec exact tree inference"
+UNIT = "queries/s"
+KMIN, KMAX = 1, 14
+SEED = 0
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="census")
+    ap.add_argument("--batch", type=int, default=1_000_000)
+    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "spec"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    return ap.parse_args()
+
+
+def load_tree(name):
+    from bayescard_b200.loader import TreeModel
+
+    return TreeModel.load(os.path.join(ROOT, "tests", "golden", "models", name + ".npz"))
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+# ------------------------------------------------------------------------------------ oracle legs
+def queries_as_dicts(tm, desc):
+    """RANGE_U8 rows -> the (bins, n_distinct) dicts VariableEliminationJIT.query takes."""
+    from bayescard_b200.decode import unpack_ranges
+
+    lo, hi = unpack_ranges(tm, desc)
+    out = []
+    for i in range(lo.shape[0]):
+        q = {}
+        for v in range(tm.n_nodes):
+            if lo[i, v] > 0 or hi[i, v] < tm.card[v] - 1:
+                q[tm.infer_names[v]] = list(range(int(lo[i, v]), int(hi[i, v]) + 1))
+        out.append(q)
+    return out
+
+
+def _oracle_chunk(args):
+    name, first, n = args
+    from bayescard_b200.engine import gen_range_queries_host
+    from oracle import bayescard_oracle as O
+
+    tm = load_tree(name)
+    qs = queries_as_dicts(tm, gen_range_queries_host(tm, SEED, first, n, KMIN, KMAX))
+    t = time.perf_counter()
+    for q in qs:
+        O.ve_query(tm, q, {k: np.ones(len(b)) for k, b in q.items()})
+    return time.perf_counter() - t
+
+
+def cpu_baseline_single(tm, name, seconds):
+    """Oracle port, one core, bounded sample of the bench workload."""
+    from bayescard_b200.engine import gen_range_queries_host
+    from oracle import bayescard_oracle as O
+
+    probe = 500
+    qs = queries_as_dicts(tm, gen_range_queries_host(tm, SEED, 0, probe, KMIN, KMAX))
+    t = time.perf_counter()
+    for q in qs:
+        O.ve_query(tm, q, {k: np.ones(len(b)) for k, b in q.items()})
+    rate = probe / (time.perf_counter() - t)
+    n = int(max(probe, min(rate * seconds, 200_000)))
+    qs = queries_as_dicts(tm, gen_range_queries_host(tm, SEED, 0, n, KMIN, KMAX))
+    t = time.perf_counter()
+    for q in qs:
+        O.ve_query(tm, q, {k: np.ones(len(b)) for k, b in q.items()})
+    dt = time.perf_counter() - t
+    return {"value": n / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"first {n} queries of the {name} bench batch, oracle/bayescard_oracle.py ve_query "
+                      f"(numpy fp64 restatement of VariableEliminationJIT.query, one Python process)"}
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU algorithm (oracle port) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+
+    cores = os.cpu_count() or 1
+    per_core = 1500
+    chunks_per_step = cores
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        def step(k):
+            jobs = [(args.model, (k * chunks_per_step + c) * per_core, per_core) for c in range(chunks_per_step)]
+            t = time.perf_counter()
+            pool.map(_oracle_chunk, jobs)
+            return time.perf_counter() - t
+
+        for k in range(args.warmup):
+            step(k)
+        t_total = sum(step(args.warmup + k) for k in range(args.steps))
+    nq = args.steps * chunks_per_step * per_core
+    value = nq / t_total
+    sample = (f"{chunks_per_step * per_core} queries of the {args.model} bench workload per step, "
+              f"oracle port (numpy fp64) in {cores} worker processes")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.model} Chow-Liu BN, synthetic range queries k~U{{{KMIN}..{KMAX}}}",
+                       "queries_per_step": chunks_per_step * per_core},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for t, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                smax = float(f[2])
+                if t0 - 0.05 <= t <= t1 + 0.05:
+                    sm.append(float(f[1]))
+                    for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                         f[4:8]):
+                        if val.lower().startswith("active"):
+                            reasons.add(name)
+            except ValueError:
+                continue
+        if not sm:  # timed region shorter than the sampling period: use every sample we have
+            for t, line in self.rows:
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    sm.append(float(f[1]))
+                except (ValueError, IndexError):
+                    pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+
+    from bayescard_b200 import _lib as L
+    from bayescard_b200.decode import unpack_ranges
+    from bayescard_b200.engine import DeviceModel, launch_count, measure_fp32_peak
+    from bayescard_b200.model import Bayescard_BN
+    from oracle import bayescard_oracle as O  # checker + cpu_baseline leg only
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: bayescard_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = f"cuda:{local}"
+    kernel = {"auto": L.KERNEL_AUTO, "generic": L.KERNEL_GENERIC, "spec": L.KERNEL_SPEC}[args.kernel]
+
+    tm = load_tree(args.model)
+    dm = DeviceModel(tm, device=local, specialize=True)
+    if kernel != L.KERNEL_GENERIC and not dm.has_spec:
+        raise SystemExit("specialised kernel unavailable: " + str(dm.spec_error))
+    B = args.batch
+    stride = dm.desc_stride(L.DESC_RANGE_U8)
+    NBUF = 4  # rotate over 4 resident batches: the working set (4 x B x stride) is far larger than L2
+    stream = torch.cuda.current_stream()
+    st = stream.cuda_stream
+    descs = [torch.empty((B, stride), dtype=torch.uint8, device=dev) for _ in range(NBUF)]
+    out = torch.empty(B, dtype=torch.float32, device=dev)
+    for b, d in enumerate(descs):
+        dm.gen_range_queries_device(SEED, (rank * NBUF + b) * B, B, KMIN, KMAX, d.data_ptr(), st)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(k):
+        dm.run_device(descs[k % NBUF].data_ptr(), B, L.DESC_RANGE_U8, out.data_ptr(), kernel=kernel, stream=st)
+
+    # ---- FP32 peak of this device, measured before the timed region ---------------------------
+    fp32_peak, _ = measure_fp32_peak(local)
+
+    # ---- device-resident throughput --------------------------------------------------------
+    for k in range(max(args.warmup, 3)):
+        step(k)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    time.sleep(0.25 if sampler else 0)
+    launches0 = launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for k in range(args.steps):
+        step(k)
+    e1.record(stream)
+    barrier()
+    t1 = time.perf_counter()
+    launches = launch_count() - launches0
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the host-buffer C-ABI call ---------------------------------------------
+    h_desc = torch.empty((B, stride), dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(B, dtype=torch.float32).pin_memory()
+    h_desc.copy_(descs[0])
+    hd, ho = h_desc.numpy(), h_out.numpy()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        dm.run_host(hd, L.DESC_RANGE_U8, None, kernel, out=ho)
+    barrier()
+    te = time.perf_counter()
+    for _ in range(e2e_steps):
+        dm.run_host(hd, L.DESC_RANGE_U8, None, kernel, out=ho)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - te
+    if dist is not None:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * B * e2e_steps / e2e_s
+    clocks = sampler.stop(t0, time.perf_counter()) if sampler else None
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- parity of this very batch against the fp64 oracle (sub-sample) ------------------------
+    rng = np.random.default_rng(0)
+    idx = np.sort(rng.choice(B, size=min(B, 10000), replace=False))
+    dm.run_device(descs[0].data_ptr(), B, L.DESC_RANGE_U8, out.data_ptr(), kernel=kernel, stream=st)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()[idx].astype(np.float64)
+    lo, hi = unpack_ranges(tm, descs[0].cpu().numpy()[idx])
+    ref = O.dense_tree(tm, O.range_weights(tm, lo, hi))
+    rel_err = float(np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300)))
+
+    # ---- p50 latency of the scalar drop-in call (B = 1, decode included) ----------------------
+    bn = Bayescard_BN(tm, device=local, infer_algo="exact-jit")
+    bn.init_inference_method()
+    qd = queries_as_dicts(tm, dm.gen_range_queries_host(SEED, 0, 300, KMIN, KMAX))
+    raw = []
+    inv = {n: {b: v for v, b in tm.encoding[n].items()} for n in tm.infer_names if tm.encoding.get(n)}
+    for q in qd:
+        raw.append({k: [inv[k][b] for b in bins] for k, bins in q.items()})
+    lat = []
+    for q in raw:
+        if not q:
+            continue
+        tq = time.perf_counter()
+        bn.query(q)
+        lat.append(time.perf_counter() - tq)
+    p50_us = float(np.median(lat[20:]) * 1e6)
+    bn.close()
+
+    # ---- roofline of the dominant kernel ------------------------------------------------------
+    peaks, peak_src = measured_peaks()
+    spec = kernel != L.KERNEL_GENERIC
+    flop_q = 2 * dm.spec_ffma() if spec else dm.flops_dense
+    kernel_s = ms * 1e-3 / args.steps
+    achieved_tf = flop_q * B / kernel_s / 1e12
+    bytes_q = stride + 4
+    roof = {"bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
+            "frac": achieved_tf / fp32_peak if fp32_peak else None, "traffic": None,
+            "kernel": "bc_spec_range8" if spec else "k1_kernel",
+            "flop_per_query": flop_q, "flop_per_query_dense": dm.flops_dense,
+            "peak_source": "FFMA micro-benchmark (bc_measure_fp32_peak) in this run",
+            "note": "exact zeros of the CPTs emit no FFMA; achieved counts executed FFMAs only"}
+    roof_hbm = {"bound": "hbm", "achieved": bytes_q * B / kernel_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": bytes_q * B / kernel_s / 1e9 / peaks["hbm_gbs"], "bytes_per_query": bytes_q,
+                "peak_source": f"MEASURED_PEAKS.json ({peak_src})"}
+
+    cpu = cpu_baseline_single(tm, args.model, args.cpu_seconds)
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.model} Chow-Liu BN ({tm.n_nodes} columns), {B} synthetic range queries per "
+                                   f"GPU per step, k~U{{{KMIN}..{KMAX}}} constrained columns, seed {SEED}",
+                       "descriptor": "RANGE_U8", "bytes_per_query": bytes_q,
+                       "l2": f"inputs rotate over {NBUF} resident batches = {NBUF * B * stride / 1e6:.0f} MB > 126 MB L2",
+                       "kernel": roof["kernel"], "parallelism": f"replica x{world}, batch sharded, no collective"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * stride, "d2h_bytes_per_step": B * 4,
+                    "steps": e2e_steps, "api": "bc_query_batch_host (pinned host buffers)"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_hbm": roof_hbm,
+            "cpu_baseline": cpu, "rel_err_max_vs_fp64_oracle": rel_err, "p50_latency_us_scalar_query": p50_us,
+            "fp32_peak_tflops_measured": fp32_peak}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.gpus > 1 and "RANK" not in os.environ:
+        # launched by hand: re-exec under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+        os.execv(sys.executable, cmd)
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,150 @@
+/*
+ * bayescard_b200 -- C ABI of the B200-native exact-inference hot path of wuziniu/BayesCard.
+ *
+ * This is the drop-in boundary.  The reference has no FFI: its seam for this
+ * path is the Python object assigned to ``Bayescard_BN.infer_machine`` (reference
+ * Models/Bayescard_BN.py:141), whose two methods are
+ *     VariableEliminationJIT.query(query, n_distinct)                 Pgmpy/inference/ExactInference.py:112-197
+ *     VariableEliminationJIT.expectation(query, fanout_attrs, n_distinct)            ...:199-287
+ * and whose constructor consumes the topologically aligned CPD list
+ *     VariableEliminationJIT.__init__(model, cpds, topological_order, ...)           ...:25-40
+ *     Bayescard_BN.align_cpds_in_topological()                        Models/Bayescard_BN.py:340-358
+ * Each entry point below names the reference interface it replaces.  All pointers are plain
+ * host or device addresses; no torch / numpy / C++ types cross this boundary.  The host side above
+ * it (bayescard_b200/*.py) binds these symbols with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every function returning int returns BC_OK (0) on success, a negative BC_E* code otherwise;
+ *     bc_last_error() then holds a human-readable message (thread local).
+ *   - there is NO CPU fallback: if no CUDA device / kernel image is usable the call fails.
+ *   - a bc_model is immutable after creation; bc_query_batch* are stream ordered and may be called
+ *     concurrently on different models / devices (one host thread per GPU).
+ *   - node indices are TOPOLOGICAL (parents before children, node 0 = root), the order of
+ *     align_cpds_in_topological() restricted to the root's component.
+ */
+#ifndef BAYESCARD_B200_H
+#define BAYESCARD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define BC_API __attribute__((visibility("default")))
+#else
+#define BC_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BC_OK 0
+#define BC_EINVAL (-1)   /* bad argument                                   */
+#define BC_ECUDA (-2)    /* CUDA runtime / driver error                    */
+#define BC_ENOMEM (-3)   /* host or device allocation failed               */
+#define BC_ECOMPILE (-4) /* NVRTC unavailable or specialised build failed  */
+#define BC_ELIMIT (-5)   /* model exceeds what the selected kernel supports */
+
+/* ---- query descriptor formats (one row per query, nodes in topological order) ------------------
+ * RANGE_U8   2*n_nodes bytes, row stride = round_up(2*n_nodes, 4):  lo_0,hi_0,lo_1,hi_1,...
+ *            w_v[c] = 1 for lo_v <= c <= hi_v, else 0 (an unconstrained column is [0, card-1];
+ *            lo > hi selects nothing).  Requires card <= 256.  This is the compact form of a
+ *            conjunction of range / equality predicates over the discretised bins, i.e. the output
+ *            of Bayescard_BN.query_decoding (Models/Bayescard_BN.py:279-325) when every predicate
+ *            is a contiguous bin interval with n_distinct weights 1.
+ * RANGE_U16  same with uint16 bounds (card <= 65536), row stride 4*n_nodes bytes.
+ * DENSE_F32  one fp32 weight per (node, state): node v occupies round_up(card_v,4) floats starting
+ *            at bc_model_dense_offset(v); row stride = bc_model_dense_width() floats.  Carries the
+ *            general output of query_decoding (IN lists, fractional n_distinct weights).
+ * For every format an optional fan-out bitmask (mask_words = ceil(n_nodes/32) uint32 per query,
+ * bit v set = multiply w_v by fanouts[v]) implements expectation(); a predicate on a fan-out
+ * column wins (ExactInference.py:209,:238), so the host clears the bit for predicated columns.
+ */
+#define BC_DESC_RANGE_U8 0
+#define BC_DESC_RANGE_U16 1
+#define BC_DESC_DENSE_F32 2
+
+/* ---- kernel selection ------------------------------------------------------------------------- */
+#define BC_KERNEL_AUTO 0     /* specialised kernel if the model has one, else generic        */
+#define BC_KERNEL_GENERIC 1  /* K1: warp per query, CPT arena staged in shared memory by TMA  */
+#define BC_KERNEL_SPEC 2     /* K-spec: per-model straight-line kernel, thread per query      */
+#define BC_KERNEL_GEMM 3     /* K2: per-edge batched GEMM for large domains                   */
+
+typedef struct bc_model bc_model;
+
+/* Replaces VariableEliminationJIT.__init__ + align_cpds_in_topological (ExactInference.py:25-40,
+ * Bayescard_BN.py:340-358): uploads the topologically ordered CPTs as ONE 16 B-aligned fp32 arena.
+ *   parent[v]   topological index of the parent, -1 for v = 0 (the root); parent[v] < v
+ *   card[v]     number of states
+ *   cpt_off[v]  offset (in floats) of T_v in cpt_arena; T_v[c][p] at cpt_off[v] + c*stride[v] + p
+ *   stride[v]   row stride in floats (>= card[parent[v]], multiple of 4); root: one row of card[0]
+ *   fan_off[v]  offset (floats) of fanouts[v] (card[v] floats) in fan_arena, or -1
+ * Host pointers; the arrays are copied.  device = CUDA ordinal. */
+BC_API int bc_model_create(int device, int n_nodes, const int32_t* parent, const int32_t* card,
+                    const int64_t* cpt_off, const int32_t* stride, const float* cpt_arena,
+                    size_t arena_floats, const int64_t* fan_off, const float* fan_arena,
+                    size_t fan_floats, bc_model** out);
+BC_API void bc_model_destroy(bc_model* m);
+
+BC_API int bc_model_n_nodes(const bc_model* m);
+BC_API int bc_model_device(const bc_model* m);
+/* DENSE_F32 row geometry */
+BC_API int64_t bc_model_dense_width(const bc_model* m);
+BC_API int64_t bc_model_dense_offset(const bc_model* m, int node);
+/* row stride in BYTES of a descriptor format for this model */
+BC_API int64_t bc_model_desc_stride(const bc_model* m, int desc_format);
+/* ALGORITHMIC flop per query of the dense tree: 2 * sum_{v != root} card(v)*card(parent(v)) */
+BC_API int64_t bc_model_flops_dense(const bc_model* m);
+
+/* Build (or load from the on-disk cache) the per-model specialised kernel (K-spec): straight-line
+ * sm_100a code for this tree with the CPT entries as FFMA immediates, compiled with NVRTC.
+ * cache_dir may be NULL (no cache).  Returns BC_ECOMPILE if NVRTC is missing or the build fails;
+ * the generic kernel keeps working. */
+BC_API int bc_model_specialize(bc_model* m, const char* cache_dir);
+BC_API int bc_model_has_spec(const bc_model* m);
+/* Write the generated CUDA source of the specialised kernel (host only, no GPU needed; used by the
+ * ahead-of-time build and by tests).  Returns the number of bytes needed including the NUL. */
+BC_API int64_t bc_model_spec_source(const bc_model* m, char* buf, size_t buf_bytes);
+/* Hash that names the cache entry "<hash>.cubin" for this model + code generator version. */
+BC_API uint64_t bc_model_spec_hash(const bc_model* m);
+/* Attach an already compiled cubin (ahead-of-time build). */
+BC_API int bc_model_load_cubin(bc_model* m, const void* image, size_t bytes);
+
+/* Replaces the per-query loop `for q: infer_machine.query(q, nd)` / `.expectation(q, fan, nd)`
+ * (Testing/BN_testing.py:21-46, Models/BN_ensemble_model.py:228-252) with ONE launch over a batch.
+ * DEVICE pointers.  desc: n_queries rows in desc_format; fanout_mask: NULL or n_queries*mask_words
+ * uint32; out_prob: n_queries fp32 = sum_x prod_v w_v[x_v] T_v[x_v, x_pa(v)].
+ * stream: a cudaStream_t (NULL = legacy default stream). */
+BC_API int bc_query_batch(bc_model* m, const void* desc, size_t n_queries, int desc_format,
+                   const uint32_t* fanout_mask, float* out_prob, int kernel, void* stream);
+
+/* Same with HOST buffers: chunks the batch, overlaps H2D / kernel / D2H on internal streams with
+ * pinned staging buffers, returns when out_prob (host) is complete.  This is the end-to-end path
+ * a caller of the reference-facing Python API goes through. */
+BC_API int bc_query_batch_host(bc_model* m, const void* desc, size_t n_queries, int desc_format,
+                        const uint32_t* fanout_mask, float* out_prob, int kernel);
+
+/* Synthetic workload generator (BASELINE.json configs 2 and 5): writes
+ * RANGE_U8 descriptors for query indices [first, first+n) from a counter-based RNG keyed by
+ * (seed, query index), so any query can be regenerated on the host for oracle spot checks
+ * (bc_gen_range_queries_host is the bit-identical host twin).  Per query k ~ U{kmin..kmax}
+ * distinct columns are constrained, each with lo ~ U{0..card-1}, hi ~ U{lo..card-1}. */
+BC_API int bc_gen_range_queries(bc_model* m, uint64_t seed, uint64_t first, size_t n, int kmin, int kmax,
+                         void* desc_dev, void* stream);
+BC_API int bc_gen_range_queries_host(int n_nodes, const int32_t* card, uint64_t seed, uint64_t first,
+                              size_t n, int kmin, int kmax, void* desc_host);
+
+/* Measured FP32 FFMA peak of the device (TFLOP/s), the roofline denominator SURVEY.md section 8d
+ * asks to measure in the same run rather than quote. */
+BC_API int bc_measure_fp32_peak(int device, double* tflops, double* sm_clock_mhz);
+
+/* Number of kernel launches issued by this library on behalf of the calling process. */
+BC_API uint64_t bc_launch_count(void);
+
+BC_API const char* bc_last_error(void);
+BC_API const char* bc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BAYESCARD_B200_H */

@@ -1,0 +1,290 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the reference's golden outputs and
+against the fp64 oracle.  Tolerance: 1e-5 relative (BASELINE.json north_star), fp32 kernels vs fp64."""
+import copy
+
+import numpy as np
+import pytest
+
+import golden_util as G
+from bayescard_b200 import _lib as L
+from bayescard_b200.decode import PredicateCompiler, unpack_ranges
+from bayescard_b200.engine import DeviceModel, ShardedModel, launch_count
+from bayescard_b200.ensemble import BN_ensemble
+from bayescard_b200.model import Bayescard_BN
+from bayescard_b200.sql_front import parse_query_single_table
+from oracle import bayescard_oracle as O
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+KERNELS = [L.KERNEL_GENERIC, L.KERNEL_SPEC]
+_dm = {}
+
+
+def dev_model(name) -> DeviceModel:
+    if name not in _dm:
+        _dm[name] = DeviceModel(G.model(name), device=0, specialize=True)
+        assert _dm[name].has_spec, _dm[name].spec_error
+    return _dm[name]
+
+
+def rel_err(got, ref):
+    got, ref = np.asarray(got, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    return np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300)
+
+
+def assert_close(got, ref, what=""):
+    ref = np.asarray(ref, dtype=np.float64)
+    err = rel_err(got, ref)
+    err[(ref == 0) & (np.asarray(got) == 0)] = 0
+    assert err.max() <= RTOL, (what, float(err.max()), int(err.argmax()))
+
+
+# ------------------------------------------------------------------------------------ kernels
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("name", G.MODEL_NAMES)
+def test_infer_cases_both_kernels(name, kernel):
+    """Decoded (bins, fractional weights, fan-out) cases: range + dense descriptors + fan-out mask."""
+    m, dm = G.model(name), dev_model(name)
+    pc = PredicateCompiler(m)
+    cases = [r for r in G.load("infer_cases.json.gz")[name] if "error" not in r]
+    decoded = [({k: list(v) for k, v in r["bins"].items()}, {k: np.asarray(v) for k, v in r["weights"].items()})
+               for r in cases]
+    ref = np.asarray([np.asarray(r["p"]["value"]).reshape(-1)[0] for r in cases])
+    for force_dense in (False, True):
+        r_idx, r_desc, d_idx, d_desc, mask = pc.pack(decoded, [r["fanout"] for r in cases], force_dense=force_dense)
+        got = np.zeros(len(cases))
+        before = launch_count()
+        if len(r_idx):
+            got[r_idx] = dm.run_host(r_desc, L.DESC_RANGE_U8, mask[r_idx], kernel)
+        if len(d_idx):
+            got[d_idx] = dm.run_host(d_desc, L.DESC_DENSE_F32, mask[d_idx], kernel)
+        assert launch_count() > before, "no kernel was launched"
+        assert_close(got, ref, (name, kernel, force_dense))
+
+
+@pytest.mark.parametrize("name", ["dmv", "census", "imdb1"])
+def test_synthetic_batch_generic_vs_spec_vs_oracle(name):
+    """Config 2/5 generator: device == host twin bit for bit; both kernels vs the fp64 dense oracle."""
+    import torch
+
+    m, dm = G.model(name), dev_model(name)
+    n = 20000 + 37  # ragged: not a multiple of the warp / CTA size
+    kmax = min(m.n_nodes, 14)
+    stride = dm.desc_stride(L.DESC_RANGE_U8)
+    desc = torch.zeros((n, stride), dtype=torch.uint8, device="cuda:0")
+    out = torch.empty(n, dtype=torch.float32, device="cuda:0")
+    st = torch.cuda.current_stream().cuda_stream
+    dm.gen_range_queries_device(11, 5, n, 1, kmax, desc.data_ptr(), st)
+    torch.cuda.synchronize()
+    host = dm.gen_range_queries_host(11, 5, n, 1, kmax)
+    assert np.array_equal(desc.cpu().numpy(), host)
+    lo, hi = unpack_ranges(m, host)
+    ref = O.dense_tree(m, O.range_weights(m, lo, hi))
+    res = {}
+    for kernel in KERNELS:
+        out.zero_()
+        dm.run_device(desc.data_ptr(), n, L.DESC_RANGE_U8, out.data_ptr(), kernel=kernel, stream=st)
+        torch.cuda.synchronize()
+        res[kernel] = out.cpu().numpy().astype(np.float64)
+        assert_close(res[kernel], ref, (name, kernel))
+    # host-buffer pipeline == device-buffer launch, bit for bit
+    via_host = dm.run_host(host, L.DESC_RANGE_U8, None, L.KERNEL_SPEC)
+    assert np.array_equal(via_host.astype(np.float64), res[L.KERNEL_SPEC])
+
+
+def test_size_independent_properties_full_batch():
+    """1M Census queries (BASELINE.json config 2): properties that need no oracle."""
+    import torch
+
+    m, dm = G.model("census"), dev_model("census")
+    n = 1_000_000
+    stride = dm.desc_stride(L.DESC_RANGE_U8)
+    desc = torch.zeros((n, stride), dtype=torch.uint8, device="cuda:0")
+    out = torch.empty(n, dtype=torch.float32, device="cuda:0")
+    st = torch.cuda.current_stream().cuda_stream
+    dm.gen_range_queries_device(0, 0, n, 1, 14, desc.data_ptr(), st)
+    dm.run_device(desc.data_ptr(), n, L.DESC_RANGE_U8, out.data_ptr(), stream=st)
+    torch.cuda.synchronize()
+    p = out.cpu().numpy().astype(np.float64)
+    assert np.all(p >= 0) and np.all(p <= 1 + 1e-5)
+    # (a) permutation: results follow their queries bit for bit
+    perm = torch.randperm(n, device="cuda:0", generator=torch.Generator(device="cuda:0").manual_seed(1))
+    desc2 = desc[perm].contiguous()
+    out2 = torch.empty_like(out)
+    dm.run_device(desc2.data_ptr(), n, L.DESC_RANGE_U8, out2.data_ptr(), stream=st)
+    torch.cuda.synchronize()
+    assert torch.equal(out2, out[perm])
+    # (b) additivity: splitting one column's range [lo,hi] into [lo,mid] + [mid+1,hi] splits the mass
+    d = desc.cpu().numpy()
+    lo, hi = unpack_ranges(m, d)
+    v = 6  # a column with 18 states
+    wide = np.nonzero(hi[:, v] > lo[:, v])[0][:200000]
+    mid = (lo[wide, v] + hi[wide, v]) // 2
+    left, right = d[wide].copy(), d[wide].copy()
+    left[:, 2 * v + 1] = mid
+    right[:, 2 * v] = mid + 1
+    pl = dm.run_host(left, L.DESC_RANGE_U8).astype(np.float64)
+    pr = dm.run_host(right, L.DESC_RANGE_U8).astype(np.float64)
+    assert np.allclose(pl + pr, p[wide], rtol=2e-6, atol=1e-12)
+    # (c) oracle on a seeded subsample of the full batch
+    idx = np.random.default_rng(0).choice(n, 10000, replace=False)
+    ref = O.dense_tree(m, O.range_weights(m, lo[idx], hi[idx]))
+    assert_close(p[idx], ref, "census 1M subsample")
+
+
+def test_edge_cases():
+    m, dm = G.model("dmv"), dev_model("dmv")
+    stride = dm.desc_stride(L.DESC_RANGE_U8)
+    full = np.zeros((1, stride), dtype=np.uint8)
+    full[0, 1:2 * m.n_nodes:2] = m.card - 1
+    for kernel in KERNELS:
+        # empty batch
+        assert dm.run_host(np.zeros((0, stride), dtype=np.uint8), L.DESC_RANGE_U8, None, kernel).shape == (0,)
+        # unconstrained query: total mass 1
+        assert abs(dm.run_host(full, L.DESC_RANGE_U8, None, kernel)[0] - 1.0) < 1e-5
+        # lo > hi selects nothing
+        none = full.copy()
+        none[0, 2 * 4], none[0, 2 * 4 + 1] = 5, 2
+        assert dm.run_host(none, L.DESC_RANGE_U8, None, kernel)[0] == 0.0
+        # hi beyond the domain is clamped
+        over = full.copy()
+        over[0, 1:2 * m.n_nodes:2] = 255
+        assert abs(dm.run_host(over, L.DESC_RANGE_U8, None, kernel)[0] - 1.0) < 1e-5
+        # single state of every column = product along the tree
+        one = full.copy()
+        one[0, 0:2 * m.n_nodes:2] = 0
+        one[0, 1:2 * m.n_nodes:2] = 0
+        ref = O.dense_tree(m, O.range_weights(m, np.zeros((1, m.n_nodes), int), np.zeros((1, m.n_nodes), int)))[0]
+        assert_close(dm.run_host(one, L.DESC_RANGE_U8, None, kernel), [ref], "all-first-state")
+    with pytest.raises(L.BayesCardError):
+        dm.run_host(full, 99)
+
+
+def test_replicas_shard_a_batch():
+    """ShardedModel splits contiguously across replicas (two replicas on cuda:0 when only one GPU)."""
+    import torch
+
+    m = G.model("dmv")
+    devs = [0, 1] if torch.cuda.device_count() > 1 else [0, 0]
+    sm = ShardedModel(m, devs)
+    desc = sm.replicas[0].gen_range_queries_host(3, 0, 50001, 1, 6)
+    got = sm.run_host(desc, L.DESC_RANGE_U8)
+    one = dev_model("dmv").run_host(desc, L.DESC_RANGE_U8)
+    assert np.array_equal(got, one)
+    sm.close()
+
+
+# ------------------------------------------------------------------------------------ drop-in API
+@pytest.mark.parametrize("name", ["dmv", "census"])
+def test_workload_end_to_end_through_dropin_api(name):
+    """BASELINE.json config 1: shipped model + real SQL through Bayescard_BN.query, as Testing/BN_testing.py."""
+    import os
+
+    bn = Bayescard_BN.load(os.path.join(G.GOLD, "models", name + ".npz"), device=0)
+    bn.infer_algo = "exact-jit"
+    bn.init_inference_method()
+    rows = G.load(f"{name}_workload.json.gz")["queries"]
+    qerrs, parsed_all = [], []
+    for r in rows:
+        parsed = parse_query_single_table(r["sql"], bn)
+        parsed_all.append(parsed)
+        card = bn.query(parsed)
+        ref, kind = r["card"]["value"], r["card"]["kind"]
+        if kind == "array":
+            assert isinstance(card, np.ndarray) and card.shape == (1,)
+        elif kind == "int":
+            assert isinstance(card, int) and card == ref
+            continue
+        else:
+            assert np.ndim(card) == 0
+        assert_close(np.asarray(card).reshape(-1), np.asarray(ref).reshape(-1), r["sql"][:60])
+        qerrs.append(O.q_error(float(np.asarray(card).reshape(-1)[0]), r["true"]))
+    pins = {"dmv": [1.0012, 1.0243, 1.0498, 1.3361, 7.6408],
+            "census": [1.0635, 1.4844, 2.0523, 15.6009, 227.5043]}[name]
+    assert np.allclose([np.percentile(qerrs, p) for p in (50, 90, 95, 99, 100)], pins, rtol=1e-4)
+    # the batch entry point gives the same numbers in one go
+    batch = bn.query_batch(parsed_all)
+    ref_all = np.asarray([np.asarray(r["card"]["value"]).reshape(-1)[0] for r in rows], dtype=np.float64)
+    assert_close(batch, ref_all, name + " batch")
+    bn.close()
+
+
+@pytest.mark.parametrize("i", range(5))
+def test_imdb_query_and_expectation_api(i):
+    import os
+
+    bn = Bayescard_BN.load(os.path.join(G.GOLD, "models", f"imdb{i}.npz"), device=0, infer_algo="exact-jit")
+    bn.init_inference_method()
+    for r in G.load("imdb_cases.json.gz")[f"imdb{i}"]:
+        q = G.unjson(r["query"])
+        if "error" in r:
+            with pytest.raises(Exception):
+                bn.expectation(copy.deepcopy(q), list(r["fanout"]), return_prob=True)
+            continue
+        p, nrows = bn.expectation(copy.deepcopy(q), list(r["fanout"]), return_prob=True)
+        assert nrows == r["nrows"]
+        ref, kind = r["p"]["value"], r["p"]["kind"]
+        if kind == "int":
+            assert isinstance(p, int) and p == ref
+            continue
+        if kind == "array":
+            assert isinstance(p, np.ndarray) and p.shape == (1,)
+        assert_close(np.asarray(p).reshape(-1), np.asarray(ref).reshape(-1), str(q)[:80])
+    bn.close()
+
+
+def test_quirks_through_api():
+    import os
+
+    bns = {}
+    for r in G.load("quirk_cases.json.gz")["cases"]:
+        name = r["model"]
+        if name not in bns:
+            bns[name] = Bayescard_BN.load(os.path.join(G.GOLD, "models", name + ".npz"), device=0, infer_algo="exact-jit")
+            bns[name].init_inference_method()
+        bn, q = bns[name], G.unjson(r["query"])
+        if "error" in r:
+            with pytest.raises(Exception):
+                bn.query(q)
+            continue
+        if r["kind"] == "decode":
+            continue
+        got = bn.query(q, return_prob=r["return_prob"]) if r["kind"] == "query" else \
+            bn.expectation(q, list(r["fanout"]), return_prob=r["return_prob"])
+        if r["return_prob"]:
+            assert got[1] == r["nrows"]
+            got = got[0]
+        ref, kind = r["result"]["value"], r["result"]["kind"]
+        if kind == "int":
+            assert isinstance(got, int) and got == ref, (q, got)
+        else:
+            if kind == "array":
+                assert isinstance(got, np.ndarray) and got.shape == (1,), (q, got)
+            assert_close(np.asarray(got).reshape(-1), np.asarray(ref).reshape(-1), str(q))
+    for bn in bns.values():
+        bn.close()
+
+
+def test_ensemble_cardinality():
+    import os
+
+    bns = {}
+    for i in range(5):
+        bns[i] = Bayescard_BN.load(os.path.join(G.GOLD, "models", f"imdb{i}.npz"), device=0, infer_algo="exact-jit")
+        bns[i].init_inference_method()
+    ens = BN_ensemble(None, bns)
+    good, parsed_good = [], []
+    for r in G.load("ensemble_cases.json.gz")["cases"]:
+        tq = G.unjson(r["table_query"])
+        if "error" in r:
+            with pytest.raises(Exception):
+                ens.cardinality(ens.parse_query_all([copy.deepcopy(tq)])[0])
+            continue
+        parsed = ens.parse_query_all([copy.deepcopy(tq)])[0]
+        assert len(parsed) - 1 == r["n_factors_kept"]
+        assert_close([ens.cardinality(parsed)], [r["card"]], "ensemble")
+        good.append(r["card"])
+        parsed_good.append(parsed)
+    assert_close(ens.cardinality_batch(parsed_good), good, "ensemble batch")
+    for bn in bns.values():
+        bn.close()

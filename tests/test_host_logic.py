@@ -1,0 +1,210 @@
+"""CPU tests of the host side: loader, SQL front end, predicate compiler, descriptor packing, the
+C-ABI library's exported symbols and its host-only entry points (no compute calls without a GPU)."""
+import copy
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import golden_util as G
+from bayescard_b200 import _lib as L
+from bayescard_b200.decode import PredicateCompiler, unpack_ranges
+from bayescard_b200.engine import DeviceModel, ShardedModel, gen_range_queries_host
+from bayescard_b200.loader import TreeModel, topological_order
+from bayescard_b200.sql_front import parse_query_single_table
+from oracle import bayescard_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _as_map(bins, wts):
+    w = np.asarray(wts, dtype=np.float64).reshape(-1)
+    if w.size == 1 and len(bins) > 1:
+        w = np.full(len(bins), w[0])
+    return {int(b): float(x) for b, x in zip(bins, w)}
+
+
+# ------------------------------------------------------------------------------------ loader
+def test_models_shapes_match_survey():
+    """node counts, CPT entries and algorithmic flop of the shipped models."""
+    expect = {"dmv": (10, 10882, 21756), "census": (68, 3335, 6654), "imdb0": (9, 20398, 40782),
+              "imdb1": (9, 30284, 60564), "imdb2": (9, 23402, 46800), "imdb3": (9, 30509, 61004),
+              "imdb4": (10, 28096, 56178)}
+    for name, (n, entries, flops) in expect.items():
+        m = G.model(name)
+        assert (m.n_nodes, m.n_cpt_entries, m.flops_dense) == (n, entries, flops)
+        assert m.parent[0] == -1 and all(0 <= m.parent[v] < v for v in range(1, n))
+        for v in range(1, n):
+            assert np.allclose(m.cpts[v].sum(axis=0), 1.0, atol=1e-9)
+        arena, off, stride = m.pack_arena()
+        assert arena.dtype == np.float32 and all(o % 4 == 0 for o in off) and all(s % 4 == 0 for s in stride)
+        for v in range(1, n):
+            t = arena[off[v]: off[v] + m.card[v] * stride[v]].reshape(m.card[v], stride[v])
+            assert np.array_equal(t[:, : m.cpts[v].shape[1]], m.cpts[v].astype(np.float32))
+
+
+def test_topological_order_rule():
+    # Models/Bayescard_BN.py:340-349: sweeps in index order, a column is placed as soon as its parent is
+    assert topological_order(((), (0,), (3,), (1,), (5,), (1,))) == [0, 1, 3, 5, 2, 4]
+    assert topological_order(((1,), ())) == [1, 0]
+    with pytest.raises(ValueError):
+        topological_order(((1,), (0,)))
+
+
+def test_pickle_loader_matches_flat_models():
+    """The restricted unpickler on the shipped pickles (only where the reference is mounted)."""
+    ref = "/root/reference/Benchmark"
+    if not os.path.isdir(ref):
+        pytest.skip("reference pickles not present on this machine")
+    from bayescard_b200.loader import load_pickle
+
+    for name, rel in {"dmv": "DMV/chow-liu_1.pkl", "imdb3": "IMDB/3_chow-liu_1.pkl"}.items():
+        a, b = load_pickle(os.path.join(ref, rel)), G.model(name)
+        assert a.infer_names == b.infer_names and a.nrows == b.nrows and type(a.nrows) is type(b.nrows)
+        assert all(np.array_equal(x, y) for x, y in zip(a.cpts, b.cpts))
+        assert a.encoding == b.encoding and a.mapping == b.mapping and a.n_in_bin == b.n_in_bin
+
+
+def test_restricted_unpickler_rejects_foreign_classes():
+    import pickle
+
+    from bayescard_b200.loader import load_pickle
+
+    blob = pickle.dumps(os.system)  # a global outside the allow list
+    with pytest.raises(pickle.UnpicklingError):
+        load_pickle(blob)
+
+
+# ------------------------------------------------------------------------------------ sql + decode
+@pytest.mark.parametrize("name", ["dmv", "census"])
+def test_sql_and_decode_match_reference(name):
+    m = G.model(name)
+    pc = PredicateCompiler(m)
+    for r in G.load(f"{name}_workload.json.gz")["queries"]:
+        parsed = parse_query_single_table(r["sql"], m)
+        ref = G.unjson(r["parsed"])
+        assert list(parsed) == list(ref)
+        for k in parsed:
+            assert (list(parsed[k]) == list(ref[k])) if isinstance(ref[k], list) else (parsed[k] == ref[k])
+        before = copy.deepcopy(parsed)
+        bins, wts = pc.decode(parsed)
+        assert parsed == before, "decode must not mutate its input"
+        if r["decoded"] is None:
+            assert bins is None
+            continue
+        for k, rb in r["decoded"]["bins"].items():
+            assert _as_map(bins[k], wts[k]) == pytest.approx(_as_map(rb, r["decoded"]["weights"][k]), rel=1e-15)
+
+
+@pytest.mark.parametrize("i", range(5))
+def test_decode_imdb_cases(i):
+    m = G.model(f"imdb{i}")
+    pc = PredicateCompiler(m)
+    for r in G.load("imdb_cases.json.gz")[f"imdb{i}"]:
+        if "decoded" not in r:
+            continue
+        bins, wts = pc.decode(G.unjson(r["query"]))
+        if r["decoded"] is None:
+            assert bins is None
+            continue
+        for k, rb in r["decoded"]["bins"].items():
+            assert list(bins[k]) == rb, (k, r["query"])  # order too (continuous walk order)
+            assert np.allclose(np.asarray(wts[k], dtype=float).reshape(-1), r["decoded"]["weights"][k], rtol=1e-15)
+
+
+def test_decode_quirks():
+    for r in G.load("quirk_cases.json.gz")["cases"]:
+        m = G.model(r["model"])
+        pc = PredicateCompiler(m)
+        q = G.unjson(r["query"])
+        if r.get("error") == "KeyError":
+            with pytest.raises(KeyError):
+                pc.decode(q)
+        elif r["kind"] == "decode":
+            bins, wts = pc.decode(q)
+            for k, rb in r["decoded"]["bins"].items():
+                assert list(bins[k]) == rb
+                assert np.allclose(wts[k], r["decoded"]["weights"][k], rtol=1e-15)
+
+
+# ------------------------------------------------------------------------------------ packing
+@pytest.mark.parametrize("name", ["dmv", "census", "imdb2"])
+def test_pack_is_equivalent_to_decoded_weights(name):
+    """Descriptors, unpacked on the CPU and pushed through the dense fp64 form, reproduce the reference."""
+    m = G.model(name)
+    pc = PredicateCompiler(m)
+    cases = G.load("infer_cases.json.gz")[name][:120]
+    decoded = [({k: list(v) for k, v in r["bins"].items()}, {k: np.asarray(v) for k, v in r["weights"].items()})
+               for r in cases]
+    fans = [r["fanout"] for r in cases]
+    r_idx, r_desc, d_idx, d_desc, mask = pc.pack(decoded, fans)
+    assert len(r_idx) + len(d_idx) == len(cases) and len(r_idx) > 0 and len(d_idx) > 0
+    got = np.zeros(len(cases))
+    lo, hi = unpack_ranges(m, r_desc)
+    got[r_idx] = O.dense_tree(m, O.range_weights(m, lo, hi, mask[r_idx]))
+    off = np.concatenate([[0], np.cumsum([-(-int(c) // 4) * 4 for c in m.card])[:-1]])
+    W = []
+    for v in range(m.n_nodes):
+        w = d_desc[:, off[v]: off[v] + m.card[v]].astype(np.float64)
+        f = m.fan_vector(v)
+        if f is not None:
+            bit = ((mask[d_idx, v // 32] >> np.uint32(v % 32)) & 1).astype(bool)
+            w = np.where(bit[:, None], w * f[None, :], w)
+        W.append(w)
+    got[d_idx] = O.dense_tree(m, W)
+    ref = np.asarray([np.asarray(r["p"]["value"]).reshape(-1)[0] for r in cases])
+    # dense descriptors carry fp32 weights: 6e-8 relative per weight
+    assert np.allclose(got, ref, rtol=5e-7, atol=0)
+
+
+# ------------------------------------------------------------------------------------ C ABI
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "bayescard_b200.h")).read()
+    declared = set(re.findall(r"^BC_API [^;(]*?\b(bc_[a-z0-9_]+)\(", header, flags=re.M))
+    assert declared == set(L.EXPORTED_SYMBOLS), declared ^ set(L.EXPORTED_SYMBOLS)
+    h = ctypes.CDLL(L.LIB_PATH)
+    for sym in declared:
+        assert hasattr(h, sym), sym
+    assert b"sm_100a" in L.lib().bc_version()
+
+
+def test_no_cpu_fallback_without_device():
+    """Creating a device model on a machine without CUDA must fail loudly, never fall back."""
+    try:
+        import torch
+
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    with pytest.raises(L.BayesCardError):
+        DeviceModel(G.model("dmv"), device=0)
+
+
+def test_host_only_model_codegen_and_generator():
+    m = G.model("census")
+    dm = DeviceModel(m, device=-1, specialize=False)
+    src = dm.spec_source()
+    assert "bc_spec_range8" in src and "bc_spec_dense" in src
+    # one FFMA per non-zero non-root CPT entry plus the root row
+    nz = sum(int(np.count_nonzero(c.astype(np.float32))) for c in m.cpts)
+    assert dm.spec_ffma() == nz
+    assert dm.flops_dense == m.flops_dense and dm.dense_width == sum(-(-int(c) // 4) * 4 for c in m.card)
+    with pytest.raises(L.BayesCardError):
+        dm.run_host(np.zeros((1, dm.desc_stride(L.DESC_RANGE_U8)), dtype=np.uint8), L.DESC_RANGE_U8)
+    # generator: deterministic, per-index reproducible, k columns constrained, bounds inside the domain
+    a = gen_range_queries_host(m, 7, 0, 512, 1, 14)
+    b = gen_range_queries_host(m, 7, 100, 50, 1, 14)
+    assert np.array_equal(a[100:150], b)
+    lo, hi = unpack_ranges(m, a)
+    assert np.all(lo <= hi) and np.all(hi < m.card[None, :])
+    k = ((lo > 0) | (hi < m.card[None, :] - 1)).sum(axis=1)
+    assert k.max() <= 14 and k.mean() > 4
+    dm.close()
+
+
+def test_shard_split():
+    assert ShardedModel.split(10, 4) == [(0, 2), (2, 4), (4, 6), (6, 10)]
+    assert ShardedModel.split(3, 8)[-1] == (0, 3)
