@@ -56,10 +56,16 @@ class BN_ensemble:
         return parsed_all
 
     # ------------------------------------------------------------------ cardinality
+    _UNDECODABLE = object()  # factor the reference would crash on IF its loop reaches it
+
     @staticmethod
     def _combine(join_size, factors, probs):
         card = join_size
         for f, p in zip(factors, probs):
+            if p is BN_ensemble._UNDECODABLE:
+                # Bayescard_BN.expectation has no `query is None` guard (Models/Bayescard_BN.py:581-583);
+                # the reference only fails if no earlier factor already returned 1 (:244-245)
+                raise AttributeError("'NoneType' object has no attribute 'keys'")
             if p == 0:
                 return 1
             card = card * (1 / p) if f["inverse"] else card * p
@@ -91,10 +97,7 @@ class BN_ensemble:
             ok = [(qi, fi, f) for qi, fi, f in items if f["query"] is not None]
             for qi, fi, f in items:
                 if f["query"] is None:
-                    if len(f["expectation"]) == 0:
-                        probs[qi][fi] = 0
-                    else:
-                        raise AttributeError("'NoneType' object has no attribute 'keys'")
+                    probs[qi][fi] = 0 if len(f["expectation"]) == 0 else self._UNDECODABLE
             if ok:
                 res = m.expectation_batch([f["query"] for _, _, f in ok], [list(f["expectation"]) for _, _, f in ok],
                                           [f["n_distinct"] for _, _, f in ok])
