@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libbayescard_b200.so")
 SPEC_CACHE_DIR = os.path.join(_HERE, "_spec_cache")
 
 BC_OK = 0
-DESC_RANGE_U8, DESC_RANGE_U16, DESC_DENSE_F32 = 0, 1, 2
+DESC_RANGE_U8, DESC_RANGE_U16, DESC_DENSE_F32, DESC_BITS = 0, 1, 2, 3
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_SPEC, KERNEL_GEMM = 0, 1, 2, 3
 
 _lib = None
@@ -48,6 +48,8 @@ _SIGS = {
     "bc_model_device": (C.c_int, [C.c_void_p]),
     "bc_model_dense_width": (C.c_int64, [C.c_void_p]),
     "bc_model_dense_offset": (C.c_int64, [C.c_void_p, C.c_int]),
+    "bc_model_bits_offset": (C.c_int64, [C.c_void_p, C.c_int]),
+    "bc_model_bits_default": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "bc_model_desc_stride": (C.c_int64, [C.c_void_p, C.c_int]),
     "bc_model_flops_dense": (C.c_int64, [C.c_void_p]),
     "bc_model_specialize": (C.c_int, [C.c_void_p, C.c_char_p]),
@@ -58,6 +60,12 @@ _SIGS = {
     "bc_query_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                  C.c_void_p]),
     "bc_query_batch_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
+    "bc_convert_desc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p]),
+    "bc_expand_sparse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "bc_query_batch_sparse_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                             C.c_int]),
+    "bc_gen_sparse_queries_host": (C.c_int, [C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_size_t, C.c_int, C.c_int,
+                                             C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t)]),
     "bc_gen_range_queries": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_size_t, C.c_int, C.c_int, C.c_void_p,
                                        C.c_void_p]),
     "bc_gen_range_queries_host": (C.c_int, [C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_size_t, C.c_int,

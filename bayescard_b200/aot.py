@@ -1,10 +1,9 @@
 """Ahead-of-time build of the specialised kernels (K-spec) for known models.
 
-``build_cubin`` runs the library's code generator on a HOST-ONLY model (no GPU needed), compiles the
-source with ``nvcc -gencode arch=compute_100a,code=sm_100a`` and stores
-``_spec_cache/spec_<hash>.cubin`` -- exactly the file ``bc_model_specialize`` looks for before it falls
-back to NVRTC.  ``__graft_entry__.build()`` does this for the models under ``tests/golden/models`` so the
-GPU box never depends on a runtime compiler for them.
+``build_cubin`` runs the library's code generator on a HOST-ONLY model (no GPU needed), assembles the
+PTX with ``ptxas -arch=sm_100a`` and stores ``_spec_cache/spec_<hash>.cubin`` -- exactly the file
+``bc_model_specialize`` looks for before it hands the PTX to the driver JIT.  ``__graft_entry__.build()``
+does this for the models under ``tests/golden/models`` so the GPU box does not pay JIT time for them.
 """
 from __future__ import annotations
 
@@ -16,7 +15,7 @@ from . import _lib as L
 from .engine import DeviceModel
 from .loader import TreeModel
 
-NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+PTXAS = os.environ.get("PTXAS", "/usr/local/cuda/bin/ptxas")
 
 
 def cubin_path(tm: TreeModel, cache_dir: str = None) -> str:
@@ -39,15 +38,15 @@ def build_cubin(tm: TreeModel, cache_dir: str = None, force: bool = False, keep_
     finally:
         dm.close()
     with tempfile.TemporaryDirectory() as td:
-        cu = os.path.join(td, "spec.cu")
-        with open(cu, "w") as f:
+        ptx = os.path.join(td, "spec.ptx")
+        with open(ptx, "w") as f:
             f.write(src)
         if keep_source:
-            with open(out[:-6] + ".cu", "w") as f:
+            with open(out[:-6] + ".ptx", "w") as f:
                 f.write(src)
-        cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-cubin", "-o", out + ".tmp", cu]
+        cmd = [PTXAS, "-arch=sm_100a", "-O3", "-o", out + ".tmp", ptx]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
-            raise L.BayesCardError("nvcc failed for the specialised kernel:\n" + res.stderr[-2000:])
+            raise L.BayesCardError("ptxas failed for the specialised kernel:\n" + res.stderr[-2000:])
         os.replace(out + ".tmp", out)
     return out

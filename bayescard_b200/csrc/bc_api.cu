@@ -34,6 +34,13 @@ struct BcHostPipe {
     uint32_t* h_mask[kSlots]{};
     float* h_out[kSlots]{};
     size_t cap_desc = 0, cap_mask = 0, cap_q = 0;
+    // SPARSE path: CSR slices in, BITS rows built on the device
+    uint32_t* d_rowoff[kSlots]{};
+    uint32_t* d_entries[kSlots]{};
+    uint32_t* d_bits[kSlots]{};
+    uint32_t* h_rowoff[kSlots]{};
+    uint32_t* h_entries[kSlots]{};
+    size_t cap_sq = 0, cap_entries = 0;
 };
 
 static void pipe_free(BcHostPipe* p) {
@@ -45,6 +52,11 @@ static void pipe_free(BcHostPipe* p) {
         cudaFreeHost(p->h_desc[i]);
         cudaFreeHost(p->h_mask[i]);
         cudaFreeHost(p->h_out[i]);
+        cudaFree(p->d_rowoff[i]);
+        cudaFree(p->d_entries[i]);
+        cudaFree(p->d_bits[i]);
+        cudaFreeHost(p->h_rowoff[i]);
+        cudaFreeHost(p->h_entries[i]);
         if (p->ev_in[i]) cudaEventDestroy(p->ev_in[i]);
         if (p->ev_k[i]) cudaEventDestroy(p->ev_k[i]);
         if (p->ev_out[i]) cudaEventDestroy(p->ev_out[i]);
@@ -111,6 +123,17 @@ extern "C" int bc_model_create(int device, int n_nodes, const int32_t* parent, c
     if (lam > (1LL << 30)) { bc_set_error("sum of domain sizes too large"); delete m; return BC_ELIMIT; }
     m->lam_total = (int)lam;
     m->mask_words = (n_nodes + 31) / 32;
+    // BITS rows: one bit per (node, state), tightly packed, row padded to 16 bytes
+    m->bits.resize(n_nodes);
+    int64_t bit = 0;
+    for (int v = 0; v < n_nodes; ++v) {
+        m->bits[v].bit_off = (int32_t)bit;
+        m->bits[v].card = card[v];
+        bit += card[v];
+    }
+    m->bits_words = (int)bc_round_up((bit + 31) / 32, 4);
+    m->bits_default.assign(m->bits_words, 0u);
+    for (int64_t b = 0; b < bit; ++b) m->bits_default[b >> 5] |= 1u << (b & 31);
     m->ent_node.resize(m->lam_total);
     for (int v = 0; v < n_nodes; ++v)
         for (int c = 0; c < (int)bc_round_up(card[v], 4); ++c) m->ent_node[m->nodes[v].lam_off + c] = (uint16_t)v;
@@ -153,6 +176,10 @@ extern "C" int bc_model_create(int device, int n_nodes, const int32_t* parent, c
         CK(cudaMemcpy(m->d_fan, m->fan.data(), m->fan.size() * sizeof(float), cudaMemcpyHostToDevice));
         CK(cudaMalloc(&m->d_nodes, m->nodes.size() * sizeof(BcNodeRec)));
         CK(cudaMemcpy(m->d_nodes, m->nodes.data(), m->nodes.size() * sizeof(BcNodeRec), cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&m->d_bits, m->bits.size() * sizeof(BcBitsRec)));
+        CK(cudaMemcpy(m->d_bits, m->bits.data(), m->bits.size() * sizeof(BcBitsRec), cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&m->d_bits_default, m->bits_default.size() * 4));
+        CK(cudaMemcpy(m->d_bits_default, m->bits_default.data(), m->bits_default.size() * 4, cudaMemcpyHostToDevice));
         CK(cudaMalloc(&m->d_ent_node, m->ent_node.size() * sizeof(uint16_t)));
         CK(cudaMemcpy(m->d_ent_node, m->ent_node.data(), m->ent_node.size() * sizeof(uint16_t),
                       cudaMemcpyHostToDevice));
@@ -171,6 +198,8 @@ extern "C" void bc_model_destroy(bc_model* m) {
         cudaFree(m->d_arena);
         cudaFree(m->d_fan);
         cudaFree(m->d_nodes);
+        cudaFree(m->d_bits);
+        cudaFree(m->d_bits_default);
         cudaFree(m->d_ent_node);
     }
     delete m;
@@ -189,11 +218,23 @@ extern "C" int64_t bc_model_desc_stride(const bc_model* m, int fmt) {
         case BC_DESC_RANGE_U8: return bc_round_up(2LL * m->n, 4);
         case BC_DESC_RANGE_U16: return 4LL * m->n;
         case BC_DESC_DENSE_F32: return 4LL * m->lam_total;
+        case BC_DESC_BITS: return 4LL * m->bits_words;
     }
     return 0;
 }
+extern "C" int64_t bc_model_bits_offset(const bc_model* m, int node) {
+    if (!m || node < 0 || node >= m->n) return -1;
+    return m->bits[node].bit_off;
+}
+extern "C" int bc_model_bits_default(const bc_model* m, void* row_host, size_t row_bytes) {
+    if (!m || !row_host || row_bytes < (size_t)m->bits_words * 4) { bc_set_error("bad arguments"); return BC_EINVAL; }
+    std::memcpy(row_host, m->bits_default.data(), (size_t)m->bits_words * 4);
+    return BC_OK;
+}
 extern "C" int64_t bc_model_flops_dense(const bc_model* m) { return m ? m->flops_dense : 0; }
-extern "C" int bc_model_has_spec(const bc_model* m) { return m && m->spec_range8 ? 1 : 0; }
+extern "C" int bc_model_has_spec(const bc_model* m) {
+    return m && (m->spec_range8 || m->spec_bits || m->spec_dense) ? 1 : 0;
+}
 
 extern "C" int64_t bc_model_spec_source(const bc_model* m, char* buf, size_t buf_bytes) {
     if (!m) { bc_set_error("model is NULL"); return BC_EINVAL; }
@@ -222,7 +263,7 @@ static int check_format(const bc_model* m, int fmt) {
         bc_set_error("RANGE_U8 needs every domain <= 256 states (max is %d); use RANGE_U16", m->max_card);
         return BC_ELIMIT;
     }
-    if (fmt < 0 || fmt > BC_DESC_DENSE_F32) { bc_set_error("unknown descriptor format %d", fmt); return BC_EINVAL; }
+    if (fmt < 0 || fmt > BC_DESC_BITS) { bc_set_error("unknown descriptor format %d", fmt); return BC_EINVAL; }
     return BC_OK;
 }
 
@@ -235,19 +276,32 @@ extern "C" int bc_query_batch(bc_model* m, const void* desc, size_t nq, int fmt,
     if (rc) return rc;
     BC_CUDA_CHECK(cudaSetDevice(m->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const bool spec_ok = m->spec_range8 && (fmt == BC_DESC_RANGE_U8 || (fmt == BC_DESC_DENSE_F32 && m->spec_dense));
-    if (kernel == BC_KERNEL_SPEC && !spec_ok) {
+    const bool is_range = fmt == BC_DESC_RANGE_U8 || fmt == BC_DESC_RANGE_U16;
+    const bool spec_direct = (fmt == BC_DESC_RANGE_U8 && m->spec_range8) || (fmt == BC_DESC_DENSE_F32 && m->spec_dense) ||
+                             (fmt == BC_DESC_BITS && m->spec_bits);
+    const bool spec_via_bits = is_range && !spec_direct && m->spec_bits;
+    if (kernel == BC_KERNEL_SPEC && !spec_direct && !spec_via_bits) {
         bc_set_error("no specialised kernel attached for this model / format (call bc_model_specialize)");
         return BC_ECOMPILE;
     }
-    if (kernel == BC_KERNEL_SPEC || (kernel == BC_KERNEL_AUTO && spec_ok))
-        return bc_spec_launch(m, desc, nq, fmt, fan_mask, out, st);
+    if (kernel == BC_KERNEL_SPEC || kernel == BC_KERNEL_AUTO) {
+        if (spec_direct) return bc_spec_launch(m, desc, nq, fmt, fan_mask, out, st);
+        if (spec_via_bits) {
+            // range rows -> BITS rows in stream-ordered scratch, then the BITS kernel
+            void* scratch = nullptr;
+            BC_CUDA_CHECK(cudaMallocAsync(&scratch, nq * (size_t)m->bits_words * 4, st));
+            rc = bc_convert_launch(m, desc, fmt, scratch, BC_DESC_BITS, nq, st);
+            if (rc == BC_OK) rc = bc_spec_launch(m, scratch, nq, BC_DESC_BITS, fan_mask, out, st);
+            cudaFreeAsync(scratch, st);
+            return rc;
+        }
+    }
     if (kernel == BC_KERNEL_GENERIC || kernel == BC_KERNEL_AUTO) return bc_k1_launch(m, desc, nq, fmt, fan_mask, out, st);
     bc_set_error("kernel %d not available in this build", kernel);
     return BC_EINVAL;
 }
 
-static int pipe_ensure(bc_model* m, size_t chunk_q, size_t desc_stride) {
+static int pipe_streams(bc_model* m) {
     if (!m->pipe) {
         m->pipe = new BcHostPipe();
         BcHostPipe* p = m->pipe;
@@ -260,6 +314,12 @@ static int pipe_ensure(bc_model* m, size_t chunk_q, size_t desc_stride) {
             BC_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_out[i], cudaEventDisableTiming));
         }
     }
+    return BC_OK;
+}
+
+static int pipe_ensure(bc_model* m, size_t chunk_q, size_t desc_stride) {
+    int rc = pipe_streams(m);
+    if (rc) return rc;
     BcHostPipe* p = m->pipe;
     const size_t need_desc = chunk_q * desc_stride, need_mask = chunk_q * m->mask_words * 4;
     if (need_desc > p->cap_desc || need_mask > p->cap_mask || chunk_q > p->cap_q) {
@@ -363,6 +423,163 @@ extern "C" int bc_query_batch_host(bc_model* m, const void* desc, size_t nq, int
     return BC_OK;
 }
 
+
+// ------------------------------------------------------------------------------------ conversion / sparse
+extern "C" int bc_convert_desc(bc_model* m, const void* src, int src_fmt, void* dst, int dst_fmt, size_t nq,
+                               void* stream) {
+    if (!m || m->device < 0) { bc_set_error("model has no device (host-only model)"); return BC_EINVAL; }
+    if (nq && (!src || !dst)) { bc_set_error("src/dst is NULL"); return BC_EINVAL; }
+    int rc = check_format(m, src_fmt);
+    if (rc) return rc;
+    BC_CUDA_CHECK(cudaSetDevice(m->device));
+    return bc_convert_launch(m, src, src_fmt, dst, dst_fmt, nq, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int bc_expand_sparse(bc_model* m, const uint32_t* row_off, const uint32_t* entries, size_t nq,
+                                void* dst_bits, void* stream) {
+    if (!m || m->device < 0) { bc_set_error("model has no device (host-only model)"); return BC_EINVAL; }
+    if (nq && (!row_off || !dst_bits)) { bc_set_error("row_off/dst is NULL"); return BC_EINVAL; }
+    BC_CUDA_CHECK(cudaSetDevice(m->device));
+    return bc_expand_sparse_launch(m, row_off, entries, nq, dst_bits, static_cast<cudaStream_t>(stream));
+}
+
+static int sparse_ensure(bc_model* m, size_t chunk_q, size_t chunk_entries) {
+    int rc = pipe_streams(m);
+    if (rc) return rc;
+    BcHostPipe* p = m->pipe;
+    if (chunk_q > p->cap_sq) {
+        for (int i = 0; i < BcHostPipe::kSlots; ++i) {
+            cudaFree(p->d_rowoff[i]); cudaFree(p->d_bits[i]);
+            cudaFreeHost(p->h_rowoff[i]);
+            p->d_rowoff[i] = nullptr; p->d_bits[i] = nullptr; p->h_rowoff[i] = nullptr;
+            BC_CUDA_CHECK(cudaMalloc(&p->d_rowoff[i], (chunk_q + 1) * 4));
+            BC_CUDA_CHECK(cudaMalloc(&p->d_bits[i], chunk_q * (size_t)m->bits_words * 4));
+        }
+        p->cap_sq = chunk_q;
+    }
+    if (chunk_entries > p->cap_entries) {
+        for (int i = 0; i < BcHostPipe::kSlots; ++i) {
+            cudaFree(p->d_entries[i]);
+            cudaFreeHost(p->h_entries[i]);
+            p->d_entries[i] = nullptr; p->h_entries[i] = nullptr;
+            BC_CUDA_CHECK(cudaMalloc(&p->d_entries[i], chunk_entries * 4));
+        }
+        p->cap_entries = chunk_entries;
+    }
+    const size_t need_mask = chunk_q * m->mask_words * 4;
+    if (chunk_q > p->cap_q || need_mask > p->cap_mask) {
+        for (int i = 0; i < BcHostPipe::kSlots; ++i) {
+            cudaFree(p->d_mask[i]); cudaFree(p->d_out[i]);
+            cudaFreeHost(p->h_mask[i]); cudaFreeHost(p->h_out[i]);
+            p->d_mask[i] = nullptr; p->d_out[i] = nullptr; p->h_mask[i] = nullptr; p->h_out[i] = nullptr;
+            BC_CUDA_CHECK(cudaMalloc(&p->d_mask[i], need_mask));
+            BC_CUDA_CHECK(cudaMalloc(&p->d_out[i], chunk_q * 4));
+        }
+        p->cap_q = chunk_q; p->cap_mask = need_mask;
+        // the RANGE/DENSE staging of this pipe is sized per (cap_q, cap_desc): force it to be rebuilt
+        for (int i = 0; i < BcHostPipe::kSlots; ++i) {
+            cudaFree(p->d_desc[i]); cudaFreeHost(p->h_desc[i]);
+            p->d_desc[i] = nullptr; p->h_desc[i] = nullptr;
+        }
+        p->cap_desc = 0;
+    }
+    return BC_OK;
+}
+
+extern "C" int bc_query_batch_sparse_host(bc_model* m, const uint32_t* row_off, const uint32_t* entries, size_t nq,
+                                          const uint32_t* fan_mask, float* out, int kernel) {
+    if (!m || m->device < 0) { bc_set_error("model has no device (host-only model)"); return BC_EINVAL; }
+    if (nq == 0) return BC_OK;
+    if (!row_off || !out) { bc_set_error("row_off/out is NULL"); return BC_EINVAL; }
+    if (row_off[nq] > row_off[0] && !entries) { bc_set_error("entries is NULL"); return BC_EINVAL; }
+    BC_CUDA_CHECK(cudaSetDevice(m->device));
+    // chunks of ~256K queries: large enough to fill the GPU several times over, small enough to overlap
+    size_t chunk = 256 * 1024;
+    if (chunk > nq) chunk = nq;
+    const size_t nchunks = (nq + chunk - 1) / chunk;
+    size_t max_entries = 1;
+    for (size_t ci = 0; ci < nchunks; ++ci) {
+        const size_t q0 = ci * chunk, q1 = q0 + chunk < nq ? q0 + chunk : nq;
+        if (row_off[q1] < row_off[q0]) { bc_set_error("row_off is not monotone at query %zu", q0); return BC_EINVAL; }
+        const size_t ne = row_off[q1] - row_off[q0];
+        if (ne > max_entries) max_entries = ne;
+    }
+    std::lock_guard<std::mutex> lock(m->pipe_mu);
+    int rc = sparse_ensure(m, chunk, max_entries);
+    if (rc) return rc;
+    BcHostPipe* p = m->pipe;
+    const bool pin_off = is_pinned(row_off), pin_ent = !entries || is_pinned(entries), pin_out = is_pinned(out),
+               pin_mask = !fan_mask || is_pinned(fan_mask);
+    auto ensure_host = [&](void** h, size_t bytes) -> int {
+        if (!*h) BC_CUDA_CHECK(cudaHostAlloc(h, bytes, cudaHostAllocDefault));
+        return BC_OK;
+    };
+    for (size_t ci = 0; ci < nchunks; ++ci) {
+        const int s = (int)(ci % BcHostPipe::kSlots);
+        const size_t q0 = ci * chunk, cq = (q0 + chunk <= nq) ? chunk : nq - q0;
+        if (ci >= (size_t)BcHostPipe::kSlots) {
+            BC_CUDA_CHECK(cudaEventSynchronize(p->ev_out[s]));
+            if (!pin_out) std::memcpy(out + (ci - BcHostPipe::kSlots) * chunk, p->h_out[s], chunk * 4);
+        }
+        const uint32_t e0 = row_off[q0];
+        const size_t ne = row_off[q0 + cq] - e0;
+        const uint32_t* osrc = row_off + q0;
+        if (!pin_off) {
+            if ((rc = ensure_host((void**)&p->h_rowoff[s], (p->cap_sq + 1) * 4))) return rc;
+            std::memcpy(p->h_rowoff[s], osrc, (cq + 1) * 4);
+            osrc = p->h_rowoff[s];
+        }
+        BC_CUDA_CHECK(cudaMemcpyAsync(p->d_rowoff[s], osrc, (cq + 1) * 4, cudaMemcpyHostToDevice, p->s_in));
+        if (ne) {
+            const uint32_t* esrc = entries + e0;
+            if (!pin_ent) {
+                if ((rc = ensure_host((void**)&p->h_entries[s], p->cap_entries * 4))) return rc;
+                std::memcpy(p->h_entries[s], esrc, ne * 4);
+                esrc = p->h_entries[s];
+            }
+            BC_CUDA_CHECK(cudaMemcpyAsync(p->d_entries[s], esrc, ne * 4, cudaMemcpyHostToDevice, p->s_in));
+        }
+        const uint32_t* dmask = nullptr;
+        if (fan_mask) {
+            const uint32_t* msrc = fan_mask + q0 * m->mask_words;
+            if (!pin_mask) {
+                if ((rc = ensure_host((void**)&p->h_mask[s], p->cap_mask))) return rc;
+                std::memcpy(p->h_mask[s], msrc, cq * m->mask_words * 4);
+                msrc = p->h_mask[s];
+            }
+            BC_CUDA_CHECK(cudaMemcpyAsync(p->d_mask[s], msrc, cq * m->mask_words * 4, cudaMemcpyHostToDevice, p->s_in));
+            dmask = p->d_mask[s];
+        }
+        BC_CUDA_CHECK(cudaEventRecord(p->ev_in[s], p->s_in));
+        BC_CUDA_CHECK(cudaStreamWaitEvent(p->s_k, p->ev_in[s], 0));
+        // row_off values are absolute entry indices: bias the entries pointer instead of rewriting them
+        rc = bc_expand_sparse_launch(m, p->d_rowoff[s], p->d_entries[s] - e0, cq, p->d_bits[s], p->s_k);
+        if (rc) return rc;
+        rc = bc_query_batch(m, p->d_bits[s], cq, BC_DESC_BITS, dmask, p->d_out[s], kernel, p->s_k);
+        if (rc) return rc;
+        BC_CUDA_CHECK(cudaEventRecord(p->ev_k[s], p->s_k));
+        BC_CUDA_CHECK(cudaStreamWaitEvent(p->s_out, p->ev_k[s], 0));
+        float* dst = out + q0;
+        if (!pin_out) {
+            if ((rc = ensure_host((void**)&p->h_out[s], p->cap_q * 4))) return rc;
+            dst = p->h_out[s];
+        }
+        BC_CUDA_CHECK(cudaMemcpyAsync(dst, p->d_out[s], cq * 4, cudaMemcpyDeviceToHost, p->s_out));
+        BC_CUDA_CHECK(cudaEventRecord(p->ev_out[s], p->s_out));
+        BC_CUDA_CHECK(cudaStreamWaitEvent(p->s_in, p->ev_out[s], 0));
+    }
+    BC_CUDA_CHECK(cudaStreamSynchronize(p->s_out));
+    if (!pin_out) {
+        const size_t first = nchunks > (size_t)BcHostPipe::kSlots ? nchunks - BcHostPipe::kSlots : 0;
+        for (size_t ci = first; ci < nchunks; ++ci) {
+            const int s = (int)(ci % BcHostPipe::kSlots);
+            const size_t q0 = ci * chunk, cq = (q0 + chunk <= nq) ? chunk : nq - q0;
+            std::memcpy(out + q0, p->h_out[s], cq * 4);
+        }
+    }
+    return BC_OK;
+}
+
 // ------------------------------------------------------------------------------------ generator
 // Counter-based RNG: splitmix64 keyed by (seed, query index); identical on host and device.
 __host__ __device__ static inline uint64_t bc_mix(uint64_t& s) {
@@ -451,6 +668,28 @@ extern "C" int bc_gen_range_queries_host(int n_nodes, const int32_t* card, uint6
         bc_gen_row(card, n_nodes, seed, first + q, kmin, kmax, row);
         for (size_t b = 2 * (size_t)n_nodes; b < stride; ++b) row[b] = 0;
     }
+    return BC_OK;
+}
+
+extern "C" int bc_gen_sparse_queries_host(int n_nodes, const int32_t* card, uint64_t seed, uint64_t first, size_t n,
+                                          int kmin, int kmax, uint32_t* row_off, uint32_t* entries, size_t* n_entries) {
+    if (!card || !row_off || !entries || n_nodes <= 0) { bc_set_error("bad arguments"); return BC_EINVAL; }
+    int mc = 0;
+    for (int v = 0; v < n_nodes; ++v) mc = card[v] > mc ? card[v] : mc;
+    int rc = gen_check(n_nodes, mc, kmin, kmax);
+    if (rc) return rc;
+    std::vector<uint8_t> row((size_t)bc_round_up(2LL * n_nodes, 4));
+    size_t ne = 0;
+    for (size_t q = 0; q < n; ++q) {
+        bc_gen_row(card, n_nodes, seed, first + q, kmin, kmax, row.data());
+        row_off[q] = (uint32_t)ne;
+        for (int v = 0; v < n_nodes; ++v) {
+            const int lo = row[2 * v], hi = row[2 * v + 1];
+            if (lo > 0 || hi < card[v] - 1) entries[ne++] = (uint32_t)v | ((uint32_t)lo << 16) | ((uint32_t)hi << 24);
+        }
+    }
+    row_off[n] = (uint32_t)ne;
+    if (n_entries) *n_entries = ne;
     return BC_OK;
 }
 

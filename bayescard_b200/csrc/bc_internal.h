@@ -13,7 +13,7 @@
 #include "../../include/bayescard_b200.h"
 
 #define BC_VERSION_STRING "bayescard_b200 0.1.0 (sm_100a)"
-#define BC_CODEGEN_VERSION 7
+#define BC_CODEGEN_VERSION 8
 
 // One record per node, copied to the device and (by K1) into shared memory.  32 bytes.
 struct BcNodeRec {
@@ -26,6 +26,12 @@ struct BcNodeRec {
     int32_t card_pa;     // card of the parent (1 for the root)
 };
 
+// Second per-node table (kept out of BcNodeRec so that record stays 32 bytes): BITS rows.
+struct BcBitsRec {
+    int32_t bit_off;     // first bit of this node's state mask in a BITS row
+    int32_t card;
+};
+
 struct BcHostPipe;  // bc_api.cu
 
 struct bc_model {
@@ -35,6 +41,8 @@ struct bc_model {
     std::vector<float> arena;        // host copy (code generator input)
     std::vector<float> fan;
     std::vector<uint16_t> ent_node;  // node id of every entry of a lambda row
+    std::vector<BcBitsRec> bits;     // BITS descriptor geometry
+    int bits_words = 0;              // 32-bit words per BITS row (multiple of 4)
     int lam_total = 0;               // floats per lambda / dense row
     int max_card = 0;
     int mask_words = 1;
@@ -44,6 +52,8 @@ struct bc_model {
     size_t arena_floats_padded = 0;
     float* d_fan = nullptr;
     BcNodeRec* d_nodes = nullptr;
+    BcBitsRec* d_bits = nullptr;
+    uint32_t* d_bits_default = nullptr;  // BITS row of the unconstrained query (every state selected)
     uint16_t* d_ent_node = nullptr;
     int sm_count = 0;
     int smem_optin = 0;
@@ -51,8 +61,11 @@ struct bc_model {
     cudaLibrary_t spec_lib = nullptr;
     cudaKernel_t spec_range8 = nullptr;
     cudaKernel_t spec_dense = nullptr;
-    int spec_threads = 0;
-    int spec_min_blocks = 0;
+    cudaKernel_t spec_bits = nullptr;
+    int spec_threads = 0;            // threads per CTA (from the image's bc_spec_meta)
+    int spec_qpt = 1;                // queries per thread per loop trip
+    int spec_blocks_bits = 1, spec_blocks_dense = 1, spec_blocks_range8 = 1;  // resident CTAs per SM
+    std::vector<uint32_t> bits_default;
     BcHostPipe* pipe = nullptr;
     std::mutex pipe_mu;
 };
@@ -74,6 +87,10 @@ static inline int64_t bc_round_up(int64_t x, int64_t a) { return (x + a - 1) / a
 // k1_generic.cu
 int bc_k1_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32_t* fan_mask,
                  float* out, cudaStream_t stream);
+// bc_convert.cu
+int bc_convert_launch(bc_model* m, const void* src, int src_fmt, void* dst, int dst_fmt, size_t nq, cudaStream_t stream);
+int bc_expand_sparse_launch(bc_model* m, const uint32_t* row_off, const uint32_t* entries, size_t nq, void* dst_bits,
+                            cudaStream_t stream);
 // spec_codegen.cc
 std::string bc_spec_generate(const bc_model& m);
 uint64_t bc_spec_hash_of(const bc_model& m);

@@ -29,6 +29,7 @@ struct K1Params {
     unsigned arena_bytes;  // multiple of 16 (only used by the shared-memory variant)
     const float* fan;
     const uint16_t* ent_node;
+    const BcBitsRec* bits;  // BITS rows only
     int lam_total;
     const uint8_t* desc;
     size_t desc_stride;  // bytes
@@ -37,7 +38,7 @@ struct K1Params {
     float* out;
     size_t nq;
     // shared memory carve-up (bytes from the base, all multiples of 16)
-    unsigned off_arena, off_nodes, off_ent, off_warp, warp_bytes, off_lam, off_desc, off_act;
+    unsigned off_arena, off_nodes, off_ent, off_bits, off_warp, warp_bytes, off_lam, off_desc, off_act;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -84,6 +85,7 @@ __global__ void __launch_bounds__(512) k1_kernel(const K1Params P) {
     float* s_arena = reinterpret_cast<float*>(smem + P.off_arena);
     BcNodeRec* s_nodes = reinterpret_cast<BcNodeRec*>(smem + P.off_nodes);
     uint16_t* s_ent = reinterpret_cast<uint16_t*>(smem + P.off_ent);
+    int32_t* s_bitoff = reinterpret_cast<int32_t*>(smem + P.off_bits);
 
     // ---- prologue: node tables by plain loads, arena by TMA bulk copies -----------------------
     if (ARENA_SMEM && threadIdx.x == 0) {
@@ -95,6 +97,8 @@ __global__ void __launch_bounds__(512) k1_kernel(const K1Params P) {
         uint4* dst = reinterpret_cast<uint4*>(s_nodes);
         for (int i = threadIdx.x; i < P.n * 2; i += blockDim.x) dst[i] = src[i];
         for (int i = threadIdx.x; i < P.lam_total; i += blockDim.x) s_ent[i] = P.ent_node[i];
+        if (FMT == BC_DESC_BITS)
+            for (int i = threadIdx.x; i < P.n; i += blockDim.x) s_bitoff[i] = P.bits[i].bit_off;
     }
     __syncthreads();
     if (ARENA_SMEM) {
@@ -132,6 +136,37 @@ __global__ void __launch_bounds__(512) k1_kernel(const K1Params P) {
                 lam[e] = w;
             }
             for (int v = lane; v < P.n; v += kWarp) act[v] = 1;
+        } else if (FMT == BC_DESC_BITS) {
+            const uint32_t* grow = reinterpret_cast<const uint32_t*>(P.desc + q * P.desc_stride);
+            const int words = (int)(P.desc_stride >> 2);
+            for (int i = lane; i < words; i += kWarp) sdesc32[i] = grow[i];
+            for (int v = lane; v < P.n; v += kWarp) act[v] = 0;
+            __syncwarp();
+            for (int e = lane; e < P.lam_total; e += kWarp) {
+                const int v = s_ent[e];
+                const BcNodeRec& nd = s_nodes[v];
+                const int c = e - nd.lam_off;
+                const int b = s_bitoff[v] + c;
+                float w = (c < nd.card && ((sdesc32[b >> 5] >> (b & 31)) & 1u)) ? 1.f : 0.f;
+                if (fm && ((fm[v >> 5] >> (v & 31)) & 1u) && nd.fan_off >= 0 && c < nd.card)
+                    w *= P.fan[nd.fan_off + c];
+                lam[e] = w;
+            }
+            // Steiner pruning: a column is constrained when any of its bits is cleared
+            for (int v = lane; v < P.n; v += kWarp) {
+                const BcNodeRec& nd = s_nodes[v];
+                bool constrained = false;
+                for (int c = 0, b = s_bitoff[v]; c < nd.card; ++c, ++b)
+                    constrained |= !((sdesc32[b >> 5] >> (b & 31)) & 1u);
+                if (fm && ((fm[v >> 5] >> (v & 31)) & 1u) && nd.fan_off >= 0) constrained = true;
+                if (constrained) {
+                    int u = v;
+                    while (u >= 0 && !act[u]) {
+                        act[u] = 1;
+                        u = s_nodes[u].parent;
+                    }
+                }
+            }
         } else {
             const uint32_t* grow = reinterpret_cast<const uint32_t*>(P.desc + q * P.desc_stride);
             const int words = (int)(P.desc_stride >> 2);
@@ -305,6 +340,7 @@ int bc_k1_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32
     P.arena = m->d_arena;
     P.fan = m->d_fan;
     P.ent_node = m->d_ent_node;
+    P.bits = m->d_bits;
     P.lam_total = m->lam_total;
     P.desc = static_cast<const uint8_t*>(desc);
     P.desc_stride = (size_t)bc_model_desc_stride(m, fmt);
@@ -316,6 +352,7 @@ int bc_k1_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32
     const size_t arena_bytes = (size_t)bc_round_up((int64_t)m->arena_floats_padded * 4, 16);
     const size_t nodes_bytes = (size_t)bc_round_up((int64_t)m->n * sizeof(BcNodeRec), 16);
     const size_t ent_bytes = (size_t)bc_round_up((int64_t)m->lam_total * 2, 16);
+    const size_t bits_bytes = fmt == BC_DESC_BITS ? (size_t)bc_round_up((int64_t)m->n * 4, 16) : 0;
     const size_t lam_bytes = (size_t)m->lam_total * 4;  // lam_total is a multiple of 4
     const size_t desc_bytes = fmt == BC_DESC_DENSE_F32 ? 0 : (size_t)bc_round_up((int64_t)P.desc_stride, 16);
     const size_t act_bytes = (size_t)bc_round_up(m->n, 16);
@@ -324,9 +361,9 @@ int bc_k1_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32
 
     // choose warps per CTA and whether the arena lives in shared memory
     int warps = 8;
-    const size_t fixed_smem = 16 + arena_bytes + nodes_bytes + ent_bytes;
+    const size_t fixed_smem = 16 + arena_bytes + nodes_bytes + ent_bytes + bits_bytes;
     bool arena_smem = arena_bytes < (1u << 20) && fixed_smem + 4 * warp_bytes <= budget;
-    size_t fixed = arena_smem ? fixed_smem : 16 + nodes_bytes + ent_bytes;
+    size_t fixed = arena_smem ? fixed_smem : 16 + nodes_bytes + ent_bytes + bits_bytes;
     if (arena_smem && arena_bytes > 48 * 1024) warps = 16;  // one big CTA per SM shares the arena
     while (warps > 1 && fixed + (size_t)warps * warp_bytes > budget) warps >>= 1;
     if (fixed + (size_t)warps * warp_bytes > budget) {
@@ -339,7 +376,8 @@ int bc_k1_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32
     P.off_arena = 16;
     P.off_nodes = (unsigned)(arena_smem ? 16 + arena_bytes : 16);
     P.off_ent = (unsigned)(P.off_nodes + nodes_bytes);
-    P.off_warp = (unsigned)(P.off_ent + ent_bytes);
+    P.off_bits = (unsigned)(P.off_ent + ent_bytes);
+    P.off_warp = (unsigned)(P.off_bits + bits_bytes);
     P.warp_bytes = (unsigned)warp_bytes;
     P.off_lam = 0;
     P.off_desc = (unsigned)lam_bytes;
@@ -358,6 +396,7 @@ int bc_k1_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32
         case BC_DESC_RANGE_U8: return launch_fmt<BC_DESC_RANGE_U8>(m, P, arena_smem, threads, (int)grid, smem, stream);
         case BC_DESC_RANGE_U16: return launch_fmt<BC_DESC_RANGE_U16>(m, P, arena_smem, threads, (int)grid, smem, stream);
         case BC_DESC_DENSE_F32: return launch_fmt<BC_DESC_DENSE_F32>(m, P, arena_smem, threads, (int)grid, smem, stream);
+        case BC_DESC_BITS: return launch_fmt<BC_DESC_BITS>(m, P, arena_smem, threads, (int)grid, smem, stream);
     }
     bc_set_error("unknown descriptor format %d", fmt);
     return BC_EINVAL;

@@ -1,47 +1,62 @@
-// K-spec code generator: turns ONE learned tree into straight-line sm_100a CUDA.
+// K-spec code generator: turns ONE learned tree into straight-line sm_100a PTX.
 //
 // The reference's docstring promises exactly this -- "Compiles a ppl program into a fixed linear
 // algebra program to speed up the inference" (Pgmpy/inference/ExactInference.py:113-114) -- but
 // re-plans every query in Python (copy.deepcopy per node, :100).  Here the plan is fixed at model
 // load: one THREAD evaluates one query; every message vector lives in registers; every non-zero
-// CPT entry T_v[c][p] becomes the immediate operand of one FFMA; there is no shared memory, no
-// synchronisation and no data-dependent branch, so all warps run the same instruction stream.
+// CPT entry T_v[c][p] is the 32-bit immediate of exactly one FMA-pipe instruction; there is no
+// shared memory, no synchronisation and no data-dependent branch.
 //
-//   m_v[p]   = sum_c u_v[c] * T_v[c][p]              (one FFMA per non-zero entry)
-//   u_v[c]   = w_v[c] * prod_{children k} m_k[c]     (registers)
-//   result   = sum_c u_0[c] * T_0[c]
+//   m_v[p]   = sum_c w_v[c] * lambda_v[c] * T_v[c][p]
+//   lambda_v = prod_{children k} m_k                       (registers)
+//   result   = sum_c w_0[c] * lambda_0[c] * T_0[c]
+//
+// Two entry points are generated (PTX, so that instruction selection is ours, not a C compiler's):
+//
+//   bc_spec_bits   w is a BITS row.  The state's bit becomes a PREDICATE (ptxas packs seven of them
+//                  per R2P) and guards the FMAs of that state directly:
+//                      @p fma.rn.f32 m_p, lambda_c, T, m_p        (leaf:  @p add.f32 m_p, m_p, T)
+//                  so selecting costs ~1/7 ALU instruction per state instead of one select per
+//                  state.  The first state of every node seeds the accumulators through one select
+//                  + multiplies, which removes the zero-initialisation.  On B200 an ALU-pipe
+//                  instruction costs two issue slots and an FMA-pipe one costs one (measured,
+//                  profiles/r1_microbench_pipes.txt), hence the care.
+//   bc_spec_dense  w is a DENSE_F32 row (fractional n_distinct weights): u = w * lambda, plain FMAs.
 //
 // Children are evaluated largest-subtree first so that the fewest message vectors are live at
 // once (Sethi-Ullman order).  Exact zeros of the CPT (30 % of the shipped DMV / Census entries)
-// emit no instruction; the number of FFMAs actually emitted is reported in the header comment of
-// the generated source and is what the roofline accounting uses.
+// emit no instruction; the number of FMAs actually emitted is reported in the header comment of
+// the generated source (BC_SPEC_FFMA) and is what the roofline accounting uses.
 #include <algorithm>
 #include <cstring>
-#include <functional>
 #include <string>
 
 #include "bc_internal.h"
 
 namespace {
 
-std::string flit(float x) {
-    char b[64];
-    snprintf(b, sizeof(b), "%.9g", (double)x);
-    std::string s(b);
-    if (s.find_first_of(".eEn") == std::string::npos) s += ".0";
-    return s + "f";
+std::string fhex(float x) {
+    uint32_t b;
+    std::memcpy(&b, &x, 4);
+    char s[16];
+    snprintf(s, sizeof(s), "0f%08X", b);
+    return s;
 }
+inline std::string I(long long x) { return std::to_string(x); }
 
 struct Gen {
     const bc_model& m;
+    const bool dense;
     std::vector<std::vector<int>> kids;
-    std::vector<long long> subtree;
     std::string out;
-    long long n_ffma = 0, n_elem = 0;
-    bool dense;
+    long long n_fma = 0;
+    int nf = 0, np = 0, nr = 0;
     bool any_fan = false;
+    std::vector<std::string> words;  // BITS row words / (dense: unused)
+    std::vector<std::string> fmw;    // fan-out mask words
 
-    explicit Gen(const bc_model& mm, bool d) : m(mm), kids(mm.n), subtree(mm.n, 0), dense(d) {
+    Gen(const bc_model& mm, bool d) : m(mm), dense(d), kids(mm.n) {
+        std::vector<long long> subtree(m.n, 0);
         for (int v = 1; v < m.n; ++v) kids[m.nodes[v].parent].push_back(v);
         for (int v = m.n - 1; v >= 0; --v) {
             subtree[v] += m.nodes[v].card;
@@ -52,139 +67,201 @@ struct Gen {
             std::stable_sort(kids[v].begin(), kids[v].end(), [&](int a, int b) { return subtree[a] > subtree[b]; });
     }
 
-    void line(const std::string& s) { out += s; out += '\n'; }
-    static std::string I(long long x) { return std::to_string(x); }
+    std::string F() { return "%f" + I(++nf); }
+    std::string P() { return "%p" + I(++np); }
+    std::string R() { return "%r" + I(++nr); }
+    void line(const std::string& s) { out += "    "; out += s; out += '\n'; }
 
-    // selection predicate of state c of node v (range formats) -> C expression of type bool
-    void emit_selector(int v) {
-        const BcNodeRec& nd = m.nodes[v];
-        const int byte = 2 * v, w = byte / 4, sh = (byte % 4) * 8;
-        line("    const unsigned lo" + I(v) + " = (d" + I(w) + " >> " + I(sh) + ") & 0xffu, hi" + I(v) + " = min((d" +
-             I(w) + " >> " + I(sh + 8) + ") & 0xffu, " + I(nd.card - 1) + "u);");
-        if (nd.card <= 32) {
-            line("    const unsigned mk" + I(v) + " = hi" + I(v) + " >= lo" + I(v) + " ? ((0xffffffffu >> (31u - hi" +
-                 I(v) + ")) & (0xffffffffu << lo" + I(v) + ")) : 0u;");
-        } else if (nd.card <= 64) {
-            line("    const unsigned long long mk" + I(v) + " = hi" + I(v) + " >= lo" + I(v) +
-                 " ? ((0xffffffffffffffffull >> (63u - hi" + I(v) + ")) & (0xffffffffffffffffull << lo" + I(v) +
-                 ")) : 0ull;");
-        } else {
-            line("    const unsigned ln" + I(v) + " = hi" + I(v) + " >= lo" + I(v) + " ? hi" + I(v) + " - lo" + I(v) +
-                 " + 1u : 0u;");
-        }
-    }
-    std::string sel(int v, int c) const {
-        const BcNodeRec& nd = m.nodes[v];
-        if (nd.card <= 32) return "(mk" + I(v) + " & " + I(1u << c) + "u)";
-        if (nd.card <= 64) return "(mk" + I(v) + " & " + I(1ull << c) + "ull)";
-        return "((" + I(c) + "u - lo" + I(v) + ") < ln" + I(v) + ")";
+    std::string bit_pred(int v, int c) {
+        const int b = m.bits[v].bit_off + c;
+        std::string t = R(), p = P();
+        line("and.b32 " + t + ", " + words[b >> 5] + ", " + I(1LL << (b & 31)) + ";");
+        line("setp.ne.u32 " + p + ", " + t + ", 0;");
+        return p;
     }
 
-    // Emits code that leaves the message of node v in registers m<v>_<p>, p < card(parent).
-    void emit_message(int v) {
+    // Emits the message of node v; returns its registers, one per parent state (root: one).
+    std::vector<std::string> message(int v) {
         const BcNodeRec& nd = m.nodes[v];
         const bool root = v == 0;
-        line("    // ---- node " + I(v) + ": card " + I(nd.card) + (root ? " (root)" : ", parent " + I(nd.parent)) +
-             ", " + I((long long)kids[v].size()) + " children");
-        // children first; their messages are indexed by this node's states
-        bool have_lam = false;
+        const int card = nd.card, cols = root ? 1 : nd.card_pa;
+        line("// ---- node " + I(v) + ": card " + I(card) + (root ? " (root)" : ", parent " + I(nd.parent)));
+        std::vector<std::string> lam;
         for (int k : kids[v]) {
-            emit_message(k);
-            if (!have_lam) {
-                for (int c = 0; c < nd.card; ++c) line("    float l" + I(v) + "_" + I(c) + " = m" + I(k) + "_" + I(c) + ";");
-                have_lam = true;
-            } else {
-                for (int c = 0; c < nd.card; ++c) line("    l" + I(v) + "_" + I(c) + " *= m" + I(k) + "_" + I(c) + ";");
-            }
+            std::vector<std::string> mk = message(k);
+            if (lam.empty()) lam = mk;
+            else
+                for (int c = 0; c < card; ++c) line("mul.f32 " + lam[c] + ", " + lam[c] + ", " + mk[c] + ";");
         }
         const bool fan = nd.fan_off >= 0;
-        if (!dense) emit_selector(v);
-        if (fan) line("    const bool fb" + I(v) + " = (fm" + I(v / 32) + " >> " + I(v % 32) + ") & 1u;");
-        const int cols = root ? 1 : nd.card_pa;
-        if (root) line("    float r = 0.f;");
-        else
-            for (int p = 0; p < cols; ++p) line("    float m" + I(v) + "_" + I(p) + " = 0.f;");
+        std::string pfb;
+        if (fan) {
+            std::string t = R();
+            pfb = P();
+            line("and.b32 " + t + ", " + fmw[v >> 5] + ", " + I(1LL << (v & 31)) + ";");
+            line("setp.ne.u32 " + pfb + ", " + t + ", 0;");
+        }
+        const float* T = m.arena.data() + nd.cpt_off;
+        const int stride = root ? 1 : nd.stride;
+        auto Tat = [&](int c, int p) { return root ? T[c] : T[(size_t)c * stride + p]; };
+        // the seed row: the state with the most non-zero entries (fewest accumulators left to zero)
+        int seed = 0, best = -1;
+        for (int c = 0; c < card; ++c) {
+            int nz = 0;
+            for (int p = 0; p < cols; ++p) nz += Tat(c, p) != 0.f;
+            if (nz > best) { best = nz; seed = c; }
+        }
+        std::vector<std::string> acc(cols);
+        std::vector<int> order;
+        order.push_back(seed);
+        for (int c = 0; c < card; ++c)
+            if (c != seed) order.push_back(c);
+        // dense rows: weights of this node, round_up(card,4)/4 vector loads
+        std::vector<std::string> wreg;
         if (dense) {
-            // weights of this node: round_up(card,4)/4 float4 loads from the query's row
-            for (int j = 0; j < (nd.card + 3) / 4; ++j)
-                line("    const float4 w" + I(v) + "_" + I(j) + " = __ldg(row + " + I(nd.lam_off / 4 + j) + ");");
+            for (int j = 0; j < (card + 3) / 4; ++j) {
+                std::string a = F(), b = F(), c2 = F(), d = F();
+                line("ld.global.nc.v4.f32 {" + a + ", " + b + ", " + c2 + ", " + d + "}, [%rrow+" + I(4LL * (nd.lam_off + 4 * j)) + "];");
+                wreg.push_back(a); wreg.push_back(b); wreg.push_back(c2); wreg.push_back(d);
+            }
         }
-        for (int c = 0; c < nd.card; ++c) {
-            ++n_elem;
-            std::string base = have_lam ? "l" + I(v) + "_" + I(c) : std::string();
-            std::string u;
+        for (int c : order) {
+            bool any = false;
+            for (int p = 0; p < cols; ++p) any |= Tat(c, p) != 0.f;
+            if (!any && c != seed) continue;
+            // lambda of this state, times the fan-out value when the query's fan bit is set
+            std::string lc = lam.empty() ? std::string() : lam[c];
+            if (fan) {
+                const std::string fv = fhex(m.fan[nd.fan_off + c]);
+                if (lc.empty()) {
+                    lc = F();
+                    line("selp.f32 " + lc + ", " + fv + ", 0f3F800000, " + pfb + ";");
+                } else {
+                    line("@" + pfb + " mul.f32 " + lc + ", " + lc + ", " + fv + ";");
+                }
+            }
             if (dense) {
-                static const char* comp[4] = {".x", ".y", ".z", ".w"};
-                u = "w" + I(v) + "_" + I(c / 4) + comp[c % 4];
-                if (fan) u = "(fb" + I(v) + " ? " + u + " * " + flit(m.fan[nd.fan_off + c]) + " : " + u + ")";
-                if (have_lam) u = u + " * " + base;
-            } else {
-                std::string val = have_lam ? base : "1.0f";
-                if (fan) {
-                    std::string fw = "(fb" + I(v) + " ? " + flit(m.fan[nd.fan_off + c]) + " : 1.0f)";
-                    val = have_lam ? base + " * " + fw : fw;
+                std::string u = wreg[c];
+                if (!lc.empty()) {
+                    u = F();
+                    line("mul.f32 " + u + ", " + wreg[c] + ", " + lc + ";");
                 }
-                u = sel(v, c) + " ? " + val + " : 0.f";
-            }
-            line("    { const float u = " + u + ";");
-            const float* T = m.arena.data() + nd.cpt_off;
-            if (root) {
-                if (T[c] != 0.f) { line("      r = fmaf(u, " + flit(T[c]) + ", r);"); ++n_ffma; }
-            } else {
-                const float* rowp = T + (size_t)c * nd.stride;
                 for (int p = 0; p < cols; ++p) {
-                    if (rowp[p] == 0.f) continue;
-                    line("      m" + I(v) + "_" + I(p) + " = fmaf(u, " + flit(rowp[p]) + ", m" + I(v) + "_" + I(p) + ");");
-                    ++n_ffma;
+                    const float t = Tat(c, p);
+                    if (c == seed) {
+                        acc[p] = F();
+                        if (t != 0.f) { line("mul.f32 " + acc[p] + ", " + u + ", " + fhex(t) + ";"); ++n_fma; }
+                        else line("mov.f32 " + acc[p] + ", 0f00000000;");
+                    } else if (t != 0.f) {
+                        line("fma.rn.f32 " + acc[p] + ", " + u + ", " + fhex(t) + ", " + acc[p] + ";");
+                        ++n_fma;
+                    }
+                }
+                continue;
+            }
+            const std::string pc = bit_pred(v, c);
+            if (c == seed) {
+                std::string u = F();
+                line("selp.f32 " + u + ", " + (lc.empty() ? std::string("0f3F800000") : lc) + ", 0f00000000, " + pc + ";");
+                for (int p = 0; p < cols; ++p) {
+                    const float t = Tat(c, p);
+                    acc[p] = F();
+                    if (t != 0.f) { line("mul.f32 " + acc[p] + ", " + u + ", " + fhex(t) + ";"); ++n_fma; }
+                    else line("mov.f32 " + acc[p] + ", 0f00000000;");
+                }
+            } else {
+                for (int p = 0; p < cols; ++p) {
+                    const float t = Tat(c, p);
+                    if (t == 0.f) continue;
+                    ++n_fma;
+                    if (lc.empty()) line("@" + pc + " add.f32 " + acc[p] + ", " + acc[p] + ", " + fhex(t) + ";");
+                    else line("@" + pc + " fma.rn.f32 " + acc[p] + ", " + lc + ", " + fhex(t) + ", " + acc[p] + ";");
                 }
             }
-            line("    }");
         }
+        return acc;
     }
 };
 
-std::string gen_kernel(const bc_model& m, bool dense, int threads, int min_blocks, long long* n_ffma) {
+std::string gen_kernel(const bc_model& m, bool dense, int threads, int min_blocks, long long* n_fma) {
     Gen g(m, dense);
-    g.emit_message(0);
-    if (n_ffma) *n_ffma = g.n_ffma;
+    const int words = m.bits_words;
+    if (!dense)
+        for (int w = 0; w < words; ++w) g.words.push_back(g.R());
+    for (int w = 0; w < m.mask_words; ++w) g.fmw.push_back(g.R());
+    const std::string res = g.message(0)[0];
+    if (n_fma) *n_fma = g.n_fma;
+
     std::string s;
-    const char* name = dense ? "bc_spec_dense" : "bc_spec_range8";
-    s += "// FFMA emitted: " + std::to_string(g.n_ffma) + "  weight elements: " + std::to_string(g.n_elem) + "\n";
-    s += std::string("extern \"C\" __global__ void __launch_bounds__(") + std::to_string(threads) + ", " +
-         std::to_string(min_blocks) + ") " + name +
-         "(const unsigned char* __restrict__ desc, unsigned long long stride, const unsigned* __restrict__ fmask, "
-         "float* __restrict__ out, unsigned long long nq)\n{\n";
-    s += "  const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x;\n";
-    s += "  for (unsigned long long q = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += step) {\n";
-    if (dense) {
-        s += "    const float4* __restrict__ row = reinterpret_cast<const float4*>(desc + q * stride);\n";
-    } else {
-        const int words = (int)(bc_round_up(2LL * m.n, 4) / 4);
-        s += "    const unsigned* __restrict__ dw = reinterpret_cast<const unsigned*>(desc + q * stride);\n";
-        for (int w = 0; w < words; ++w) s += "    const unsigned d" + std::to_string(w) + " = __ldg(dw + " + std::to_string(w) + ");\n";
-    }
+    const char* name = dense ? "bc_spec_dense" : "bc_spec_bits";
+    s += std::string(".visible .entry ") + name +
+         "(\n    .param .u64 p_desc,\n    .param .u64 p_stride,\n    .param .u64 p_fmask,\n    .param .u64 p_out,\n"
+         "    .param .u64 p_nq\n)\n.maxntid " + I(threads) + ", 1, 1\n.minnctapersm " + I(min_blocks) + "\n{\n";
+    s += "    .reg .pred %p<" + I(g.np + 1) + ">;\n    .reg .pred %pfm, %pdone;\n";
+    s += "    .reg .f32 %f<" + I(g.nf + 1) + ">;\n    .reg .b32 %r<" + I(g.nr + 1) + ">;\n";
+    s += "    .reg .b32 %t0, %t1, %t2, %t3, %t4;\n";
+    s += "    .reg .b64 %rdesc, %rstride, %rfmask, %rout, %rnq, %rq, %rstep, %rtmp, %rrow;\n";
+    auto e = [&](const std::string& x) { s += "    " + x + "\n"; };
+    e("ld.param.u64 %rdesc, [p_desc];");
+    e("ld.param.u64 %rstride, [p_stride];");
+    e("ld.param.u64 %rfmask, [p_fmask];");
+    e("ld.param.u64 %rout, [p_out];");
+    e("ld.param.u64 %rnq, [p_nq];");
+    e("cvta.to.global.u64 %rdesc, %rdesc;");
+    e("cvta.to.global.u64 %rout, %rout;");
+    e("setp.ne.u64 %pfm, %rfmask, 0;");
+    e("@%pfm cvta.to.global.u64 %rfmask, %rfmask;");
+    // query index of round k:  ((k * warps_per_cta + warp) * n_cta + cta) * 32 + lane.
+    // Consecutive warp slots belong to DIFFERENT CTAs, so the last, partial round is spread over all
+    // CTAs (and SMs) instead of filling the first ones only.
+    e("mov.u32 %t0, %tid.x;");
+    e("mov.u32 %t1, %ctaid.x;");
+    e("mov.u32 %t2, %ntid.x;");
+    e("mov.u32 %t3, %nctaid.x;");
+    e("shr.u32 %t4, %t0, 5;");
+    e("mad.lo.u32 %t4, %t4, %t3, %t1;");
+    e("and.b32 %t0, %t0, 31;");
+    e("mul.wide.u32 %rq, %t4, 32;");
+    e("cvt.u64.u32 %rtmp, %t0;");
+    e("add.u64 %rq, %rq, %rtmp;");
+    e("mul.wide.u32 %rstep, %t2, %t3;");
+    s += "LOOP:\n";
+    e("setp.ge.u64 %pdone, %rq, %rnq;");
+    e("@%pdone bra DONE;");
+    e("mad.lo.u64 %rrow, %rq, %rstride, %rdesc;");
+    if (!dense)
+        for (int w = 0; w < words; w += 4)
+            e("ld.global.nc.v4.u32 {" + g.words[w] + ", " + g.words[w + 1] + ", " + g.words[w + 2] + ", " + g.words[w + 3] +
+              "}, [%rrow+" + I(4LL * w) + "];");
     if (g.any_fan) {
-        for (int w = 0; w < m.mask_words; ++w)
-            s += "    const unsigned fm" + std::to_string(w) + " = fmask ? __ldg(fmask + q * " + std::to_string(m.mask_words) +
-                 "ull + " + std::to_string(w) + ") : 0u;\n";
+        e("mad.lo.u64 %rtmp, %rq, " + I(4LL * m.mask_words) + ", %rfmask;");
+        for (int w = 0; w < m.mask_words; ++w) {
+            e("mov.u32 " + g.fmw[w] + ", 0;");
+            e("@%pfm ld.global.nc.u32 " + g.fmw[w] + ", [%rtmp+" + I(4LL * w) + "];");
+        }
     }
     s += g.out;
-    s += "    out[q] = r;\n  }\n}\n\n";
+    e("shl.b64 %rtmp, %rq, 2;");
+    e("add.u64 %rtmp, %rtmp, %rout;");
+    e("st.global.f32 [%rtmp], " + res + ";");
+    e("add.u64 %rq, %rq, %rstep;");
+    e("bra LOOP;");
+    s += "DONE:\n    ret;\n}\n\n";
     return s;
 }
 
 }  // namespace
 
 // Thread count / occupancy target of the generated kernels.  Register need grows with the widest
-// pair of (node, parent) domains on a root-to-leaf path; 128 threads x up to 255 registers always
-// fits, small trees get more resident warps.
+// (node, parent) pair of domains on a root-to-leaf path.  Measured on B200 (profiles/r1_spec_v2_sweep.txt):
+// small trees like 256-thread CTAs with <= 85 registers; DMV-sized ones want all 255 registers and no
+// spills; beyond that three resident CTAs with a few spilled values beat two without.
 void bc_spec_geometry(const bc_model& m, int* threads, int* min_blocks) {
     int widest = 0;
     for (int v = 1; v < m.n; ++v) widest = std::max(widest, m.nodes[v].card + m.nodes[v].card_pa);
-    *threads = 128;
-    if (widest <= 40) *min_blocks = 4;        // <= 128 regs/thread
-    else if (widest <= 72) *min_blocks = 3;   // <= 168
-    else *min_blocks = 2;                     // <= 255
+    if (widest <= 40) { *threads = 256; *min_blocks = 3; }
+    else if (widest <= 110) { *threads = 128; *min_blocks = 2; }
+    else { *threads = 128; *min_blocks = 3; }
 }
 
 std::string bc_spec_generate(const bc_model& m) {
@@ -194,12 +271,13 @@ std::string bc_spec_generate(const bc_model& m) {
     std::string k1 = gen_kernel(m, false, threads, min_blocks, &f1);
     std::string k2 = gen_kernel(m, true, threads, min_blocks, &f2);
     std::string s;
-    s += "// Generated by bayescard_b200 spec_codegen (version " + std::to_string(BC_CODEGEN_VERSION) + ") -- do not edit.\n";
-    s += "// nodes: " + std::to_string(m.n) + "  dense flop/query: " + std::to_string(m.flops_dense) +
-         "  executed flop/query: " + std::to_string(2 * f1) + "\n";
-    s += "// BC_SPEC_THREADS=" + std::to_string(threads) + " BC_SPEC_MIN_BLOCKS=" + std::to_string(min_blocks) +
-         " BC_SPEC_FFMA=" + std::to_string(f1) + "\n";
-    if (m.max_card <= 256) s += k1;
+    s += "//\n// Generated by bayescard_b200 spec_codegen (version " + I(BC_CODEGEN_VERSION) + ") -- do not edit.\n";
+    s += "// nodes: " + I(m.n) + "  dense flop/query: " + I(m.flops_dense) + "  executed flop/query: " + I(2 * f1) + "\n";
+    s += "// BC_SPEC_THREADS=" + I(threads) + " BC_SPEC_MIN_BLOCKS=" + I(min_blocks) + " BC_SPEC_FFMA=" + I(f1) + "\n//\n";
+    s += ".version 8.7\n.target sm_100a\n.address_size 64\n\n";
+    // geometry travels with the image: {threads per CTA, queries per thread and trip, codegen version, 0}
+    s += ".visible .global .align 4 .u32 bc_spec_meta[4] = {" + I(threads) + ", 1, " + I(BC_CODEGEN_VERSION) + ", 0};\n\n";
+    s += k1;
     s += k2;
     return s;
 }

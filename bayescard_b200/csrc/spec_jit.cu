@@ -1,7 +1,8 @@
-// K-spec runtime: compile the generated source with NVRTC (dlopen'ed, never linked), cache the
-// cubin on disk, load it with cudaLibraryLoadData and launch it.
-#include <dlfcn.h>
-
+// K-spec runtime: obtain the per-model image and launch it.
+//
+// bc_model_specialize() looks for an ahead-of-time cubin ("<cache_dir>/spec_<hash>.cubin", written by
+// bayescard_b200/aot.py with `ptxas -arch=sm_100a`) and otherwise hands the generated PTX to the
+// driver's JIT through cudaLibraryLoadData -- no NVRTC, no compiler on the serving box.
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
@@ -11,42 +12,6 @@
 void bc_spec_geometry(const bc_model& m, int* threads, int* min_blocks);
 
 namespace {
-
-typedef struct _nvrtcProgram* nvrtcProgram;
-struct Nvrtc {
-    void* h = nullptr;
-    int (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*);
-    int (*CompileProgram)(nvrtcProgram, int, const char* const*);
-    int (*GetCUBINSize)(nvrtcProgram, size_t*);
-    int (*GetCUBIN)(nvrtcProgram, char*);
-    int (*GetProgramLogSize)(nvrtcProgram, size_t*);
-    int (*GetProgramLog)(nvrtcProgram, char*);
-    int (*DestroyProgram)(nvrtcProgram*);
-    const char* (*GetErrorString)(int);
-};
-
-bool load_nvrtc(Nvrtc& n) {
-    static const char* names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12",
-                                  "/usr/local/cuda/lib64/libnvrtc.so"};
-    for (const char* nm : names) {
-        n.h = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
-        if (n.h) break;
-    }
-    if (!n.h) return false;
-#define SYM(field, sym)                                             \
-    *(void**)(&n.field) = dlsym(n.h, sym);                          \
-    if (!n.field) return false;
-    SYM(CreateProgram, "nvrtcCreateProgram")
-    SYM(CompileProgram, "nvrtcCompileProgram")
-    SYM(GetCUBINSize, "nvrtcGetCUBINSize")
-    SYM(GetCUBIN, "nvrtcGetCUBIN")
-    SYM(GetProgramLogSize, "nvrtcGetProgramLogSize")
-    SYM(GetProgramLog, "nvrtcGetProgramLog")
-    SYM(DestroyProgram, "nvrtcDestroyProgram")
-    SYM(GetErrorString, "nvrtcGetErrorString")
-#undef SYM
-    return true;
-}
 
 std::string cache_path(const bc_model& m, const char* dir) {
     char name[64];
@@ -59,38 +24,57 @@ std::string cache_path(const bc_model& m, const char* dir) {
 int bc_spec_attach(bc_model* m, const void* image, size_t bytes) {
     BC_CUDA_CHECK(cudaSetDevice(m->device));
     cudaLibrary_t lib = nullptr;
-    // the image must outlive the library only for the duration of the call (it is copied)
-    cudaError_t e = cudaLibraryLoadData(&lib, image, nullptr, nullptr, 0, nullptr, nullptr, 0);
+    // cubin (ELF) or NUL-terminated PTX; the image is copied by the driver during the call
+    char log[4096] = "";
+    cudaJitOption opts[] = {cudaJitErrorLogBuffer, cudaJitErrorLogBufferSizeBytes};
+    void* vals[] = {log, (void*)(uintptr_t)sizeof(log)};
+    cudaError_t e = cudaLibraryLoadData(&lib, image, opts, vals, 2, nullptr, nullptr, 0);
     if (e != cudaSuccess) {
-        bc_set_error("cudaLibraryLoadData failed: %s", cudaGetErrorString(e));
-        return BC_ECUDA;
+        bc_set_error("cudaLibraryLoadData failed: %s %.600s", cudaGetErrorString(e), log);
+        cudaGetLastError();
+        return BC_ECOMPILE;
     }
-    cudaKernel_t kr = nullptr, kd = nullptr;
-    e = cudaLibraryGetKernel(&kd, lib, "bc_spec_dense");
-    if (e != cudaSuccess) {
-        bc_set_error("specialised image has no bc_spec_dense: %s", cudaGetErrorString(e));
+    // an image may hold any subset of the entry points; formats without one use the generic kernel
+    cudaKernel_t kr = nullptr, kd = nullptr, kb = nullptr;
+    if (cudaLibraryGetKernel(&kd, lib, "bc_spec_dense") != cudaSuccess) { kd = nullptr; cudaGetLastError(); }
+    if (cudaLibraryGetKernel(&kr, lib, "bc_spec_range8") != cudaSuccess) { kr = nullptr; cudaGetLastError(); }
+    if (cudaLibraryGetKernel(&kb, lib, "bc_spec_bits") != cudaSuccess) { kb = nullptr; cudaGetLastError(); }
+    if (!kd && !kr && !kb) {
+        bc_set_error("specialised image has none of bc_spec_bits / bc_spec_range8 / bc_spec_dense");
         cudaLibraryUnload(lib);
         return BC_ECUDA;
     }
-    if (m->max_card <= 256) {
-        e = cudaLibraryGetKernel(&kr, lib, "bc_spec_range8");
-        if (e != cudaSuccess) {
-            bc_set_error("specialised image has no bc_spec_range8: %s", cudaGetErrorString(e));
-            cudaLibraryUnload(lib);
-            return BC_ECUDA;
-        }
+    // geometry travels with the image: {threads per CTA, queries per thread and trip, version, 0}
+    uint32_t meta[4] = {128, 1, 0, 0};
+    void* dptr = nullptr;
+    size_t gbytes = 0;
+    if (cudaLibraryGetGlobal(&dptr, &gbytes, lib, "bc_spec_meta") == cudaSuccess && gbytes >= sizeof(meta))
+        BC_CUDA_CHECK(cudaMemcpy(meta, dptr, sizeof(meta), cudaMemcpyDeviceToHost));
+    else
+        cudaGetLastError();
+    if (meta[0] == 0 || meta[0] > 1024 || meta[0] % 32) {
+        bc_set_error("specialised image declares %u threads per CTA", meta[0]);
+        cudaLibraryUnload(lib);
+        return BC_ECUDA;
     }
     if (m->spec_lib) cudaLibraryUnload(m->spec_lib);
     m->spec_lib = lib;
     m->spec_range8 = kr;
     m->spec_dense = kd;
-    bc_spec_geometry(*m, &m->spec_threads, &m->spec_min_blocks);
-    int nb = 0;
-    if (kr && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)kr, m->spec_threads, 0) == cudaSuccess &&
-        nb > 0)
-        m->spec_min_blocks = nb;
-    else
-        cudaGetLastError();
+    m->spec_bits = kb;
+    m->spec_threads = (int)meta[0];
+    m->spec_qpt = meta[1] ? (int)meta[1] : 1;
+    auto blocks_of = [&](cudaKernel_t k) {
+        int nb = 0;
+        if (!k || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)k, m->spec_threads, 0) != cudaSuccess || nb <= 0) {
+            cudaGetLastError();
+            nb = 1;
+        }
+        return nb;
+    };
+    m->spec_blocks_bits = blocks_of(kb);
+    m->spec_blocks_dense = blocks_of(kd);
+    m->spec_blocks_range8 = blocks_of(kr);
     return BC_OK;
 }
 
@@ -99,53 +83,20 @@ int bc_spec_build(bc_model* m, const char* cache_dir) {
         bc_set_error("model too large for a specialised kernel");
         return BC_ELIMIT;
     }
-    std::string path;
     if (cache_dir && *cache_dir) {
-        path = cache_path(*m, cache_dir);
-        std::ifstream f(path, std::ios::binary);
+        std::ifstream f(cache_path(*m, cache_dir), std::ios::binary);
         if (f) {
             std::string img((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
             if (!img.empty() && bc_spec_attach(m, img.data(), img.size()) == BC_OK) return BC_OK;
         }
     }
-    Nvrtc n{};
-    if (!load_nvrtc(n)) {
-        bc_set_error("NVRTC (libnvrtc.so.12) could not be loaded: %s", dlerror() ? dlerror() : "missing symbols");
-        return BC_ECOMPILE;
-    }
-    const std::string src = bc_spec_generate(*m);
-    nvrtcProgram prog = nullptr;
-    int rc = n.CreateProgram(&prog, src.c_str(), "bc_spec.cu", 0, nullptr, nullptr);
-    if (rc) {
-        bc_set_error("nvrtcCreateProgram: %s", n.GetErrorString(rc));
-        return BC_ECOMPILE;
-    }
-    const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "--fmad=true"};
-    rc = n.CompileProgram(prog, 4, opts);
-    if (rc) {
-        size_t ls = 0;
-        n.GetProgramLogSize(prog, &ls);
-        std::string log(ls + 1, 0);
-        if (ls) n.GetProgramLog(prog, &log[0]);
-        bc_set_error("NVRTC compile failed (%s): %.800s", n.GetErrorString(rc), log.c_str());
-        n.DestroyProgram(&prog);
-        return BC_ECOMPILE;
-    }
-    size_t cs = 0;
-    n.GetCUBINSize(prog, &cs);
-    std::string cubin(cs, 0);
-    n.GetCUBIN(prog, &cubin[0]);
-    n.DestroyProgram(&prog);
-    if (!path.empty()) {
-        std::ofstream f(path, std::ios::binary);
-        if (f) f.write(cubin.data(), (std::streamsize)cubin.size());
-    }
-    return bc_spec_attach(m, cubin.data(), cubin.size());
+    const std::string ptx = bc_spec_generate(*m);  // std::string::c_str() is NUL terminated
+    return bc_spec_attach(m, ptx.c_str(), ptx.size() + 1);
 }
 
 int bc_spec_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32_t* fan_mask, float* out,
                    cudaStream_t stream) {
-    cudaKernel_t k = fmt == BC_DESC_DENSE_F32 ? m->spec_dense : m->spec_range8;
+    cudaKernel_t k = fmt == BC_DESC_DENSE_F32 ? m->spec_dense : fmt == BC_DESC_BITS ? m->spec_bits : m->spec_range8;
     if (!k) {
         bc_set_error("no specialised kernel for descriptor format %d", fmt);
         return BC_ECOMPILE;
@@ -155,8 +106,11 @@ int bc_spec_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint
     unsigned long long n = nq;
     void* args[] = {(void*)&d, (void*)&stride, (void*)&fan_mask, (void*)&out, (void*)&n};
     const int threads = m->spec_threads;
-    long long grid = (long long)m->sm_count * m->spec_min_blocks;
-    const long long needed = (long long)((nq + threads - 1) / threads);
+    const size_t per_cta = (size_t)threads * m->spec_qpt;
+    const int resident = fmt == BC_DESC_DENSE_F32 ? m->spec_blocks_dense : fmt == BC_DESC_BITS ? m->spec_blocks_bits : m->spec_blocks_range8;
+    // persistent grid: a whole number of CTAs per SM; smaller batches get one CTA per 'per_cta' queries
+    long long grid = (long long)m->sm_count * resident;
+    const long long needed = (long long)((nq + per_cta - 1) / per_cta);
     if (grid > needed) grid = needed;
     BC_CUDA_CHECK(cudaLaunchKernel((const void*)k, dim3((unsigned)grid), dim3(threads), args, 0, stream));
     bc_count_launch();

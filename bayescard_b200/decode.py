@@ -16,11 +16,12 @@ Stage 1 (:meth:`PredicateCompiler.decode`) has the semantics of ``Bayescard_BN.q
 
 Unlike the reference nothing is mutated: ``decode`` returns fresh dicts.
 
-Stage 2 (:meth:`PredicateCompiler.pack`) writes descriptors for the CUDA kernels: the compact
-``RANGE_U8`` row when every predicate of a query is a contiguous bin interval with unit weights
-(89 % / 83 % of the shipped DMV / Census predicates), the dense fp32 weight row otherwise; fan-out
-columns of ``expectation`` become a bitmask (a predicate on the same column clears the bit, because the
-reference tests the predicate first: ``Pgmpy/inference/ExactInference.py:209,:238``).
+Stage 2 (:meth:`PredicateCompiler.pack`) writes descriptors for the CUDA kernels: a ``BITS`` row (one
+bit per column state) when every weight of a query is 1 -- ranges, equality and IN lists, 96 % of the
+shipped DMV predicates -- and the dense fp32 weight row otherwise; fan-out columns of ``expectation``
+become a bitmask (a predicate on the same column clears the bit, because the reference tests the
+predicate first: ``Pgmpy/inference/ExactInference.py:209,:238``).  :meth:`pack_sparse` writes the
+compact CSR form the host-buffer entry point ships over PCIe.
 """
 from __future__ import annotations
 
@@ -207,53 +208,54 @@ class PredicateCompiler:
         return bins_out, wts_out
 
     # ------------------------------------------------------------------ stage 2
-    def _is_unit_range(self, b: Sequence[int], w: np.ndarray) -> Optional[Tuple[int, int]]:
-        if len(b) == 0:
-            return (1, 0)  # selects nothing
-        lo, hi = min(b), max(b)
-        if hi - lo + 1 != len(b) or len(set(b)) != len(b):
-            return None
+    @staticmethod
+    def _unit_bins(b: Sequence[int], w) -> bool:
+        """True when the selected bins all carry weight exactly 1 and none repeats."""
+        if len(set(b)) != len(b):
+            return False
         w = np.asarray(w, dtype=np.float64).reshape(-1)
-        if w.size == 1 and len(b) > 1:
-            return (lo, hi) if w[0] == 1 else None
-        return (lo, hi) if np.all(w == 1) else None
+        return bool(np.all(w == 1))
+
+    def geometry(self):
+        """(bit offsets int64[n], BITS row bytes, dense offsets int64[n], dense width) -- same rules as the C ABI."""
+        card = self.tm.card.astype(np.int64)
+        bit_off = np.concatenate([[0], np.cumsum(card)[:-1]]).astype(np.int64)
+        row_bytes = -(-int(card.sum()) // 128) * 16
+        pad = -(-card // 4) * 4
+        dense_off = np.concatenate([[0], np.cumsum(pad)[:-1]]).astype(np.int64)
+        return bit_off, row_bytes, dense_off, int(pad.sum())
 
     def pack(self, decoded: Sequence[Tuple[Dict[str, Sequence[int]], Dict[str, np.ndarray]]],
              fanouts: Optional[Sequence[Sequence[str]]] = None, force_dense: bool = False):
         """Pack already decoded queries.
 
-        Returns ``(range_idx, range_desc, dense_idx, dense_desc, mask)``: indices of the queries that
-        went to the ``RANGE_U8`` / ``DENSE_F32`` batch, the two descriptor arrays and the fan-out
-        bitmask rows (``None`` when no query has fan-out columns), all in input order within a batch.
-        Columns outside the root component are ignored, as the reference's Steiner walk never sees them.
+        Returns ``(bits_idx, bits_desc, dense_idx, dense_desc, mask)``: indices of the queries that
+        went to the ``BITS`` / ``DENSE_F32`` batch, the two descriptor arrays (uint8 rows / fp32 rows)
+        and the fan-out bitmask rows (``None`` when no query has fan-out columns), all in input order
+        within a batch.  Columns outside the root component are ignored, as the reference's Steiner
+        walk never sees them.
         """
         tm = self.tm
         n = tm.n_nodes
         nq = len(decoded)
-        stride = -(-2 * n // 4) * 4
-        width = int(sum(-(-int(c) // 4) * 4 for c in tm.card))
-        off = np.concatenate([[0], np.cumsum([-(-int(c) // 4) * 4 for c in tm.card])[:-1]]).astype(np.int64)
-        allow_range = (not force_dense) and int(tm.card.max()) <= 256
-        base_row = np.zeros(stride, dtype=np.uint8)
-        base_row[1:2 * n:2] = np.minimum(tm.card - 1, 255).astype(np.uint8)
+        bit_off, row_bytes, off, width = self.geometry()
+        total_bits = int(tm.card.sum())
         words = (n + 31) // 32
         mask = np.zeros((nq, words), dtype=np.uint32) if fanouts is not None else None
-        kinds = np.zeros(nq, dtype=np.int8)  # 0 = range, 1 = dense
-        range_rows: List[np.ndarray] = []
+        kinds = np.zeros(nq, dtype=np.int8)  # 0 = bits, 1 = dense
+        bit_rows: List[np.ndarray] = []
         dense_rows: List[np.ndarray] = []
         for qi, (bins, wts) in enumerate(decoded):
-            ranges = {}
-            ok = allow_range
+            cols = []
+            ok = not force_dense
             for attr, b in bins.items():
                 v = tm._index.get(attr)
                 if v is None:
                     continue
                 bl = list(b) if isinstance(b, (list, tuple, np.ndarray)) else [b]
-                r = self._is_unit_range(bl, wts[attr]) if ok else None
-                if r is None:
+                cols.append((v, bl, wts[attr]))
+                if ok and not self._unit_bins(bl, wts[attr]):
                     ok = False
-                    break
-                ranges[v] = r
             if fanouts is not None:
                 for attr in fanouts[qi]:
                     v = tm._index.get(attr)
@@ -261,21 +263,19 @@ class PredicateCompiler:
                         continue
                     mask[qi, v >> 5] |= np.uint32(1 << (v & 31))
             if ok:
-                row = base_row.copy()
-                for v, (lo, hi) in ranges.items():
-                    row[2 * v], row[2 * v + 1] = lo, hi
-                range_rows.append(row)
+                row = np.ones(total_bits, dtype=bool)
+                for v, bl, _ in cols:
+                    row[bit_off[v]: bit_off[v] + int(tm.card[v])] = False
+                    if len(bl):
+                        row[bit_off[v] + np.asarray(bl, dtype=np.int64)] = True
+                bit_rows.append(row)
             else:
                 kinds[qi] = 1
                 row = np.zeros(width, dtype=np.float32)
                 for v in range(n):
                     row[off[v]: off[v] + int(tm.card[v])] = 1.0
-                for attr, b in bins.items():
-                    v = tm._index.get(attr)
-                    if v is None:
-                        continue
-                    bl = list(b) if isinstance(b, (list, tuple, np.ndarray)) else [b]
-                    w = np.asarray(wts[attr], dtype=np.float64).reshape(-1)
+                for v, bl, w in cols:
+                    w = np.asarray(w, dtype=np.float64).reshape(-1)
                     seg = np.zeros(int(tm.card[v]), dtype=np.float64)
                     if len(bl):
                         if w.size == 1 and len(bl) > 1:
@@ -283,11 +283,44 @@ class PredicateCompiler:
                         np.add.at(seg, np.asarray(bl, dtype=np.int64), w)
                     row[off[v]: off[v] + int(tm.card[v])] = seg
                 dense_rows.append(row)
-        range_idx = np.nonzero(kinds == 0)[0]
+        bits_idx = np.nonzero(kinds == 0)[0]
         dense_idx = np.nonzero(kinds == 1)[0]
-        range_desc = np.stack(range_rows) if range_rows else np.zeros((0, stride), dtype=np.uint8)
+        bits_desc = np.zeros((len(bit_rows), row_bytes), dtype=np.uint8)
+        if bit_rows:
+            packed = np.packbits(np.stack(bit_rows), axis=1, bitorder="little")
+            bits_desc[:, : packed.shape[1]] = packed
         dense_desc = np.stack(dense_rows) if dense_rows else np.zeros((0, width), dtype=np.float32)
-        return range_idx, range_desc, dense_idx, dense_desc, mask
+        return bits_idx, bits_desc, dense_idx, dense_desc, mask
+
+    def pack_sparse(self, lo: np.ndarray, hi: np.ndarray):
+        """SPARSE (CSR) form of ``[B, n_nodes]`` bin bounds: ``(row_off uint32[B+1], entries uint32[...])``.
+
+        One entry ``col | lo<<16 | hi<<24`` per column whose bounds are narrower than its domain,
+        ascending column order.  Vectorised; needs every domain <= 256 states."""
+        card = self.tm.card.astype(np.int64)
+        if int(card.max()) > 256:
+            raise ValueError("SPARSE entries hold 8-bit state bounds")
+        lo = np.asarray(lo, dtype=np.int64)
+        hi = np.asarray(hi, dtype=np.int64)
+        con = (lo > 0) | (hi < card[None, :] - 1)
+        row_off = np.zeros(lo.shape[0] + 1, dtype=np.uint32)
+        np.cumsum(con.sum(axis=1), out=row_off[1:])
+        qi, vi = np.nonzero(con)  # row-major: ascending query, then ascending column
+        entries = (vi.astype(np.uint32) | (lo[qi, vi].astype(np.uint32) << 16) | (hi[qi, vi].astype(np.uint32) << 24))
+        return row_off, entries.astype(np.uint32)
+
+    def pack_bits(self, lo: np.ndarray, hi: np.ndarray) -> np.ndarray:
+        """Vectorised BITS packing of ``[B, n_nodes]`` bin bounds (uint8 rows)."""
+        bit_off, row_bytes, _, _ = self.geometry()
+        card = self.tm.card.astype(np.int64)
+        cols = []
+        for v in range(self.tm.n_nodes):
+            c = np.arange(int(card[v]))[None, :]
+            cols.append((c >= np.asarray(lo)[:, v:v + 1]) & (c <= np.asarray(hi)[:, v:v + 1]))
+        packed = np.packbits(np.concatenate(cols, axis=1), axis=1, bitorder="little")
+        out = np.zeros((packed.shape[0], row_bytes), dtype=np.uint8)
+        out[:, : packed.shape[1]] = packed
+        return out
 
     def pack_ranges(self, lo: np.ndarray, hi: np.ndarray) -> np.ndarray:
         """Vectorised RANGE_U8 packing of ``[B, n_nodes]`` bin bounds (topological node order)."""

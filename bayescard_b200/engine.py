@@ -36,6 +36,7 @@ class DeviceModel:
         self.mask_words = (tm.n_nodes + 31) // 32
         self.dense_width = int(lib.bc_model_dense_width(h))
         self.dense_offset = np.array([lib.bc_model_dense_offset(h, v) for v in range(tm.n_nodes)], dtype=np.int64)
+        self.bits_offset = np.array([lib.bc_model_bits_offset(h, v) for v in range(tm.n_nodes)], dtype=np.int64)
         self.flops_dense = int(lib.bc_model_flops_dense(h))
         self.max_card = int(card.max())
         self.spec_error: Optional[str] = None
@@ -87,6 +88,13 @@ class DeviceModel:
                 return int(line.split("BC_SPEC_FFMA=")[1].split()[0])
         raise L.BayesCardError("generated source has no BC_SPEC_FFMA header")
 
+    def load_image(self, image: bytes) -> None:
+        """Attach a compiled specialised image (cubin, or PTX text for the driver JIT)."""
+        if not image.endswith(b"\0") and image[:4] != b"\x7fELF":
+            image = image + b"\0"  # PTX must be NUL terminated
+        buf = C.create_string_buffer(image, len(image))
+        L.check(L.lib().bc_model_load_cubin(self._h, buf, len(image)))
+
     # ------------------------------------------------------------------ geometry
     def desc_stride(self, fmt: int) -> int:
         s = int(L.lib().bc_model_desc_stride(self._h, fmt))
@@ -117,6 +125,46 @@ class DeviceModel:
         L.check(L.lib().bc_query_batch_host(self._h, desc.ctypes.data, n, fmt,
                                             mask.ctypes.data if mask is not None else None, out.ctypes.data, kernel))
         return out
+
+    def bits_default(self) -> np.ndarray:
+        row = np.zeros(self.desc_stride(L.DESC_BITS) // 4, dtype=np.uint32)
+        L.check(L.lib().bc_model_bits_default(self._h, row.ctypes.data, row.nbytes))
+        return row
+
+    def convert_device(self, src_ptr: int, src_fmt: int, dst_ptr: int, dst_fmt: int, n: int, stream: int = 0) -> None:
+        """Stream-ordered descriptor conversion on DEVICE buffers (RANGE_U8 / RANGE_U16 -> BITS)."""
+        L.check(L.lib().bc_convert_desc(self._h, src_ptr, src_fmt, dst_ptr, dst_fmt, n, stream or None))
+
+    def expand_sparse_device(self, row_off_ptr: int, entries_ptr: int, n: int, dst_ptr: int, stream: int = 0) -> None:
+        L.check(L.lib().bc_expand_sparse(self._h, row_off_ptr, entries_ptr, n, dst_ptr, stream or None))
+
+    def run_sparse_host(self, row_off: np.ndarray, entries: np.ndarray, mask: Optional[np.ndarray] = None,
+                        kernel: int = L.KERNEL_AUTO, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """SPARSE (CSR) queries from host buffers: H2D, expand to BITS, infer, D2H -- pipelined in the library."""
+        row_off = np.ascontiguousarray(row_off, dtype=np.uint32)
+        entries = np.ascontiguousarray(entries, dtype=np.uint32)
+        n = row_off.size - 1
+        if n < 0 or (n > 0 and int(row_off[-1]) > entries.size):
+            raise ValueError("row_off does not match the entries array")
+        if mask is not None:
+            mask = np.ascontiguousarray(mask, dtype=np.uint32)
+            if mask.size != n * self.mask_words:
+                raise ValueError("fan-out mask has the wrong size")
+        if out is None:
+            out = np.empty(n, dtype=np.float32)
+        L.check(L.lib().bc_query_batch_sparse_host(self._h, row_off.ctypes.data, entries.ctypes.data if entries.size else None,
+                                                   n, mask.ctypes.data if mask is not None else None, out.ctypes.data,
+                                                   kernel))
+        return out
+
+    def gen_sparse_queries_host(self, seed: int, first: int, n: int, kmin: int, kmax: int):
+        card = np.ascontiguousarray(self.tm.card, dtype=np.int32)
+        row_off = np.zeros(n + 1, dtype=np.uint32)
+        entries = np.zeros(max(1, n * min(kmax, self.n_nodes)), dtype=np.uint32)
+        ne = C.c_size_t()
+        L.check(L.lib().bc_gen_sparse_queries_host(self.n_nodes, card.ctypes.data, seed, first, n, kmin, kmax,
+                                                   row_off.ctypes.data, entries.ctypes.data, C.byref(ne)))
+        return row_off, entries[: ne.value]
 
     def gen_range_queries_device(self, seed: int, first: int, n: int, kmin: int, kmax: int, desc_ptr: int,
                                  stream: int = 0) -> None:

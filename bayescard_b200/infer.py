@@ -41,9 +41,9 @@ class VariableEliminationB200:
         out = np.zeros(nq, dtype=np.float64)
         if nq == 0:
             return out
-        r_idx, r_desc, d_idx, d_desc, mask = self.compiler.pack(decoded, fanouts)
-        if len(r_idx):
-            out[r_idx] = self.dev.run_host(r_desc, L.DESC_RANGE_U8, None if mask is None else mask[r_idx], self.kernel)
+        b_idx, b_desc, d_idx, d_desc, mask = self.compiler.pack(decoded, fanouts)
+        if len(b_idx):
+            out[b_idx] = self.dev.run_host(b_desc, L.DESC_BITS, None if mask is None else mask[b_idx], self.kernel)
         if len(d_idx):
             out[d_idx] = self.dev.run_host(d_desc, L.DESC_DENSE_F32, None if mask is None else mask[d_idx], self.kernel)
         return out

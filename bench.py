@@ -11,9 +11,11 @@ every rank runs the same per-GPU batch on its own replica of the CPT arena (weak
 has no exchange step, so no collective runs inside the timed region -- NCCL is used for the barrier
 and the max-over-ranks reduction only).
 
-  value      whole-job q/s, descriptors already resident in HBM, CUDA events around K steps
-  e2e        same metric through the host-buffer C-ABI call (bc_query_batch_host): pinned host
-             descriptors -> H2D -> kernel -> D2H of the fp32 results, all inside the timed region
+  value      whole-job q/s, BITS descriptors (one bit per column state) already resident in HBM,
+             CUDA events around K steps
+  e2e        same metric through the host-buffer C-ABI call (bc_query_batch_sparse_host): pinned host
+             SPARSE (CSR) queries -> H2D -> expand to BITS -> kernel -> D2H of the fp32 results, all
+             inside the timed region
   roofline   dominant kernel vs the FP32 FFMA peak measured in this same run (the kernel keeps the
              CPTs in the instruction stream, so HBM is not its bound; the HBM view is reported too)
   cpu_baseline  the oracle port of the reference algorithm (numpy fp64, per query, as the reference
@@ -235,15 +237,25 @@ def run_ours(args):
     if kernel != L.KERNEL_GENERIC and not dm.has_spec:
         raise SystemExit("specialised kernel unavailable: " + str(dm.spec_error))
     B = args.batch
-    stride = dm.desc_stride(L.DESC_RANGE_U8)
-    NBUF = 4  # rotate over 4 resident batches: the working set (4 x B x stride) is far larger than L2
+    rstride = dm.desc_stride(L.DESC_RANGE_U8)
+    spec = kernel != L.KERNEL_GENERIC
+    fmt = L.DESC_BITS
+    stride = dm.desc_stride(fmt)
+    NBUF = 4  # rotate over 4 resident batches: the working set (4 x B x stride) is larger than L2
     stream = torch.cuda.current_stream()
     st = stream.cuda_stream
+    # seeded queries are generated on the device as RANGE_U8 rows (the form the host twin of the generator
+    # and the oracle read) and converted once, outside the timed region, to the resident BITS rows
+    ranges0 = torch.empty((B, rstride), dtype=torch.uint8, device=dev)
+    tmp = torch.empty((B, rstride), dtype=torch.uint8, device=dev)
     descs = [torch.empty((B, stride), dtype=torch.uint8, device=dev) for _ in range(NBUF)]
     out = torch.empty(B, dtype=torch.float32, device=dev)
     for b, d in enumerate(descs):
-        dm.gen_range_queries_device(SEED, (rank * NBUF + b) * B, B, KMIN, KMAX, d.data_ptr(), st)
+        r = ranges0 if b == 0 else tmp
+        dm.gen_range_queries_device(SEED, (rank * NBUF + b) * B, B, KMIN, KMAX, r.data_ptr(), st)
+        dm.convert_device(r.data_ptr(), L.DESC_RANGE_U8, d.data_ptr(), fmt, B, st)
     torch.cuda.synchronize()
+    del tmp
 
     def barrier():
         if dist is not None:
@@ -251,7 +263,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def step(k):
-        dm.run_device(descs[k % NBUF].data_ptr(), B, L.DESC_RANGE_U8, out.data_ptr(), kernel=kernel, stream=st)
+        dm.run_device(descs[k % NBUF].data_ptr(), B, fmt, out.data_ptr(), kernel=kernel, stream=st)
 
     # ---- FP32 peak of this device, measured before the timed region ---------------------------
     fp32_peak, _ = measure_fp32_peak(local)
@@ -281,17 +293,22 @@ def run_ours(args):
     value = world * B * args.steps / (ms * 1e-3)
 
     # ---- end to end through the host-buffer C-ABI call ---------------------------------------------
-    h_desc = torch.empty((B, stride), dtype=torch.uint8).pin_memory()
+    # the same B queries as SPARSE (CSR) entries in pinned host memory -- what a caller holding the
+    # reference's sparse {column: bins} dicts would hand over
+    row_off_np, entries_np = dm.gen_sparse_queries_host(SEED, rank * NBUF * B, B, KMIN, KMAX)
+    h_off = torch.from_numpy(row_off_np.view(np.int32)).pin_memory()
+    h_ent = torch.from_numpy(entries_np.view(np.int32)).pin_memory()
     h_out = torch.empty(B, dtype=torch.float32).pin_memory()
-    h_desc.copy_(descs[0])
-    hd, ho = h_desc.numpy(), h_out.numpy()
+    ho_np, he_np, ho = h_off.numpy().view(np.uint32), h_ent.numpy().view(np.uint32), h_out.numpy()
+    h2d_bytes = int(ho_np.nbytes + he_np.nbytes)
     e2e_steps = max(3, min(args.steps, 10))
     for _ in range(2):
-        dm.run_host(hd, L.DESC_RANGE_U8, None, kernel, out=ho)
+        dm.run_sparse_host(ho_np, he_np, None, kernel, out=ho)
+    e2e_first = ho.copy()
     barrier()
     te = time.perf_counter()
     for _ in range(e2e_steps):
-        dm.run_host(hd, L.DESC_RANGE_U8, None, kernel, out=ho)
+        dm.run_sparse_host(ho_np, he_np, None, kernel, out=ho)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - te
     if dist is not None:
@@ -310,10 +327,13 @@ def run_ours(args):
     # ---- parity of this very batch against the fp64 oracle (sub-sample) ------------------------
     rng = np.random.default_rng(0)
     idx = np.sort(rng.choice(B, size=min(B, 10000), replace=False))
-    dm.run_device(descs[0].data_ptr(), B, L.DESC_RANGE_U8, out.data_ptr(), kernel=kernel, stream=st)
+    dm.run_device(descs[0].data_ptr(), B, fmt, out.data_ptr(), kernel=kernel, stream=st)
     torch.cuda.synchronize()
-    got = out.cpu().numpy()[idx].astype(np.float64)
-    lo, hi = unpack_ranges(tm, descs[0].cpu().numpy()[idx])
+    full = out.cpu().numpy()
+    if not np.array_equal(full, e2e_first):
+        raise SystemExit("end-to-end (SPARSE host) results differ from the device-resident (BITS) results")
+    got = full[idx].astype(np.float64)
+    lo, hi = unpack_ranges(tm, ranges0.cpu().numpy()[idx])
     ref = O.dense_tree(tm, O.range_weights(tm, lo, hi))
     rel_err = float(np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300)))
 
@@ -337,14 +357,20 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel ------------------------------------------------------
     peaks, peak_src = measured_peaks()
-    spec = kernel != L.KERNEL_GENERIC
     flop_q = 2 * dm.spec_ffma() if spec else dm.flops_dense
     kernel_s = ms * 1e-3 / args.steps
     achieved_tf = flop_q * B / kernel_s / 1e12
     bytes_q = stride + 4
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    kname = "bc_spec_bits" if spec else "k1_kernel"
+    if os.path.exists(tpath):  # dram__bytes_read+write per query of this kernel, from the committed ncu capture
+        with open(tpath) as f:
+            per_q = json.load(f).get(f"{args.model}:{kname}")
+        traffic = per_q * B if per_q is not None else None
     roof = {"bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
-            "frac": achieved_tf / fp32_peak if fp32_peak else None, "traffic": None,
-            "kernel": "bc_spec_range8" if spec else "k1_kernel",
+            "frac": achieved_tf / fp32_peak if fp32_peak else None, "traffic": traffic,
+            "kernel": kname,
             "flop_per_query": flop_q, "flop_per_query_dense": dm.flops_dense,
             "peak_source": "FFMA micro-benchmark (bc_measure_fp32_peak) in this run",
             "note": "exact zeros of the CPTs emit no FFMA; achieved counts executed FFMAs only"}
@@ -359,11 +385,12 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.model} Chow-Liu BN ({tm.n_nodes} columns), {B} synthetic range queries per "
                                    f"GPU per step, k~U{{{KMIN}..{KMAX}}} constrained columns, seed {SEED}",
-                       "descriptor": "RANGE_U8", "bytes_per_query": bytes_q,
+                       "descriptor": "BITS (resident) / SPARSE CSR (e2e)", "bytes_per_query": bytes_q,
                        "l2": f"inputs rotate over {NBUF} resident batches = {NBUF * B * stride / 1e6:.0f} MB > 126 MB L2",
                        "kernel": roof["kernel"], "parallelism": f"replica x{world}, batch sharded, no collective"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * stride, "d2h_bytes_per_step": B * 4,
-                    "steps": e2e_steps, "api": "bc_query_batch_host (pinned host buffers)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": B * 4,
+                    "steps": e2e_steps, "api": "bc_query_batch_sparse_host (pinned host CSR -> H2D -> expand -> "
+                                               "infer -> D2H)"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_hbm": roof_hbm,
             "cpu_baseline": cpu, "rel_err_max_vs_fp64_oracle": rel_err, "p50_latency_us_scalar_query": p50_us,
             "fp32_peak_tflops_measured": fp32_peak}

@@ -11,7 +11,7 @@
  *     Bayescard_BN.align_cpds_in_topological()                        Models/Bayescard_BN.py:340-358
  * Each entry point below names the reference interface it replaces.  All pointers are plain
  * host or device addresses; no torch / numpy / C++ types cross this boundary.  The host side above
- * it (bayescard_b200/*.py) binds these symbols with ctypes; INTEGRATION.md shows the stub.
+ * it (bayescard_b200 / *.py) binds these symbols with ctypes; INTEGRATION.md shows the stub.
  *
  * Conventions
  *   - every function returning int returns BC_OK (0) on success, a negative BC_E* code otherwise;
@@ -56,6 +56,18 @@ extern "C" {
  * DENSE_F32  one fp32 weight per (node, state): node v occupies round_up(card_v,4) floats starting
  *            at bc_model_dense_offset(v); row stride = bc_model_dense_width() floats.  Carries the
  *            general output of query_decoding (IN lists, fractional n_distinct weights).
+ * BITS       one bit per (node, state): node v owns bits [bc_model_bits_offset(v), +card_v) of the row,
+ *            nodes tightly packed in topological order, row stride = bc_model_desc_stride() bytes
+ *            (a multiple of 16).  w_v[c] = bit ? 1 : 0; an unconstrained column has all bits set
+ *            (bc_model_bits_default() returns that row).  Carries every predicate whose n_distinct
+ *            weights are all 1: ranges, equality and IN lists over the discretised bins.  This is
+ *            the format the specialised kernel is fastest on.
+ * SPARSE     (host-facing, bc_query_batch_sparse*) CSR: row_off[nq+1] (uint32, in entries) and 32-bit
+ *            entries  col[0:15) | cont<<15 | lo<<16 | hi<<24 : states lo..hi of column col; cont=1
+ *            ORs into the column's mask built so far (IN lists), cont=0 replaces it.  Columns that
+ *            are not mentioned are unconstrained -- the shape of the reference's query dict
+ *            (Evaluation/cardinality_estimation.py:60-111).  Needs card <= 256.  Expanded to BITS
+ *            rows on the device; only PCIe sees this form.
  * For every format an optional fan-out bitmask (mask_words = ceil(n_nodes/32) uint32 per query,
  * bit v set = multiply w_v by fanouts[v]) implements expectation(); a predicate on a fan-out
  * column wins (ExactInference.py:209,:238), so the host clears the bit for predicated columns.
@@ -63,6 +75,7 @@ extern "C" {
 #define BC_DESC_RANGE_U8 0
 #define BC_DESC_RANGE_U16 1
 #define BC_DESC_DENSE_F32 2
+#define BC_DESC_BITS 3
 
 /* ---- kernel selection ------------------------------------------------------------------------- */
 #define BC_KERNEL_AUTO 0     /* specialised kernel if the model has one, else generic        */
@@ -91,6 +104,9 @@ BC_API int bc_model_device(const bc_model* m);
 /* DENSE_F32 row geometry */
 BC_API int64_t bc_model_dense_width(const bc_model* m);
 BC_API int64_t bc_model_dense_offset(const bc_model* m, int node);
+/* BITS row geometry: first bit of node v; the all-selected row (row stride bytes, host copy) */
+BC_API int64_t bc_model_bits_offset(const bc_model* m, int node);
+BC_API int bc_model_bits_default(const bc_model* m, void* row_host, size_t row_bytes);
 /* row stride in BYTES of a descriptor format for this model */
 BC_API int64_t bc_model_desc_stride(const bc_model* m, int desc_format);
 /* ALGORITHMIC flop per query of the dense tree: 2 * sum_{v != root} card(v)*card(parent(v)) */
@@ -124,6 +140,18 @@ BC_API int bc_query_batch(bc_model* m, const void* desc, size_t n_queries, int d
 BC_API int bc_query_batch_host(bc_model* m, const void* desc, size_t n_queries, int desc_format,
                         const uint32_t* fanout_mask, float* out_prob, int kernel);
 
+/* Device-side descriptor conversion (stream ordered, DEVICE pointers): RANGE_U8 / RANGE_U16 -> BITS. */
+BC_API int bc_convert_desc(bc_model* m, const void* src, int src_format, void* dst, int dst_format, size_t n_queries,
+                    void* stream);
+/* SPARSE queries.  bc_expand_sparse: DEVICE pointers, writes n_queries BITS rows (stream ordered).
+ * bc_query_batch_sparse_host: HOST pointers (pinned or pageable); chunks the batch and overlaps
+ * H2D(row_off, entries) / expand / inference kernel / D2H(out) on internal streams.  This is the
+ * end-to-end call behind Bayescard_BN.query_batch: per query it moves 4 + 4*k bytes in and 4 out. */
+BC_API int bc_expand_sparse(bc_model* m, const uint32_t* row_off, const uint32_t* entries, size_t n_queries,
+                     void* dst_bits, void* stream);
+BC_API int bc_query_batch_sparse_host(bc_model* m, const uint32_t* row_off, const uint32_t* entries, size_t n_queries,
+                               const uint32_t* fanout_mask, float* out_prob, int kernel);
+
 /* Synthetic workload generator (BASELINE.json configs 2 and 5): writes
  * RANGE_U8 descriptors for query indices [first, first+n) from a counter-based RNG keyed by
  * (seed, query index), so any query can be regenerated on the host for oracle spot checks
@@ -133,6 +161,10 @@ BC_API int bc_gen_range_queries(bc_model* m, uint64_t seed, uint64_t first, size
                          void* desc_dev, void* stream);
 BC_API int bc_gen_range_queries_host(int n_nodes, const int32_t* card, uint64_t seed, uint64_t first,
                               size_t n, int kmin, int kmax, void* desc_host);
+/* The same queries in SPARSE form (host): row_off[n+1], entries (capacity n*kmax); entries of a query
+ * are in ascending column order.  Returns the number of entries written in *n_entries. */
+BC_API int bc_gen_sparse_queries_host(int n_nodes, const int32_t* card, uint64_t seed, uint64_t first, size_t n,
+                               int kmin, int kmax, uint32_t* row_off, uint32_t* entries, size_t* n_entries);
 
 /* Measured FP32 FFMA peak of the device (TFLOP/s), the roofline denominator SURVEY.md section 8d
  * asks to measure in the same run rather than quote. */

@@ -55,7 +55,7 @@ def test_infer_cases_both_kernels(name, kernel):
         got = np.zeros(len(cases))
         before = launch_count()
         if len(r_idx):
-            got[r_idx] = dm.run_host(r_desc, L.DESC_RANGE_U8, mask[r_idx], kernel)
+            got[r_idx] = dm.run_host(r_desc, L.DESC_BITS, mask[r_idx], kernel)
         if len(d_idx):
             got[d_idx] = dm.run_host(d_desc, L.DESC_DENSE_F32, mask[d_idx], kernel)
         assert launch_count() > before, "no kernel was launched"
@@ -90,6 +90,53 @@ def test_synthetic_batch_generic_vs_spec_vs_oracle(name):
     # host-buffer pipeline == device-buffer launch, bit for bit
     via_host = dm.run_host(host, L.DESC_RANGE_U8, None, L.KERNEL_SPEC)
     assert np.array_equal(via_host.astype(np.float64), res[L.KERNEL_SPEC])
+    # the three descriptor forms of the same queries give the same bits out: device conversion == host packing
+    pc = PredicateCompiler(m)
+    bits_host = pc.pack_bits(lo, hi)
+    bits_dev = torch.empty((n, dm.desc_stride(L.DESC_BITS)), dtype=torch.uint8, device="cuda:0")
+    dm.convert_device(desc.data_ptr(), L.DESC_RANGE_U8, bits_dev.data_ptr(), L.DESC_BITS, n, st)
+    torch.cuda.synchronize()
+    assert np.array_equal(bits_dev.cpu().numpy(), bits_host)
+    for kernel in KERNELS:
+        via_bits = dm.run_host(bits_host, L.DESC_BITS, None, kernel)
+        assert np.array_equal(via_bits.astype(np.float64), res[kernel])
+    row_off, entries = dm.gen_sparse_queries_host(11, 5, n, 1, kmax)
+    ro2, en2 = pc.pack_sparse(lo, hi)
+    assert np.array_equal(row_off, ro2) and np.array_equal(entries, en2)
+    for kernel in KERNELS:
+        via_sparse = dm.run_sparse_host(row_off, entries, None, kernel)
+        assert np.array_equal(via_sparse.astype(np.float64), res[kernel])
+
+
+def test_sparse_in_lists_and_chunking():
+    """SPARSE entries with the continuation bit build IN lists; > 256K queries exercise the chunked pipeline."""
+    m, dm = G.model("dmv"), dev_model("dmv")
+    pc = PredicateCompiler(m)
+    rng = np.random.default_rng(3)
+    n = 600_000 + 11
+    v = 9  # a 63-state leaf
+    card = int(m.card[v])
+    picks = rng.integers(0, card, size=(n, 3))
+    bits = np.zeros((n, card), dtype=bool)
+    np.put_along_axis(bits, picks, True, axis=1)
+    row_off = (np.arange(n + 1, dtype=np.uint32) * 3).astype(np.uint32)
+    ent = (np.uint32(v) | (picks.astype(np.uint32) << 16) | (picks.astype(np.uint32) << 24))
+    ent[:, 1:] |= np.uint32(1 << 15)  # OR into the mask started by the first entry
+    got = dm.run_sparse_host(row_off, ent.reshape(-1)).astype(np.float64)
+    W = [np.ones((n, int(c))) for c in m.card]
+    W[v] = bits.astype(np.float64)
+    sub = rng.choice(n, 5000, replace=False)
+    ref = O.dense_tree(m, [w[sub] for w in W])
+    assert_close(got[sub], ref, "sparse IN lists")
+    # the same masks as BITS rows, built on the host
+    decoded = [({m.infer_names[v]: sorted(set(map(int, picks[i])))}, {m.infer_names[v]: np.ones(len(set(picks[i])))})
+               for i in sub[:300]]
+    b_idx, b_desc, d_idx, _, _ = pc.pack(decoded)
+    assert len(d_idx) == 0
+    assert np.array_equal(dm.run_host(b_desc, L.DESC_BITS).astype(np.float64), got[sub[:300]])
+    # an empty SPARSE row is the unconstrained query
+    one = dm.run_sparse_host(np.zeros(2, dtype=np.uint32), np.zeros(0, dtype=np.uint32))
+    assert abs(one[0] - 1.0) < 1e-5
 
 
 def test_size_independent_properties_full_batch():

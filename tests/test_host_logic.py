@@ -130,6 +130,44 @@ def test_decode_quirks():
 
 
 # ------------------------------------------------------------------------------------ packing
+def bits_weights(m, desc, mask=None):
+    """BITS rows -> dense fp64 weights per node (CPU; the inverse of PredicateCompiler.pack)."""
+    bits = np.unpackbits(np.asarray(desc, dtype=np.uint8), axis=1, bitorder="little")
+    W, off = [], 0
+    for v in range(m.n_nodes):
+        w = bits[:, off: off + int(m.card[v])].astype(np.float64)
+        off += int(m.card[v])
+        f = m.fan_vector(v)
+        if mask is not None and f is not None:
+            bit = ((mask[:, v // 32] >> np.uint32(v % 32)) & 1).astype(bool)
+            w = np.where(bit[:, None], w * f[None, :], w)
+        W.append(w)
+    return W
+
+
+def test_bits_and_sparse_forms_of_range_queries():
+    """RANGE_U8 rows, BITS rows and SPARSE (CSR) entries of the same seeded queries agree; the host twin of
+    the generator writes the same queries in both forms."""
+    m = G.model("census")
+    pc = PredicateCompiler(m)
+    dm = DeviceModel(m, device=-1, specialize=False)
+    desc = gen_range_queries_host(m, 5, 40, 3000, 1, 14)
+    lo, hi = unpack_ranges(m, desc)
+    bits = pc.pack_bits(lo, hi)
+    assert bits.shape[1] == dm.desc_stride(L.DESC_BITS) and bits.shape[1] % 16 == 0
+    W1, W2 = O.range_weights(m, lo, hi), bits_weights(m, bits)
+    assert all(np.array_equal(a, b) for a, b in zip(W1, W2))
+    assert np.array_equal(dm.bits_offset, pc.geometry()[0])
+    full = pc.pack_bits(np.zeros((1, m.n_nodes), int), (m.card - 1)[None, :])
+    assert np.array_equal(full.view(np.uint32)[0], dm.bits_default())
+    row_off, entries = pc.pack_sparse(lo, hi)
+    ro2, en2 = dm.gen_sparse_queries_host(5, 40, 3000, 1, 14)
+    assert np.array_equal(row_off, ro2) and np.array_equal(entries, en2)
+    k = np.diff(row_off.astype(np.int64))
+    assert k.min() >= 0 and k.max() <= 14 and entries.size == k.sum()
+    dm.close()
+
+
 @pytest.mark.parametrize("name", ["dmv", "census", "imdb2"])
 def test_pack_is_equivalent_to_decoded_weights(name):
     """Descriptors, unpacked on the CPU and pushed through the dense fp64 form, reproduce the reference."""
@@ -142,8 +180,7 @@ def test_pack_is_equivalent_to_decoded_weights(name):
     r_idx, r_desc, d_idx, d_desc, mask = pc.pack(decoded, fans)
     assert len(r_idx) + len(d_idx) == len(cases) and len(r_idx) > 0 and len(d_idx) > 0
     got = np.zeros(len(cases))
-    lo, hi = unpack_ranges(m, r_desc)
-    got[r_idx] = O.dense_tree(m, O.range_weights(m, lo, hi, mask[r_idx]))
+    got[r_idx] = O.dense_tree(m, bits_weights(m, r_desc, mask[r_idx]))
     off = np.concatenate([[0], np.cumsum([-(-int(c) // 4) * 4 for c in m.card])[:-1]])
     W = []
     for v in range(m.n_nodes):
@@ -187,7 +224,7 @@ def test_host_only_model_codegen_and_generator():
     m = G.model("census")
     dm = DeviceModel(m, device=-1, specialize=False)
     src = dm.spec_source()
-    assert "bc_spec_range8" in src and "bc_spec_dense" in src
+    assert "bc_spec_bits" in src and "bc_spec_dense" in src and ".target sm_100a" in src
     # one FFMA per non-zero non-root CPT entry plus the root row
     nz = sum(int(np.count_nonzero(c.astype(np.float32))) for c in m.cpts)
     assert dm.spec_ffma() == nz
