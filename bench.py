@@ -216,6 +216,7 @@ def run_ours(args):
     from bayescard_b200.decode import unpack_ranges
     from bayescard_b200.engine import DeviceModel, launch_count, measure_fp32_peak
     from bayescard_b200.model import Bayescard_BN
+    from bayescard_b200.sharding import max_over_ranks
     from oracle import bayescard_oracle as O  # checker + cpu_baseline leg only
 
     rank = int(os.environ.get("RANK", "0"))
@@ -285,11 +286,7 @@ def run_ours(args):
     barrier()
     t1 = time.perf_counter()
     launches = launch_count() - launches0
-    ms = e0.elapsed_time(e1)
-    if dist is not None:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = max_over_ranks(e0.elapsed_time(e1), device=dev)
     value = world * B * args.steps / (ms * 1e-3)
 
     # ---- end to end through the host-buffer C-ABI call ---------------------------------------------
@@ -311,10 +308,7 @@ def run_ours(args):
         dm.run_sparse_host(ho_np, he_np, None, kernel, out=ho)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - te
-    if dist is not None:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    e2e_s = max_over_ranks(e2e_s, device=dev)
     e2e_value = world * B * e2e_steps / e2e_s
     clocks = sampler.stop(t0, time.perf_counter()) if sampler else None
 

@@ -221,6 +221,25 @@ def test_replicas_shard_a_batch():
     sm.close()
 
 
+def test_sharded_ranks_on_gpu():
+    """The per-rank slice evaluator of bayescard_b200.sharding on the real device (single rank = whole batch;
+    the two-rank split itself is covered on CPU by tests/test_sharding_gloo.py)."""
+    from bayescard_b200.sharding import csr_slice, evaluate_sharded, rank_range
+
+    m, dm = G.model("census"), dev_model("census")
+    n = 30011
+    row_off, entries = dm.gen_sparse_queries_host(2, 0, n, 1, 14)
+    whole = dm.run_sparse_host(row_off, entries)
+
+    def evaluate(a, b):
+        ro, en = csr_slice(row_off, entries, a, b)
+        return dm.run_sparse_host(ro, en)
+
+    assert np.array_equal(evaluate_sharded(evaluate, n), whole)
+    parts = [evaluate(*rank_range(n, r, 4)) for r in range(4)]
+    assert np.array_equal(np.concatenate(parts), whole)
+
+
 # ------------------------------------------------------------------------------------ drop-in API
 @pytest.mark.parametrize("name", ["dmv", "census"])
 def test_workload_end_to_end_through_dropin_api(name):
