@@ -1,6 +1,7 @@
 // C ABI of libbayescard_b200.so: model lifecycle, kernel dispatch, host-buffer pipeline,
 // synthetic query generator, FP32 peak probe.  See include/bayescard_b200.h for the contract.
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -194,6 +195,7 @@ extern "C" void bc_model_destroy(bc_model* m) {
     if (m->device >= 0) {
         cudaSetDevice(m->device);
         pipe_free(m->pipe);
+        bc_k2_free(m);
         if (m->spec_lib) cudaLibraryUnload(m->spec_lib);
         cudaFree(m->d_arena);
         cudaFree(m->d_fan);
@@ -296,6 +298,11 @@ extern "C" int bc_query_batch(bc_model* m, const void* desc, size_t nq, int fmt,
             return rc;
         }
     }
+    if (kernel == BC_KERNEL_GEMM || kernel == BC_KERNEL_GEMM_SIMT)
+        return bc_k2_launch(m, desc, nq, fmt, fan_mask, out, kernel == BC_KERNEL_GEMM, st);
+    // no image: large domains go to the batched path (K1 re-reads every CPT once per query)
+    if (kernel == BC_KERNEL_AUTO && is_range && !fan_mask && (m->max_card > 256 || m->lam_total > 4096))
+        return bc_k2_launch(m, desc, nq, fmt, fan_mask, out, 1, st);
     if (kernel == BC_KERNEL_GENERIC || kernel == BC_KERNEL_AUTO) return bc_k1_launch(m, desc, nq, fmt, fan_mask, out, st);
     bc_set_error("kernel %d not available in this build", kernel);
     return BC_EINVAL;
@@ -493,8 +500,14 @@ extern "C" int bc_query_batch_sparse_host(bc_model* m, const uint32_t* row_off, 
     if (!row_off || !out) { bc_set_error("row_off/out is NULL"); return BC_EINVAL; }
     if (row_off[nq] > row_off[0] && !entries) { bc_set_error("entries is NULL"); return BC_EINVAL; }
     BC_CUDA_CHECK(cudaSetDevice(m->device));
-    // chunks of ~256K queries: large enough to fill the GPU several times over, small enough to overlap
-    size_t chunk = 256 * 1024;
+    // chunks of 1M queries (~30 MB of CSR): measured on B200 (profiles/r1_e2e_chunk_sweep.txt) every extra
+    // chunk costs ~50 us of copy / event latency, more than the overlap wins back below a few million
+    // queries; larger batches pipeline H2D | expand+infer | D2H over three slots (BC_SPARSE_CHUNK overrides)
+    size_t chunk = 1024 * 1024;
+    if (const char* env = std::getenv("BC_SPARSE_CHUNK")) {
+        const long long v = std::atoll(env);
+        if (v >= 1024) chunk = (size_t)v;
+    }
     if (chunk > nq) chunk = nq;
     const size_t nchunks = (nq + chunk - 1) / chunk;
     size_t max_entries = 1;

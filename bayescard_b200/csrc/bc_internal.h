@@ -33,6 +33,14 @@ struct BcBitsRec {
 };
 
 struct BcHostPipe;  // bc_api.cu
+struct BcUmmaPlan;  // k2_umma.cu
+
+// State of the batched large-domain path (K2), built on first use.
+struct BcK2Plan {
+    std::vector<char> is_internal;     // node has children
+    std::vector<double*> d_prefix;     // leaves: fp64 column prefix sums of T_v, (card+1) x card_pa
+    BcUmmaPlan* umma = nullptr;        // tensor-core operands (transposed hi / lo CPTs, tensor maps)
+};
 
 struct bc_model {
     int device = -1;     // -1: host-only model (code generation / ahead-of-time build)
@@ -66,6 +74,8 @@ struct bc_model {
     int spec_qpt = 1;                // queries per thread per loop trip
     int spec_blocks_bits = 1, spec_blocks_dense = 1, spec_blocks_range8 = 1;  // resident CTAs per SM
     std::vector<uint32_t> bits_default;
+    BcK2Plan* k2 = nullptr;
+    std::mutex k2_mu;                // guards the lazy construction of k2 (pipe_mu may already be held)
     BcHostPipe* pipe = nullptr;
     std::mutex pipe_mu;
 };
@@ -91,6 +101,14 @@ int bc_k1_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32
 int bc_convert_launch(bc_model* m, const void* src, int src_fmt, void* dst, int dst_fmt, size_t nq, cudaStream_t stream);
 int bc_expand_sparse_launch(bc_model* m, const uint32_t* row_off, const uint32_t* entries, size_t nq, void* dst_bits,
                             cudaStream_t stream);
+// k2_batched.cu / k2_umma.cu
+int bc_k2_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32_t* fan_mask, float* out, int use_umma,
+                 cudaStream_t stream);
+void bc_k2_free(bc_model* m);
+// one internal edge on the tensor cores; BC_ELIMIT = shape not served (caller falls back to FP32 SIMT)
+int bc_k2_umma_edge(bc_model* m, const uint8_t* desc, size_t dstride, int fmt, size_t q0, int rows, int v, float* lam_v,
+                    int ld_v, float* lam_pa, int ld_pa, int accumulate, cudaStream_t stream);
+void bc_k2_umma_free(bc_model* m);
 // spec_codegen.cc
 std::string bc_spec_generate(const bc_model& m);
 uint64_t bc_spec_hash_of(const bc_model& m);

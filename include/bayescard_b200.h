@@ -81,7 +81,9 @@ extern "C" {
 #define BC_KERNEL_AUTO 0     /* specialised kernel if the model has one, else generic        */
 #define BC_KERNEL_GENERIC 1  /* K1: warp per query, CPT arena staged in shared memory by TMA  */
 #define BC_KERNEL_SPEC 2     /* K-spec: per-model straight-line kernel, thread per query      */
-#define BC_KERNEL_GEMM 3     /* K2: per-edge batched GEMM for large domains                   */
+#define BC_KERNEL_GEMM 3     /* K2: per-edge batched path for large domains, tcgen05 3xTF32 GEMM
+                                where the edge shape allows, FP32 SIMT GEMM otherwise; RANGE_* rows */
+#define BC_KERNEL_GEMM_SIMT 4 /* K2 with the FP32 SIMT GEMM only (the comparator for K2)      */
 
 typedef struct bc_model bc_model;
 

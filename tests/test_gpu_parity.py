@@ -221,6 +221,38 @@ def test_replicas_shard_a_batch():
     sm.close()
 
 
+@pytest.mark.parametrize("shape", [(8, 300, 6000), (20, 10, 5000), (12, [7, 130, 33, 257, 64, 5, 90, 200, 17, 128, 40, 3], 4001),
+                                   (1, 50, 100)])
+def test_batched_large_domain_path(shape):
+    """K2 (BASELINE.json config 4): synthetic random trees, RANGE_U16 rows, FP32 SIMT and tensor-core GEMM edges."""
+    from bayescard_b200.synth import make_tree_model, pack_ranges_u16, random_range_queries
+
+    n_cols, card, nq = shape
+    m = make_tree_model(n_cols, card, seed=n_cols)
+    dm = DeviceModel(m, device=0, specialize=False)
+    lo, hi = random_range_queries(m, nq, seed=1, kmax=10)
+    lo[0], hi[0] = 0, m.card - 1                       # unconstrained query
+    if nq > 2:
+        lo[1, 0], hi[1, 0] = 3, 2                      # empty range on the root
+    desc = pack_ranges_u16(lo, hi)
+    ref = O.dense_tree(m, O.range_weights(m, lo, hi))
+    assert abs(ref[0] - 1) < 1e-9
+    for kernel in (L.KERNEL_GEMM_SIMT, L.KERNEL_GEMM):
+        got = dm.run_host(desc, L.DESC_RANGE_U16, None, kernel)
+        assert_close(got, ref, (shape, kernel))
+    if int(m.card.max()) <= 256 and sum(-(-int(c) // 4) * 4 for c in m.card) * 4 < 40000:
+        # the same queries through the generic kernel (RANGE_U16 rows)
+        assert_close(dm.run_host(desc, L.DESC_RANGE_U16, None, L.KERNEL_GENERIC), ref, (shape, "generic"))
+    # small workspace: many tiles
+    import os
+    os.environ["BC_K2_WORKSPACE_MB"] = "16"
+    try:
+        assert_close(dm.run_host(desc, L.DESC_RANGE_U16, None, L.KERNEL_GEMM_SIMT), ref, (shape, "tiled"))
+    finally:
+        del os.environ["BC_K2_WORKSPACE_MB"]
+    dm.close()
+
+
 def test_sharded_ranks_on_gpu():
     """The per-rank slice evaluator of bayescard_b200.sharding on the real device (single rank = whole batch;
     the two-rank split itself is covered on CPU by tests/test_sharding_gloo.py)."""
