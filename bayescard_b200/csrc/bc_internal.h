@@ -107,7 +107,7 @@ int bc_k2_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32
 void bc_k2_free(bc_model* m);
 // one internal edge on the tensor cores; BC_ELIMIT = shape not served (caller falls back to FP32 SIMT)
 int bc_k2_umma_edge(bc_model* m, const uint8_t* desc, size_t dstride, int fmt, size_t q0, int rows, int v, float* lam_v,
-                    int ld_v, float* lam_pa, int ld_pa, int accumulate, cudaStream_t stream);
+                    float* lam_v_lo, int ld_v, float* lam_pa, int ld_pa, int accumulate, cudaStream_t stream);
 void bc_k2_umma_free(bc_model* m);
 // spec_codegen.cc
 std::string bc_spec_generate(const bc_model& m);

@@ -208,8 +208,8 @@ __global__ void __launch_bounds__(256) k2_root_kernel(const uint8_t* __restrict_
 }
 
 template <int FMT>
-int run_tile(bc_model* m, const uint8_t* desc, size_t dstride, size_t q0, int rows, float* out, float* const* lam,
-             const int* ld, int use_umma, cudaStream_t st) {
+int run_tile(bc_model* m, const uint8_t* desc, size_t dstride, size_t q0, int rows, size_t tile_rows, float* out,
+             float* const* lam, const int* ld, int use_umma, cudaStream_t st) {
     const int n = m->n;
     std::vector<char> written(n, 0);
     for (int v = n - 1; v >= 1; --v) {
@@ -225,7 +225,10 @@ int run_tile(bc_model* m, const uint8_t* desc, size_t dstride, size_t q0, int ro
         } else {
             const float* T = m->d_arena + nd.cpt_off;
             int rc = BC_ELIMIT;
-            if (use_umma) rc = bc_k2_umma_edge(m, desc, dstride, FMT, q0, rows, v, lam[v], ld[v], lam[pa], ld[pa], acc, st);
+            // with use_umma the low halves of Lambda_v sit right behind the high halves in the workspace
+            if (use_umma)
+                rc = bc_k2_umma_edge(m, desc, dstride, FMT, q0, rows, v, lam[v], lam[v] + tile_rows * (size_t)ld[v], ld[v],
+                                     lam[pa], ld[pa], acc, st);
             if (rc == BC_ELIMIT) {  // shape not served by the tensor-core kernel: FP32 SIMT
                 if (nd.card_pa > 32) {
                     dim3 grid((nd.card_pa + 127) / 128, (rows + 127) / 128);
@@ -333,8 +336,8 @@ int bc_k2_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32
     int rc = BC_OK;
     for (size_t q0 = 0; q0 < nq && rc == BC_OK; q0 += tile) {
         const int rows = (int)(nq - q0 < tile ? nq - q0 : tile);
-        rc = fmt == BC_DESC_RANGE_U8 ? run_tile<BC_DESC_RANGE_U8>(m, d, dstride, q0, rows, out, lam.data(), ld.data(), use_umma, stream)
-                                     : run_tile<BC_DESC_RANGE_U16>(m, d, dstride, q0, rows, out, lam.data(), ld.data(), use_umma, stream);
+        rc = fmt == BC_DESC_RANGE_U8 ? run_tile<BC_DESC_RANGE_U8>(m, d, dstride, q0, rows, tile, out, lam.data(), ld.data(), use_umma, stream)
+                                     : run_tile<BC_DESC_RANGE_U16>(m, d, dstride, q0, rows, tile, out, lam.data(), ld.data(), use_umma, stream);
     }
     if (ws) cudaFreeAsync(ws, stream);
     return rc;

@@ -1,8 +1,375 @@
-// K2 tensor-core edge kernel (tcgen05 / TMEM / TMA, 3xTF32) -- placeholder until the kernel lands:
-// every shape is reported as "not served", so K2 runs its FP32 SIMT GEMM.
+// K2 tensor-core edge kernel: one internal edge of the batched sum-product as a tcgen05 GEMM.
+//
+//     C[rows x N] = mask(Lambda_v)[rows x K] . T_v[K x N]         K = card(v), N = card(parent)
+//     Lambda_pa   = accumulate ? Lambda_pa * C : C
+//
+// TF32 alone (10-bit mantissa) would miss the 1e-5 budget, so the product is error compensated
+// ("3xTF32"): every fp32 operand x is split into hi = x rounded to the nearest TF32 number and
+// lo = (x - hi) rounded to TF32, and
+//
+//     A.B  ~=  A_lo.B_hi + A_hi.B_lo + A_hi.B_hi                  (fp32 accumulation in TMEM)
+//
+// which leaves a relative error of ~2^-21 per product (measured against the fp64 oracle in
+// tests/test_gpu_parity.py::test_batched_large_domain_path).
+//
+// Shape of the kernel (sm_100a only):
+//   * CTA tile 128 queries x BN parent states (BN = 32 / 64 / 128), K in blocks of 32 floats = one
+//     128-byte swizzle atom;
+//   * warp 0: TMA producer -- four 2-D tiled bulk tensor loads per stage (A_hi, A_lo, B_hi, B_lo; 128-byte
+//     swizzle, out-of-bounds rows zero filled) completing on an mbarrier (SASS UTMALDG);
+//   * warp 1: allocates TMEM and issues tcgen05.mma.cta_group::1.kind::tf32 (SASS UTCHMMA/UTC*MMA) from one
+//     thread, 12 MMAs (4 k-steps x 3 products) per stage, tcgen05.commit frees the stage;
+//   * warps 2-5: epilogue -- tcgen05.ld (SASS LDTM) of the 128 x BN fp32 accumulator, fused multiply into
+//     Lambda_pa;
+//   * both operands K-major: Lambda rows are K-contiguous as produced by the previous edge, the CPT is
+//     stored transposed (and pre-split) once per model.
+// The range mask of column v and the hi/lo split of Lambda_v are one elementwise pass (k2_split_kernel).
+#include <cuda.h>
+
 #include "bc_internal.h"
 
-int bc_k2_umma_edge(bc_model*, const uint8_t*, size_t, int, size_t, int, int, float*, int, float*, int, int, cudaStream_t) {
-    return BC_ELIMIT;
+struct BcUmmaPlan {
+    std::vector<float*> d_tt_hi, d_tt_lo;  // per internal non-root node: T^T split, [N x ldk]
+    std::vector<int> ldk;
+    void* encode = nullptr;                // cuTensorMapEncodeTiled
+    int failed = 0;
+};
+
+namespace {
+
+constexpr int kBM = 128, kBK = 32, kStages = 3, kThreads = 192;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// fp32 -> nearest TF32 (round half to even on the 13 dropped mantissa bits); the result is a valid fp32 whose
+// low 13 bits are zero, so the tensor core's own fp32->tf32 conversion is exact whatever its rounding mode
+__device__ __forceinline__ float tf32_rn(float x) {
+    uint32_t b = __float_as_uint(x);
+    b += 0xFFFu + ((b >> 13) & 1u);
+    return __uint_as_float(b & 0xFFFFE000u);
 }
-void bc_k2_umma_free(bc_model*) {}
+// x = hi + lo with both halves TF32 numbers (|x - hi - lo| <= 2^-23 |x|); rounding, not truncating, keeps
+// the compensated product unbiased -- truncation gave a systematic -1e-5 over a 7-edge tree
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    hi = tf32_rn(x);
+    lo = tf32_rn(x - hi);
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, unsigned parity) {
+    asm volatile(
+        "{\n.reg .pred p;\nWAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+// K-major, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO = 1 (unused), version 1 (sm_100)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_c),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+k2_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+               const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, int rows, int N,
+               int num_kb, float* __restrict__ lam_pa, int ld_pa, int accumulate) {
+    constexpr int A_BYTES = kBM * kBK * 4, B_BYTES = BN * kBK * 4, STAGE = 2 * A_BYTES + 2 * B_BYTES;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // the dynamic shared window is only 16 B aligned by contract: round up to the 1024 B the swizzle needs
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * STAGE);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kStages), tfull = smem_u32(bars + 2 * kStages);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * BN;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        mbar_init(tfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // TMEM: BN fp32 columns x 128 lanes
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ---- TMA producer
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % kStages;
+                mbar_wait(empty0 + 8 * s, ((kb / kStages) & 1) ^ 1);
+                const uint32_t base = smem_u32(smem + s * STAGE), bar = full0 + 8 * s;
+                mbar_expect_tx(bar, STAGE);
+                tma_load_2d(base, &tm_a_hi, kb * kBK, m0, bar);
+                tma_load_2d(base + A_BYTES, &tm_a_lo, kb * kBK, m0, bar);
+                tma_load_2d(base + 2 * A_BYTES, &tm_b_hi, kb * kBK, n0, bar);
+                tma_load_2d(base + 2 * A_BYTES + B_BYTES, &tm_b_lo, kb * kBK, n0, bar);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ---- MMA issuer
+            // instruction descriptor: D = F32, A = B = TF32, both K-major, N = BN, M = 128
+            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % kStages;
+                mbar_wait(full0 + 8 * s, (kb / kStages) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t base = smem_u32(smem + s * STAGE);
+                const uint64_t a_hi = umma_desc(base), a_lo = umma_desc(base + A_BYTES);
+                const uint64_t b_hi = umma_desc(base + 2 * A_BYTES), b_lo = umma_desc(base + 2 * A_BYTES + B_BYTES);
+#pragma unroll
+                for (int kk = 0; kk < kBK / 8; ++kk) {  // 8 TF32 = 32 bytes per MMA: +2 in the 16-byte address field
+                    const uint64_t o = (uint64_t)(kk * 2);
+                    umma_tf32(tmem, a_lo + o, b_hi + o, idesc, (kb | kk) != 0);
+                    umma_tf32(tmem, a_hi + o, b_lo + o, idesc, 1);
+                    umma_tf32(tmem, a_hi + o, b_hi + o, idesc, 1);
+                }
+                umma_commit(empty0 + 8 * s);  // the stage is free once these MMAs have read it
+            }
+            umma_commit(tfull);               // accumulator complete
+        }
+    } else {  // ---- epilogue: warps 2..5 own TMEM lane quarters (warp % 4)
+        const int quarter = warp & 3;
+        mbar_wait(tfull, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int r = m0 + quarter * 32 + lane;
+        float* dst_row = lam_pa + (size_t)r * ld_pa + n0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            float v[32];
+            tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+            if (r < rows) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const int n = n0 + c0 + j;
+                    float* d = dst_row + c0 + j;
+                    if (n + 3 < N) {  // ld_pa and n are multiples of 4: 16 B aligned
+                        float4 x = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        if (accumulate) {
+                            const float4 o = *reinterpret_cast<const float4*>(d);
+                            x.x *= o.x; x.y *= o.y; x.z *= o.z; x.w *= o.w;
+                        }
+                        *reinterpret_cast<float4*>(d) = x;
+                    } else {
+                        for (int t = 0; t < 4; ++t)
+                            if (n + t < N) d[t] = accumulate ? d[t] * v[j + t] : v[j + t];
+                    }
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(BN) : "memory");
+    }
+}
+
+// Lambda_v: apply the range mask of column v, clear the padding columns, split into hi (in place) / lo
+template <int FMT>
+__global__ void __launch_bounds__(256) k2_split_kernel(const uint8_t* __restrict__ desc, size_t dstride, size_t q0, int rows,
+                                                       int v, int card, float* __restrict__ hi_io, float* __restrict__ lo_out,
+                                                       int ld) {
+    const int ld4 = ld >> 2;
+    const long long total = (long long)rows * ld4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(i / ld4), c = (int)(i - (long long)b * ld4) * 4;
+        const uint8_t* row = desc + (q0 + b) * dstride;
+        int lo, hi;
+        if (FMT == BC_DESC_RANGE_U8) {
+            const uint16_t p = reinterpret_cast<const uint16_t*>(row)[v];
+            lo = p & 0xff; hi = p >> 8;
+        } else {
+            const uint32_t p = reinterpret_cast<const uint32_t*>(row)[v];
+            lo = p & 0xffff; hi = p >> 16;
+        }
+        if (hi > card - 1) hi = card - 1;
+        float4* ph = reinterpret_cast<float4*>(hi_io + (size_t)b * ld + c);
+        float4 x = *ph;
+        float xs[4] = {x.x, x.y, x.z, x.w}, hs[4], ls[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const float val = (c + t >= lo && c + t <= hi) ? xs[t] : 0.f;  // also clears c >= card (uninitialised)
+            split_tf32(val, hs[t], ls[t]);
+        }
+        *ph = make_float4(hs[0], hs[1], hs[2], hs[3]);
+        *reinterpret_cast<float4*>(lo_out + (size_t)b * ld + c) = make_float4(ls[0], ls[1], ls[2], ls[3]);
+    }
+}
+
+// T_v [K x N] (row stride) -> T^T split [N x ldk], zero padded
+__global__ void k2_transpose_split_kernel(const float* __restrict__ T, int K, int N, int stride, float* __restrict__ hi,
+                                          float* __restrict__ lo, int ldk) {
+    __shared__ float tile[32][33];
+    const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int k = k0 + j, n = n0 + threadIdx.x;
+        tile[j][threadIdx.x] = (k < K && n < N) ? T[(size_t)k * stride + n] : 0.f;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int n = n0 + j, k = k0 + threadIdx.x;
+        if (n < N && k < ldk) {
+            const float x = tile[threadIdx.x][j];
+            float h, l;
+            split_tf32(x, h, l);
+            hi[(size_t)n * ldk + k] = h;
+            lo[(size_t)n * ldk + k] = l;
+        }
+    }
+}
+
+int encode_map(EncodeTiledFn fn, CUtensorMap* map, const float* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
+               uint32_t box_rows) {
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {ld_elems * 4};
+    cuuint32_t box[2] = {(cuuint32_t)kBK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        bc_set_error("cuTensorMapEncodeTiled failed (%d) for a %llu x %llu fp32 tensor", (int)r, (unsigned long long)outer,
+                     (unsigned long long)inner);
+        return BC_ECUDA;
+    }
+    return BC_OK;
+}
+
+template <int BN>
+int launch_edge(const CUtensorMap* maps, int rows, int N, int num_kb, float* lam_pa, int ld_pa, int accumulate, cudaStream_t st) {
+    constexpr size_t smem = (size_t)kStages * (2 * kBM * kBK * 4 + 2 * BN * kBK * 4) + 1024 /* alignment slack */ + 128;
+    BC_CUDA_CHECK(cudaFuncSetAttribute(k2_umma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((N + BN - 1) / BN, (rows + kBM - 1) / kBM);
+    k2_umma_kernel<BN><<<grid, kThreads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], rows, N, num_kb, lam_pa, ld_pa, accumulate);
+    BC_CUDA_CHECK(cudaGetLastError());
+    bc_count_launch();
+    return BC_OK;
+}
+
+int umma_prepare(bc_model* m) {
+    BcK2Plan* k2 = m->k2;
+    if (k2->umma) return k2->umma->failed ? BC_ELIMIT : BC_OK;
+    BcUmmaPlan* u = new BcUmmaPlan();
+    k2->umma = u;
+    u->d_tt_hi.assign(m->n, nullptr);
+    u->d_tt_lo.assign(m->n, nullptr);
+    u->ldk.assign(m->n, 0);
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &u->encode, cudaEnableDefault, &q) != cudaSuccess || !u->encode ||
+        q != cudaDriverEntryPointSuccess) {
+        cudaGetLastError();
+        u->failed = 1;  // driver without tensor maps: K2 stays on its SIMT GEMM
+        return BC_ELIMIT;
+    }
+    for (int v = 1; v < m->n; ++v) {
+        if (!k2->is_internal[v]) continue;
+        const BcNodeRec& nd = m->nodes[v];
+        const int K = nd.card, N = nd.card_pa;
+        if (K < 64 || N < 16) continue;  // tiny edges stay on the SIMT kernel
+        const int ldk = (int)bc_round_up(K, kBK);
+        u->ldk[v] = ldk;
+        BC_CUDA_CHECK(cudaMalloc(&u->d_tt_hi[v], (size_t)N * ldk * 4));
+        BC_CUDA_CHECK(cudaMalloc(&u->d_tt_lo[v], (size_t)N * ldk * 4));
+        dim3 grid((ldk + 31) / 32, (N + 31) / 32), block(32, 8);
+        k2_transpose_split_kernel<<<grid, block>>>(m->d_arena + nd.cpt_off, K, N, nd.stride, u->d_tt_hi[v], u->d_tt_lo[v], ldk);
+        BC_CUDA_CHECK(cudaGetLastError());
+        bc_count_launch();
+    }
+    BC_CUDA_CHECK(cudaDeviceSynchronize());
+    return BC_OK;
+}
+
+}  // namespace
+
+int bc_k2_umma_edge(bc_model* m, const uint8_t* desc, size_t dstride, int fmt, size_t q0, int rows, int v, float* lam_v,
+                    float* lam_lo, int ld_v, float* lam_pa, int ld_pa, int accumulate, cudaStream_t st) {
+    {
+        std::lock_guard<std::mutex> lock(m->k2_mu);
+        int rc = umma_prepare(m);
+        if (rc) return rc;
+    }
+    BcUmmaPlan* u = m->k2->umma;
+    if (!u->d_tt_hi[v]) return BC_ELIMIT;
+    const BcNodeRec& nd = m->nodes[v];
+    const int K = nd.card, N = nd.card_pa, ldk = u->ldk[v];
+    if (ld_v < ldk) return BC_ELIMIT;
+    const long long total = (long long)rows * (ld_v / 4);
+    long long sgrid = (total + 255) / 256;
+    if (sgrid > (long long)m->sm_count * 16) sgrid = (long long)m->sm_count * 16;
+    if (fmt == BC_DESC_RANGE_U8)
+        k2_split_kernel<BC_DESC_RANGE_U8><<<(int)sgrid, 256, 0, st>>>(desc, dstride, q0, rows, v, K, lam_v, lam_lo, ld_v);
+    else
+        k2_split_kernel<BC_DESC_RANGE_U16><<<(int)sgrid, 256, 0, st>>>(desc, dstride, q0, rows, v, K, lam_v, lam_lo, ld_v);
+    BC_CUDA_CHECK(cudaGetLastError());
+    bc_count_launch();
+    EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(u->encode);
+    const int BN = N <= 32 ? 32 : N <= 64 ? 64 : 128;
+    CUtensorMap maps[4];
+    int rc;
+    if ((rc = encode_map(fn, &maps[0], lam_v, (uint64_t)ldk, (uint64_t)rows, (uint64_t)ld_v, kBM))) return rc;
+    if ((rc = encode_map(fn, &maps[1], lam_lo, (uint64_t)ldk, (uint64_t)rows, (uint64_t)ld_v, kBM))) return rc;
+    if ((rc = encode_map(fn, &maps[2], u->d_tt_hi[v], (uint64_t)ldk, (uint64_t)N, (uint64_t)ldk, (uint32_t)BN))) return rc;
+    if ((rc = encode_map(fn, &maps[3], u->d_tt_lo[v], (uint64_t)ldk, (uint64_t)N, (uint64_t)ldk, (uint32_t)BN))) return rc;
+    const int num_kb = ldk / kBK;
+    switch (BN) {
+        case 32: return launch_edge<32>(maps, rows, N, num_kb, lam_pa, ld_pa, accumulate, st);
+        case 64: return launch_edge<64>(maps, rows, N, num_kb, lam_pa, ld_pa, accumulate, st);
+        default: return launch_edge<128>(maps, rows, N, num_kb, lam_pa, ld_pa, accumulate, st);
+    }
+}
+
+void bc_k2_umma_free(bc_model* m) {
+    if (!m->k2 || !m->k2->umma) return;
+    for (float* p : m->k2->umma->d_tt_hi) cudaFree(p);
+    for (float* p : m->k2->umma->d_tt_lo) cudaFree(p);
+    delete m->k2->umma;
+    m->k2->umma = nullptr;
+}
