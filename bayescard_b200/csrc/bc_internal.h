@@ -40,6 +40,11 @@ struct BcK2Plan {
     std::vector<char> is_internal;     // node has children
     std::vector<double*> d_prefix;     // leaves: fp64 column prefix sums of T_v, (card+1) x card_pa
     BcUmmaPlan* umma = nullptr;        // tensor-core operands (transposed hi / lo CPTs, tensor maps)
+    // Lambda workspace, kept between calls (grow only): calls on one model are serialised on ws_event, so a call
+    // on another stream cannot overwrite the workspace of one that is still running
+    float* d_ws = nullptr;
+    size_t ws_bytes = 0;
+    cudaEvent_t ws_event = nullptr;
 };
 
 struct bc_model {

@@ -262,6 +262,8 @@ int run_tile(bc_model* m, const uint8_t* desc, size_t dstride, size_t q0, int ro
 void bc_k2_free(bc_model* m) {
     if (!m->k2) return;
     for (double* p : m->k2->d_prefix) cudaFree(p);
+    if (m->k2->d_ws) cudaFree(m->k2->d_ws);
+    if (m->k2->ws_event) cudaEventDestroy(m->k2->ws_event);
     bc_k2_umma_free(m);
     delete m->k2;
     m->k2 = nullptr;
@@ -298,8 +300,8 @@ int bc_k2_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32
         return BC_EINVAL;
     }
     if (nq == 0) return BC_OK;
+    std::lock_guard<std::mutex> lock(m->k2_mu);  // held while the call is enqueued (the workspace is shared)
     {
-        std::lock_guard<std::mutex> lock(m->k2_mu);
         int rc = k2_prepare(m);
         if (rc) return rc;
     }
@@ -322,8 +324,19 @@ int bc_k2_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32
     if (tile < 128) tile = 128;
     if (tile > 65536) tile = 65536;
     if (tile > nq) tile = (size_t)bc_round_up((int64_t)nq, 128);
-    float* ws = nullptr;
-    if (floats_per_query) BC_CUDA_CHECK(cudaMallocAsync(&ws, tile * floats_per_query * 4, stream));
+    BcK2Plan* k2 = m->k2;
+    const size_t need = tile * floats_per_query * 4;
+    if (!k2->ws_event) BC_CUDA_CHECK(cudaEventCreateWithFlags(&k2->ws_event, cudaEventDisableTiming));
+    if (need > k2->ws_bytes) {
+        BC_CUDA_CHECK(cudaEventSynchronize(k2->ws_event));  // nothing may still be using the old workspace
+        if (k2->d_ws) cudaFree(k2->d_ws);
+        k2->d_ws = nullptr;
+        k2->ws_bytes = 0;
+        BC_CUDA_CHECK(cudaMalloc(&k2->d_ws, need));
+        k2->ws_bytes = need;
+    }
+    BC_CUDA_CHECK(cudaStreamWaitEvent(stream, k2->ws_event, 0));
+    float* ws = k2->d_ws;
     std::vector<float*> lam(n, nullptr);
     size_t off = 0;
     for (int v = 0; v < n; ++v)
@@ -339,6 +352,6 @@ int bc_k2_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32
         rc = fmt == BC_DESC_RANGE_U8 ? run_tile<BC_DESC_RANGE_U8>(m, d, dstride, q0, rows, tile, out, lam.data(), ld.data(), use_umma, stream)
                                      : run_tile<BC_DESC_RANGE_U16>(m, d, dstride, q0, rows, tile, out, lam.data(), ld.data(), use_umma, stream);
     }
-    if (ws) cudaFreeAsync(ws, stream);
+    BC_CUDA_CHECK(cudaEventRecord(k2->ws_event, stream));
     return rc;
 }

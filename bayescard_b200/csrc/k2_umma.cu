@@ -13,14 +13,15 @@
 // tests/test_gpu_parity.py::test_batched_large_domain_path).
 //
 // Shape of the kernel (sm_100a only):
-//   * CTA tile 128 queries x BN parent states (BN = 32 / 64 / 128), K in blocks of 32 floats = one
-//     128-byte swizzle atom;
+//   * CTA tile 128 queries x BN parent states (BN = 32 / 64 / 128 / 256), K in blocks of 32 floats = one
+//     128-byte swizzle atom; tiles are ordered so that co-resident CTAs share A panels and B panels through L2;
 //   * warp 0: TMA producer -- four 2-D tiled bulk tensor loads per stage (A_hi, A_lo, B_hi, B_lo; 128-byte
 //     swizzle, out-of-bounds rows zero filled) completing on an mbarrier (SASS UTMALDG);
-//   * warp 1: allocates TMEM and issues tcgen05.mma.cta_group::1.kind::tf32 (SASS UTCHMMA/UTC*MMA) from one
-//     thread, 12 MMAs (4 k-steps x 3 products) per stage, tcgen05.commit frees the stage;
-//   * warps 2-5: epilogue -- tcgen05.ld (SASS LDTM) of the 128 x BN fp32 accumulator, fused multiply into
-//     Lambda_pa;
+//   * warp 1: allocates TMEM (two accumulator buffers) and issues tcgen05.mma.cta_group::1.kind::tf32 (SASS
+//     UTCHMMA/UTC*MMA) from one thread, 12 MMAs (4 k-steps x 3 products) per stage in chunks of KS k-steps;
+//     tcgen05.commit frees the stage and hands every chunk sum to the epilogue;
+//   * warps 2..: epilogue -- tcgen05.ld (SASS LDTM) of every chunk sum into fp32 round-to-nearest register
+//     accumulators (the tensor core truncates: see UmmaCfg), then the fused multiply into Lambda_pa;
 //   * both operands K-major: Lambda rows are K-contiguous as produced by the previous edge, the CPT is
 //     stored transposed (and pre-split) once per model.
 // The range mask of column v and the hi/lo split of Lambda_v are one elementwise pass (k2_split_kernel).
@@ -37,7 +38,7 @@ struct BcUmmaPlan {
 
 namespace {
 
-constexpr int kBM = 128, kBK = 32, kStages = 3, kThreads = 192;
+constexpr int kBM = 128, kBK = 32;
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -91,7 +92,11 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t da, uint64_t
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 columns of fp32 from TMEM, NO wait: pair with tmem_ld_wait() before the registers are read
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float* v) {
     uint32_t* r = reinterpret_cast<uint32_t*>(v);
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -103,34 +108,73 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-template <int BN>
-__global__ void __launch_bounds__(kThreads, 1)
+// Geometry of one kernel variant.  BN = parent states per CTA tile, KS = k-steps (of 8 TF32) accumulated inside
+// TMEM before the partial sum is drained into fp32 registers.
+//
+// Why drain at all: tcgen05.mma adds into its fp32 accumulator with TRUNCATION, and every quantity of this path is
+// a non-negative probability, so the truncation errors do not cancel -- measured on the first version of this
+// kernel (one accumulator over the whole K loop): -2e-8 relative per MMA, i.e. -7e-6 per edge at K = 1000 and
+// -3.3e-4 over the 51 internal edges of a 100-column tree, far outside the 1e-5 budget.  Here a TMEM accumulator
+// only ever holds a chunk of KS k-steps; the chunk's two small correction products (A_lo.B_hi, A_hi.B_lo, 2^-11
+// of the result) are issued FIRST, while the accumulator is still tiny, so only the KS main products truncate at
+// full magnitude; the epilogue warps add the chunk sums in fp32 round-to-nearest registers while the tensor core
+// fills the other TMEM buffer.
+template <int BN_, int KS_>
+struct UmmaCfg {
+    static constexpr int BN = BN_, KS = KS_;
+    static constexpr int EPI_COLS = BN < 128 ? BN : 128;      // accumulator columns per epilogue thread (registers)
+    static constexpr int EPI_WARPS = 4 * (BN / EPI_COLS);     // 4 TMEM lane quarters x column groups
+    static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+    static constexpr int A_BYTES = kBM * kBK * 4, B_BYTES = BN * kBK * 4, STAGE = 2 * A_BYTES + 2 * B_BYTES;
+    static constexpr int STAGES = BN >= 256 ? 2 : BN >= 128 ? 3 : 4;
+    static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // two accumulator buffers; power of two >= 32
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE + 1024 /* alignment slack */ + 256 /* barriers */;
+    static constexpr int CHUNKS_PER_KB = (kBK / 8) / KS;
+};
+
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS, 1)
 k2_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, int rows, int N,
-               int num_kb, float* __restrict__ lam_pa, int ld_pa, int accumulate) {
-    constexpr int A_BYTES = kBM * kBK * 4, B_BYTES = BN * kBK * 4, STAGE = 2 * A_BYTES + 2 * B_BYTES;
+               int num_kb, int n_col_tiles, int n_row_tiles, float* __restrict__ lam_pa, int ld_pa, int accumulate) {
+    constexpr int BN = Cfg::BN, KS = Cfg::KS, A_BYTES = Cfg::A_BYTES, B_BYTES = Cfg::B_BYTES, STAGE = Cfg::STAGE;
+    constexpr int kStg = Cfg::STAGES;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // the dynamic shared window is only 16 B aligned by contract: round up to the 1024 B the swizzle needs
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * STAGE);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
-    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kStages), tfull = smem_u32(bars + 2 * kStages);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStg * STAGE);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStg + 4);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kStg);
+    const uint32_t acc_full0 = smem_u32(bars + 2 * kStg), acc_empty0 = smem_u32(bars + 2 * kStg + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * BN;
+    // tile order: groups of up to 8 column tiles; inside a group the column index runs fastest, so the CTAs that
+    // are resident together cover ~8 column tiles x ~18 row tiles: each A panel is read from HBM once and shared
+    // through L2 by its column tiles, and a group's B panels stay L2 resident while the row tiles stream past
+    int tile = blockIdx.x;
+    const int group_cols = 8;
+    const int group = tile / (group_cols * n_row_tiles);
+    const int first_col = group * group_cols;
+    const int cols_here = n_col_tiles - first_col < group_cols ? n_col_tiles - first_col : group_cols;
+    tile -= group * group_cols * n_row_tiles;
+    const int m0 = (tile / cols_here) * kBM, n0 = (first_col + tile % cols_here) * BN;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) {
+        for (int s = 0; s < kStg; ++s) {
             mbar_init(full0 + 8 * s, 1);
             mbar_init(empty0 + 8 * s, 1);
         }
-        mbar_init(tfull, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(acc_full0 + 8 * b, 1);
+            mbar_init(acc_empty0 + 8 * b, Cfg::EPI_WARPS);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {  // TMEM: BN fp32 columns x 128 lanes
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN)
+    if (warp == 1) {  // TMEM: two accumulator buffers of BN fp32 columns x 128 lanes
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(Cfg::TMEM_COLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -142,8 +186,8 @@ k2_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     if (warp == 0) {
         if (lane == 0) {  // ---- TMA producer
             for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % kStages;
-                mbar_wait(empty0 + 8 * s, ((kb / kStages) & 1) ^ 1);
+                const int s = kb % kStg;
+                mbar_wait(empty0 + 8 * s, ((kb / kStg) & 1) ^ 1);
                 const uint32_t base = smem_u32(smem + s * STAGE), bar = full0 + 8 * s;
                 mbar_expect_tx(bar, STAGE);
                 tma_load_2d(base, &tm_a_hi, kb * kBK, m0, bar);
@@ -156,50 +200,86 @@ k2_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         if (lane == 0) {  // ---- MMA issuer
             // instruction descriptor: D = F32, A = B = TF32, both K-major, N = BN, M = 128
             constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+            int chunk = 0;
             for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % kStages;
-                mbar_wait(full0 + 8 * s, (kb / kStages) & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const int s = kb % kStg;
+                mbar_wait(full0 + 8 * s, (kb / kStg) & 1);
                 const uint32_t base = smem_u32(smem + s * STAGE);
                 const uint64_t a_hi = umma_desc(base), a_lo = umma_desc(base + A_BYTES);
                 const uint64_t b_hi = umma_desc(base + 2 * A_BYTES), b_lo = umma_desc(base + 2 * A_BYTES + B_BYTES);
 #pragma unroll
-                for (int kk = 0; kk < kBK / 8; ++kk) {  // 8 TF32 = 32 bytes per MMA: +2 in the 16-byte address field
-                    const uint64_t o = (uint64_t)(kk * 2);
-                    umma_tf32(tmem, a_lo + o, b_hi + o, idesc, (kb | kk) != 0);
-                    umma_tf32(tmem, a_hi + o, b_lo + o, idesc, 1);
-                    umma_tf32(tmem, a_hi + o, b_hi + o, idesc, 1);
+                for (int c = 0; c < Cfg::CHUNKS_PER_KB; ++c, ++chunk) {
+                    const int buf = chunk & 1;
+                    mbar_wait(acc_empty0 + 8 * buf, ((chunk >> 1) & 1) ^ 1);  // the epilogue has drained this buffer
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t d = tmem + (uint32_t)(buf * BN);
+                    // 8 TF32 = 32 bytes per MMA: +2 in the 16-byte address field of the descriptors
+#pragma unroll
+                    for (int kk = c * KS; kk < (c + 1) * KS; ++kk) {   // the small products first (see UmmaCfg)
+                        const uint64_t o = (uint64_t)(kk * 2);
+                        umma_tf32(d, a_lo + o, b_hi + o, idesc, kk != c * KS);
+                        umma_tf32(d, a_hi + o, b_lo + o, idesc, 1);
+                    }
+#pragma unroll
+                    for (int kk = c * KS; kk < (c + 1) * KS; ++kk) {
+                        const uint64_t o = (uint64_t)(kk * 2);
+                        umma_tf32(d, a_hi + o, b_hi + o, idesc, 1);
+                    }
+                    umma_commit(acc_full0 + 8 * buf);  // chunk sum complete -> epilogue
                 }
                 umma_commit(empty0 + 8 * s);  // the stage is free once these MMAs have read it
             }
-            umma_commit(tfull);               // accumulator complete
         }
-    } else {  // ---- epilogue: warps 2..5 own TMEM lane quarters (warp % 4)
-        const int quarter = warp & 3;
-        mbar_wait(tfull, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int r = m0 + quarter * 32 + lane;
-        float* dst_row = lam_pa + (size_t)r * ld_pa + n0;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            float v[32];
-            tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
-            if (r < rows) {
+    } else {  // ---- epilogue warps: TMEM lane quarter = warp % 4 (hardware rule), column group = (warp - 2) / 4
+        constexpr int EC = Cfg::EPI_COLS;
+        const int quarter = warp & 3, cgrp = (warp - 2) >> 2;
+        const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cgrp * EC);
+        float acc[EC];
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const int n = n0 + c0 + j;
-                    float* d = dst_row + c0 + j;
-                    if (n + 3 < N) {  // ld_pa and n are multiples of 4: 16 B aligned
-                        float4 x = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                        if (accumulate) {
-                            const float4 o = *reinterpret_cast<const float4*>(d);
-                            x.x *= o.x; x.y *= o.y; x.z *= o.z; x.w *= o.w;
-                        }
-                        *reinterpret_cast<float4*>(d) = x;
-                    } else {
-                        for (int t = 0; t < 4; ++t)
-                            if (n + t < N) d[t] = accumulate ? d[t] * v[j + t] : v[j + t];
+        for (int j = 0; j < EC; ++j) acc[j] = 0.f;
+        const int n_chunks = num_kb * Cfg::CHUNKS_PER_KB;
+        for (int chunk = 0; chunk < n_chunks; ++chunk) {
+            const int buf = chunk & 1;
+            mbar_wait(acc_full0 + 8 * buf, (chunk >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t src = lane_base + (uint32_t)(buf * BN);
+            float v0[32], v1[32];
+            tmem_ld32_nowait(src, v0);
+#pragma unroll
+            for (int c0 = 0; c0 < EC; c0 += 64) {
+                tmem_ld_wait();
+                if (c0 + 32 < EC) tmem_ld32_nowait(src + (uint32_t)(c0 + 32), v1);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[c0 + j] += v0[j];
+                if (c0 + 32 < EC) {
+                    tmem_ld_wait();
+                    if (c0 + 64 < EC) tmem_ld32_nowait(src + (uint32_t)(c0 + 64), v0);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[c0 + 32 + j] += v1[j];
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty0 + 8 * buf);
+        }
+        const int r = m0 + quarter * 32 + lane;
+        if (r < rows) {
+            float* dst_row = lam_pa + (size_t)r * ld_pa + n0 + cgrp * EC;
+#pragma unroll
+            for (int j = 0; j < EC; j += 4) {
+                const int n = n0 + cgrp * EC + j;
+                float* d = dst_row + j;
+                if (n + 3 < N) {  // ld_pa and n are multiples of 4: 16 B aligned
+                    float4 x = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+                    if (accumulate) {
+                        const float4 o = *reinterpret_cast<const float4*>(d);
+                        x.x *= o.x; x.y *= o.y; x.z *= o.z; x.w *= o.w;
                     }
+                    *reinterpret_cast<float4*>(d) = x;
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+                        if (n + t < N) d[t] = accumulate ? d[t] * acc[j + t] : acc[j + t];
                 }
             }
         }
@@ -208,7 +288,7 @@ k2_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(BN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(Cfg::TMEM_COLS) : "memory");
     }
 }
 
@@ -283,15 +363,32 @@ int encode_map(EncodeTiledFn fn, CUtensorMap* map, const float* base, uint64_t i
     return BC_OK;
 }
 
-template <int BN>
+template <int BN, int KS>
 int launch_edge(const CUtensorMap* maps, int rows, int N, int num_kb, float* lam_pa, int ld_pa, int accumulate, cudaStream_t st) {
-    constexpr size_t smem = (size_t)kStages * (2 * kBM * kBK * 4 + 2 * BN * kBK * 4) + 1024 /* alignment slack */ + 128;
-    BC_CUDA_CHECK(cudaFuncSetAttribute(k2_umma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((N + BN - 1) / BN, (rows + kBM - 1) / kBM);
-    k2_umma_kernel<BN><<<grid, kThreads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], rows, N, num_kb, lam_pa, ld_pa, accumulate);
+    using Cfg = UmmaCfg<BN, KS>;
+    static bool attr_set[64] = {};  // per device (the attribute lives in the device's context) and instantiation
+    int dev = 0;
+    BC_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        BC_CUDA_CHECK(cudaFuncSetAttribute(k2_umma_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    const int n_col_tiles = (N + BN - 1) / BN, n_row_tiles = (rows + kBM - 1) / kBM;
+    k2_umma_kernel<Cfg><<<n_col_tiles * n_row_tiles, Cfg::THREADS, Cfg::SMEM, st>>>(maps[0], maps[1], maps[2], maps[3], rows, N, num_kb,
+                                                                                   n_col_tiles, n_row_tiles, lam_pa, ld_pa, accumulate);
     BC_CUDA_CHECK(cudaGetLastError());
     bc_count_launch();
     return BC_OK;
+}
+
+template <int BN>
+int launch_edge_ks(int ks, const CUtensorMap* maps, int rows, int N, int num_kb, float* lam_pa, int ld_pa, int accumulate,
+                   cudaStream_t st) {
+    switch (ks) {
+        case 1: return launch_edge<BN, 1>(maps, rows, N, num_kb, lam_pa, ld_pa, accumulate, st);
+        case 2: return launch_edge<BN, 2>(maps, rows, N, num_kb, lam_pa, ld_pa, accumulate, st);
+        default: return launch_edge<BN, 4>(maps, rows, N, num_kb, lam_pa, ld_pa, accumulate, st);
+    }
 }
 
 int umma_prepare(bc_model* m) {
@@ -331,8 +428,7 @@ int umma_prepare(bc_model* m) {
 
 int bc_k2_umma_edge(bc_model* m, const uint8_t* desc, size_t dstride, int fmt, size_t q0, int rows, int v, float* lam_v,
                     float* lam_lo, int ld_v, float* lam_pa, int ld_pa, int accumulate, cudaStream_t st) {
-    {
-        std::lock_guard<std::mutex> lock(m->k2_mu);
+    {   // the caller (bc_k2_launch) holds m->k2_mu
         int rc = umma_prepare(m);
         if (rc) return rc;
     }
@@ -351,7 +447,17 @@ int bc_k2_umma_edge(bc_model* m, const uint8_t* desc, size_t dstride, int fmt, s
     BC_CUDA_CHECK(cudaGetLastError());
     bc_count_launch();
     EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(u->encode);
-    const int BN = N <= 32 ? 32 : N <= 64 ? 64 : 128;
+    // tile width: the widest tile that the edge fills; BC_K2_UMMA_BN / BC_K2_UMMA_KS override it for experiments
+    int BN = N <= 32 ? 32 : N <= 64 ? 64 : N <= 128 ? 128 : 256;
+    int KS = 2;
+    if (const char* e = std::getenv("BC_K2_UMMA_BN")) {
+        const int x = std::atoi(e);
+        if (x == 32 || x == 64 || x == 128 || x == 256) BN = x;
+    }
+    if (const char* e = std::getenv("BC_K2_UMMA_KS")) {
+        const int x = std::atoi(e);
+        if (x == 1 || x == 2 || x == 4) KS = x;
+    }
     CUtensorMap maps[4];
     int rc;
     if ((rc = encode_map(fn, &maps[0], lam_v, (uint64_t)ldk, (uint64_t)rows, (uint64_t)ld_v, kBM))) return rc;
@@ -360,9 +466,10 @@ int bc_k2_umma_edge(bc_model* m, const uint8_t* desc, size_t dstride, int fmt, s
     if ((rc = encode_map(fn, &maps[3], u->d_tt_lo[v], (uint64_t)ldk, (uint64_t)N, (uint64_t)ldk, (uint32_t)BN))) return rc;
     const int num_kb = ldk / kBK;
     switch (BN) {
-        case 32: return launch_edge<32>(maps, rows, N, num_kb, lam_pa, ld_pa, accumulate, st);
-        case 64: return launch_edge<64>(maps, rows, N, num_kb, lam_pa, ld_pa, accumulate, st);
-        default: return launch_edge<128>(maps, rows, N, num_kb, lam_pa, ld_pa, accumulate, st);
+        case 32: return launch_edge_ks<32>(KS, maps, rows, N, num_kb, lam_pa, ld_pa, accumulate, st);
+        case 64: return launch_edge_ks<64>(KS, maps, rows, N, num_kb, lam_pa, ld_pa, accumulate, st);
+        case 128: return launch_edge_ks<128>(KS, maps, rows, N, num_kb, lam_pa, ld_pa, accumulate, st);
+        default: return launch_edge_ks<256>(KS, maps, rows, N, num_kb, lam_pa, ld_pa, accumulate, st);
     }
 }
 

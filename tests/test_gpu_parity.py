@@ -222,9 +222,11 @@ def test_replicas_shard_a_batch():
 
 
 @pytest.mark.parametrize("shape", [(8, 300, 6000), (20, 10, 5000), (12, [7, 130, 33, 257, 64, 5, 90, 200, 17, 128, 40, 3], 4001),
-                                   (1, 50, 100)])
+                                   (1, 50, 100), (10, 1000, 1024), (40, 260, 1500)])
 def test_batched_large_domain_path(shape):
-    """K2 (BASELINE.json config 4): synthetic random trees, RANGE_U16 rows, FP32 SIMT and tensor-core GEMM edges."""
+    """K2 (BASELINE.json config 4): synthetic random trees, RANGE_U16 rows, FP32 SIMT and tensor-core GEMM edges.
+    The (10, 1000) and (40, 260) shapes are the ones that expose accumulator truncation inside the tensor core: with
+    one TMEM accumulator over the whole K loop they came out 3e-5 low (see UmmaCfg in k2_umma.cu)."""
     from bayescard_b200.synth import make_tree_model, pack_ranges_u16, random_range_queries
 
     n_cols, card, nq = shape
