@@ -305,25 +305,57 @@ int bc_k2_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32
         int rc = k2_prepare(m);
         if (rc) return rc;
     }
-    // workspace: one Lambda matrix per node that has children, for a tile of queries
+    // Workspace: Lambda matrices for a tile of queries.  Lambda_v is first written by the edge of v's highest-numbered
+    // child and last read by edge v itself (edges run v = n-1 .. 1, stream ordered), so the matrices share a few
+    // SLOTS by lifetime -- O(depth) of them instead of one per internal node -- and the tile can be that much taller.
     const int n = m->n;
-    std::vector<int> ld(n, 0);
-    size_t floats_per_query = 0;
+    std::vector<int> ld(n, 0), slot(n, -1);
+    int max_ld = 0;
     for (int v = 0; v < n; ++v)
         if (m->k2->is_internal[v]) {
             ld[v] = (int)bc_round_up(m->nodes[v].card, 32);  // 128 B rows: what the TMA path wants
-            floats_per_query += (size_t)ld[v] * (use_umma ? 2 : 1);  // + the low halves for 3xTF32
+            if (ld[v] > max_ld) max_ld = ld[v];
         }
-    size_t budget = (size_t)4 << 30;
+    int n_slots = 0;
+    {
+        std::vector<int> free_slots;
+        for (int v = n - 1; v >= 1; --v) {
+            const int pa = m->nodes[v].parent;
+            if (slot[pa] < 0) {
+                if (free_slots.empty()) slot[pa] = n_slots++;
+                else { slot[pa] = free_slots.back(); free_slots.pop_back(); }
+            }
+            if (slot[v] >= 0) free_slots.push_back(slot[v]);  // edge v was the last reader of Lambda_v
+        }
+    }
+    const size_t slot_floats = (size_t)max_ld * (use_umma ? 2 : 1);  // + the low halves for 3xTF32
+    const size_t floats_per_query = slot_floats * (size_t)n_slots;
+    size_t budget = (size_t)32 << 30;
+    {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            const size_t have = free_b + m->k2->ws_bytes;  // what is free once the cached workspace is counted
+            if (budget > have / 2) budget = have / 2;
+        } else {
+            cudaGetLastError();
+        }
+    }
     if (const char* env = std::getenv("BC_K2_WORKSPACE_MB")) {
         const long long v = std::atoll(env);
         if (v >= 16) budget = (size_t)v << 20;
     }
     size_t tile = floats_per_query ? budget / (floats_per_query * 4) : nq;
-    tile = tile / 128 * 128;
-    if (tile < 128) tile = 128;
-    if (tile > 65536) tile = 65536;
-    if (tile > nq) tile = (size_t)bc_round_up((int64_t)nq, 128);
+    if (tile > 262144) tile = 262144;
+    if (tile >= nq) {
+        tile = (size_t)bc_round_up((int64_t)nq, 128);
+    } else {
+        // equal tiles, each a whole number of 128-row CTA tiles and -- when tall enough -- of 148-SM waves
+        const size_t wave = (size_t)m->sm_count * 128;
+        tile = tile >= wave ? tile / wave * wave : (tile / 128 ? tile / 128 * 128 : 128);
+        const size_t n_tiles = (nq + tile - 1) / tile;
+        const size_t even = (size_t)bc_round_up((int64_t)((nq + n_tiles - 1) / n_tiles), 128);
+        if (even < tile) tile = even;
+    }
     BcK2Plan* k2 = m->k2;
     const size_t need = tile * floats_per_query * 4;
     if (!k2->ws_event) BC_CUDA_CHECK(cudaEventCreateWithFlags(&k2->ws_event, cudaEventDisableTiming));
@@ -338,12 +370,8 @@ int bc_k2_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32
     BC_CUDA_CHECK(cudaStreamWaitEvent(stream, k2->ws_event, 0));
     float* ws = k2->d_ws;
     std::vector<float*> lam(n, nullptr);
-    size_t off = 0;
     for (int v = 0; v < n; ++v)
-        if (ld[v]) {
-            lam[v] = ws + off;
-            off += tile * (size_t)ld[v] * (use_umma ? 2 : 1);
-        }
+        if (slot[v] >= 0) lam[v] = ws + (size_t)slot[v] * tile * slot_floats;
     const size_t dstride = (size_t)bc_model_desc_stride(m, fmt);
     const uint8_t* d = static_cast<const uint8_t*>(desc);
     int rc = BC_OK;

@@ -38,7 +38,7 @@ struct BcUmmaPlan {
 
 namespace {
 
-constexpr int kBM = 128, kBK = 32;
+constexpr int kBM = 128, kLdkAlign = 32;  // K is padded to 32 floats whatever the stage depth
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -78,9 +78,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
         : "memory");
 }
-// K-major, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO = 1 (unused), version 1 (sm_100)
+// K-major shared-memory operand descriptor.  128-byte swizzle (BK = 32 floats): rows of 128 B, 8-row groups 1024 B
+// apart (SBO), layout type 2.  64-byte swizzle (BK = 16 floats): rows of 64 B, 8-row groups 512 B apart, layout type 4.
+// LBO = 1 (unused for swizzled K-major), version 1 (sm_100).
+template <int BK>
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
-    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+    constexpr uint64_t sbo = (BK == 32 ? 1024 : 512) >> 4, layout = BK == 32 ? 2 : 4;
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -122,25 +126,32 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // of the result) are issued FIRST, while the accumulator is still tiny, so only the KS main products truncate at
 // full magnitude; the epilogue warps add the chunk sums in fp32 round-to-nearest registers while the tensor core
 // fills the other TMEM buffer.
-template <int BN_, int KS_>
+//
+// BK = floats of K per pipeline stage (32: 128-byte swizzle, 16: 64-byte swizzle -- half the bytes per stage, so
+// twice the stages in the same shared memory: what hides the TMA latency at BN = 256), EC = accumulator columns
+// per epilogue thread, OCC = CTAs per SM the variant is sized for.
+template <int BN_, int BK_, int KS_, int EC_, int OCC_>
 struct UmmaCfg {
-    static constexpr int BN = BN_, KS = KS_;
-    static constexpr int EPI_COLS = BN < 128 ? BN : 128;      // accumulator columns per epilogue thread (registers)
+    static constexpr int BN = BN_, BK = BK_, KS = KS_, OCC = OCC_;
+    static constexpr int EPI_COLS = EC_;                      // accumulator columns per epilogue thread (registers)
     static constexpr int EPI_WARPS = 4 * (BN / EPI_COLS);     // 4 TMEM lane quarters x column groups
     static constexpr int THREADS = 64 + 32 * EPI_WARPS;
-    static constexpr int A_BYTES = kBM * kBK * 4, B_BYTES = BN * kBK * 4, STAGE = 2 * A_BYTES + 2 * B_BYTES;
-    static constexpr int STAGES = BN >= 256 ? 2 : BN >= 128 ? 3 : 4;
+    static constexpr int A_BYTES = kBM * BK * 4, B_BYTES = BN * BK * 4, STAGE = 2 * A_BYTES + 2 * B_BYTES;
+    static constexpr int BUDGET = (OCC == 1 ? 200 : 96) * 1024;
+    static constexpr int STAGES = BUDGET / STAGE > 6 ? 6 : BUDGET / STAGE;
     static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // two accumulator buffers; power of two >= 32
     static constexpr size_t SMEM = (size_t)STAGES * STAGE + 1024 /* alignment slack */ + 256 /* barriers */;
-    static constexpr int CHUNKS_PER_KB = (kBK / 8) / KS;
+    static constexpr int CHUNKS_PER_KB = (BK / 8) / KS;
+    static_assert(BK == 32 || BK == 16, "one swizzle atom per stage row");
+    static_assert((BK / 8) % KS == 0 && STAGES >= 2 && BN % EC_ == 0 && TMEM_COLS * OCC <= 512, "bad variant");
 };
 
 template <class Cfg>
-__global__ void __launch_bounds__(Cfg::THREADS, 1)
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::OCC)
 k2_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, int rows, int N,
                int num_kb, int n_col_tiles, int n_row_tiles, float* __restrict__ lam_pa, int ld_pa, int accumulate) {
-    constexpr int BN = Cfg::BN, KS = Cfg::KS, A_BYTES = Cfg::A_BYTES, B_BYTES = Cfg::B_BYTES, STAGE = Cfg::STAGE;
+    constexpr int BN = Cfg::BN, KS = Cfg::KS, kBK = Cfg::BK, A_BYTES = Cfg::A_BYTES, B_BYTES = Cfg::B_BYTES, STAGE = Cfg::STAGE;
     constexpr int kStg = Cfg::STAGES;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // the dynamic shared window is only 16 B aligned by contract: round up to the 1024 B the swizzle needs
@@ -205,8 +216,8 @@ k2_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                 const int s = kb % kStg;
                 mbar_wait(full0 + 8 * s, (kb / kStg) & 1);
                 const uint32_t base = smem_u32(smem + s * STAGE);
-                const uint64_t a_hi = umma_desc(base), a_lo = umma_desc(base + A_BYTES);
-                const uint64_t b_hi = umma_desc(base + 2 * A_BYTES), b_lo = umma_desc(base + 2 * A_BYTES + B_BYTES);
+                const uint64_t a_hi = umma_desc<kBK>(base), a_lo = umma_desc<kBK>(base + A_BYTES);
+                const uint64_t b_hi = umma_desc<kBK>(base + 2 * A_BYTES), b_lo = umma_desc<kBK>(base + 2 * A_BYTES + B_BYTES);
 #pragma unroll
                 for (int c = 0; c < Cfg::CHUNKS_PER_KB; ++c, ++chunk) {
                     const int buf = chunk & 1;
@@ -347,13 +358,13 @@ __global__ void k2_transpose_split_kernel(const float* __restrict__ T, int K, in
 }
 
 int encode_map(EncodeTiledFn fn, CUtensorMap* map, const float* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
-               uint32_t box_rows) {
+               uint32_t box_rows, int bk) {
     cuuint64_t dims[2] = {inner, outer};
     cuuint64_t strides[1] = {ld_elems * 4};
-    cuuint32_t box[2] = {(cuuint32_t)kBK, box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)bk, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         bc_set_error("cuTensorMapEncodeTiled failed (%d) for a %llu x %llu fp32 tensor", (int)r, (unsigned long long)outer,
@@ -363,9 +374,9 @@ int encode_map(EncodeTiledFn fn, CUtensorMap* map, const float* base, uint64_t i
     return BC_OK;
 }
 
-template <int BN, int KS>
-int launch_edge(const CUtensorMap* maps, int rows, int N, int num_kb, float* lam_pa, int ld_pa, int accumulate, cudaStream_t st) {
-    using Cfg = UmmaCfg<BN, KS>;
+template <class Cfg>
+int launch_edge(EncodeTiledFn fn, const float* a_hi, const float* a_lo, int ld_a, const float* b_hi, const float* b_lo, int ldk,
+                int rows, int N, float* lam_pa, int ld_pa, int accumulate, cudaStream_t st) {
     static bool attr_set[64] = {};  // per device (the attribute lives in the device's context) and instantiation
     int dev = 0;
     BC_CUDA_CHECK(cudaGetDevice(&dev));
@@ -373,22 +384,18 @@ int launch_edge(const CUtensorMap* maps, int rows, int N, int num_kb, float* lam
         BC_CUDA_CHECK(cudaFuncSetAttribute(k2_umma_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
-    const int n_col_tiles = (N + BN - 1) / BN, n_row_tiles = (rows + kBM - 1) / kBM;
-    k2_umma_kernel<Cfg><<<n_col_tiles * n_row_tiles, Cfg::THREADS, Cfg::SMEM, st>>>(maps[0], maps[1], maps[2], maps[3], rows, N, num_kb,
-                                                                                   n_col_tiles, n_row_tiles, lam_pa, ld_pa, accumulate);
+    CUtensorMap maps[4];
+    int rc;
+    if ((rc = encode_map(fn, &maps[0], a_hi, (uint64_t)ldk, (uint64_t)rows, (uint64_t)ld_a, kBM, Cfg::BK))) return rc;
+    if ((rc = encode_map(fn, &maps[1], a_lo, (uint64_t)ldk, (uint64_t)rows, (uint64_t)ld_a, kBM, Cfg::BK))) return rc;
+    if ((rc = encode_map(fn, &maps[2], b_hi, (uint64_t)ldk, (uint64_t)N, (uint64_t)ldk, (uint32_t)Cfg::BN, Cfg::BK))) return rc;
+    if ((rc = encode_map(fn, &maps[3], b_lo, (uint64_t)ldk, (uint64_t)N, (uint64_t)ldk, (uint32_t)Cfg::BN, Cfg::BK))) return rc;
+    const int n_col_tiles = (N + Cfg::BN - 1) / Cfg::BN, n_row_tiles = (rows + kBM - 1) / kBM;
+    k2_umma_kernel<Cfg><<<n_col_tiles * n_row_tiles, Cfg::THREADS, Cfg::SMEM, st>>>(
+        maps[0], maps[1], maps[2], maps[3], rows, N, ldk / Cfg::BK, n_col_tiles, n_row_tiles, lam_pa, ld_pa, accumulate);
     BC_CUDA_CHECK(cudaGetLastError());
     bc_count_launch();
     return BC_OK;
-}
-
-template <int BN>
-int launch_edge_ks(int ks, const CUtensorMap* maps, int rows, int N, int num_kb, float* lam_pa, int ld_pa, int accumulate,
-                   cudaStream_t st) {
-    switch (ks) {
-        case 1: return launch_edge<BN, 1>(maps, rows, N, num_kb, lam_pa, ld_pa, accumulate, st);
-        case 2: return launch_edge<BN, 2>(maps, rows, N, num_kb, lam_pa, ld_pa, accumulate, st);
-        default: return launch_edge<BN, 4>(maps, rows, N, num_kb, lam_pa, ld_pa, accumulate, st);
-    }
 }
 
 int umma_prepare(bc_model* m) {
@@ -411,7 +418,7 @@ int umma_prepare(bc_model* m) {
         const BcNodeRec& nd = m->nodes[v];
         const int K = nd.card, N = nd.card_pa;
         if (K < 64 || N < 16) continue;  // tiny edges stay on the SIMT kernel
-        const int ldk = (int)bc_round_up(K, kBK);
+        const int ldk = (int)bc_round_up(K, kLdkAlign);
         u->ldk[v] = ldk;
         BC_CUDA_CHECK(cudaMalloc(&u->d_tt_hi[v], (size_t)N * ldk * 4));
         BC_CUDA_CHECK(cudaMalloc(&u->d_tt_lo[v], (size_t)N * ldk * 4));
@@ -447,29 +454,20 @@ int bc_k2_umma_edge(bc_model* m, const uint8_t* desc, size_t dstride, int fmt, s
     BC_CUDA_CHECK(cudaGetLastError());
     bc_count_launch();
     EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(u->encode);
-    // tile width: the widest tile that the edge fills; BC_K2_UMMA_BN / BC_K2_UMMA_KS override it for experiments
-    int BN = N <= 32 ? 32 : N <= 64 ? 64 : N <= 128 ? 128 : 256;
-    int KS = 2;
-    if (const char* e = std::getenv("BC_K2_UMMA_BN")) {
-        const int x = std::atoi(e);
-        if (x == 32 || x == 64 || x == 128 || x == 256) BN = x;
-    }
-    if (const char* e = std::getenv("BC_K2_UMMA_KS")) {
-        const int x = std::atoi(e);
-        if (x == 1 || x == 2 || x == 4) KS = x;
-    }
-    CUtensorMap maps[4];
-    int rc;
-    if ((rc = encode_map(fn, &maps[0], lam_v, (uint64_t)ldk, (uint64_t)rows, (uint64_t)ld_v, kBM))) return rc;
-    if ((rc = encode_map(fn, &maps[1], lam_lo, (uint64_t)ldk, (uint64_t)rows, (uint64_t)ld_v, kBM))) return rc;
-    if ((rc = encode_map(fn, &maps[2], u->d_tt_hi[v], (uint64_t)ldk, (uint64_t)N, (uint64_t)ldk, (uint32_t)BN))) return rc;
-    if ((rc = encode_map(fn, &maps[3], u->d_tt_lo[v], (uint64_t)ldk, (uint64_t)N, (uint64_t)ldk, (uint32_t)BN))) return rc;
-    const int num_kb = ldk / kBK;
-    switch (BN) {
-        case 32: return launch_edge_ks<32>(KS, maps, rows, N, num_kb, lam_pa, ld_pa, accumulate, st);
-        case 64: return launch_edge_ks<64>(KS, maps, rows, N, num_kb, lam_pa, ld_pa, accumulate, st);
-        case 128: return launch_edge_ks<128>(KS, maps, rows, N, num_kb, lam_pa, ld_pa, accumulate, st);
-        default: return launch_edge_ks<256>(KS, maps, rows, N, num_kb, lam_pa, ld_pa, accumulate, st);
+    // Variant: the widest tile the edge fills.  Letters select the same kernels by hand (BC_K2_UMMA_VARIANT, for
+    // the sweeps in profiles/): A = 128x256 tile, 32-float stages (2 stages); B = 128x256, 16-float stages (4);
+    // C = 128x128, 16-float stages (6); D = 128x128, 32-float stages (3).
+    char variant = N > 128 ? 'B' : N > 64 ? 'D' : N > 32 ? 'E' : 'F';
+    if (const char* e = std::getenv("BC_K2_UMMA_VARIANT"))
+        if (*e >= 'A' && *e <= 'D' && N > 64) variant = *e;
+    const float *bh = u->d_tt_hi[v], *bl = u->d_tt_lo[v];
+    switch (variant) {
+        case 'A': return launch_edge<UmmaCfg<256, 32, 2, 128, 1>>(fn, lam_v, lam_lo, ld_v, bh, bl, ldk, rows, N, lam_pa, ld_pa, accumulate, st);
+        case 'B': return launch_edge<UmmaCfg<256, 16, 2, 128, 1>>(fn, lam_v, lam_lo, ld_v, bh, bl, ldk, rows, N, lam_pa, ld_pa, accumulate, st);
+        case 'C': return launch_edge<UmmaCfg<128, 16, 2, 128, 1>>(fn, lam_v, lam_lo, ld_v, bh, bl, ldk, rows, N, lam_pa, ld_pa, accumulate, st);
+        case 'D': return launch_edge<UmmaCfg<128, 32, 2, 128, 1>>(fn, lam_v, lam_lo, ld_v, bh, bl, ldk, rows, N, lam_pa, ld_pa, accumulate, st);
+        case 'E': return launch_edge<UmmaCfg<64, 32, 2, 64, 1>>(fn, lam_v, lam_lo, ld_v, bh, bl, ldk, rows, N, lam_pa, ld_pa, accumulate, st);
+        default: return launch_edge<UmmaCfg<32, 32, 2, 32, 1>>(fn, lam_v, lam_lo, ld_v, bh, bl, ldk, rows, N, lam_pa, ld_pa, accumulate, st);
     }
 }
 

@@ -28,6 +28,7 @@
 // emit no instruction; the number of FMAs actually emitted is reported in the header comment of
 // the generated source (BC_SPEC_FFMA) and is what the roofline accounting uses.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -43,6 +44,19 @@ std::string fhex(float x) {
     return s;
 }
 inline std::string I(long long x) { return std::to_string(x); }
+
+// Experiment knobs (they are part of the image hash, so every variant has its own cache entry):
+//   BC_SPEC_SYNC_EVERY=N   re-align the warps of a CTA with bar.sync every N generated instructions.  The code of
+//                          a big tree is a straight line of 100-400 KB, larger than the SM's instruction cache;
+//                          warps that drift apart each stream it from L2 on their own, warps kept within one
+//                          cache-sized window of each other share the fetched lines.
+//   BC_SPEC_THREADS / BC_SPEC_MIN_BLOCKS   override the CTA geometry chosen by bc_spec_geometry.
+int env_int(const char* name, int dflt) {
+    const char* e = std::getenv(name);
+    if (!e || !*e) return dflt;
+    const int v = std::atoi(e);
+    return v >= 0 ? v : dflt;
+}
 
 struct Gen {
     const bc_model& m;
@@ -70,7 +84,14 @@ struct Gen {
     std::string F() { return "%f" + I(++nf); }
     std::string P() { return "%p" + I(++np); }
     std::string R() { return "%r" + I(++nr); }
-    void line(const std::string& s) { out += "    "; out += s; out += '\n'; }
+    int sync_every = 0, since_sync = 0;
+    void line(const std::string& s) {
+        out += "    "; out += s; out += '\n';
+        if (sync_every > 0 && ++since_sync >= sync_every && s[0] != '/') {
+            out += "    bar.sync 0;\n";
+            since_sync = 0;
+        }
+    }
 
     std::string bit_pred(int v, int c) {
         const int b = m.bits[v].bit_off + c;
@@ -185,6 +206,8 @@ struct Gen {
 
 std::string gen_kernel(const bc_model& m, bool dense, int threads, int min_blocks, long long* n_fma) {
     Gen g(m, dense);
+    const int sync_every = env_int("BC_SPEC_SYNC_EVERY", 0);
+    g.sync_every = sync_every;
     const int words = m.bits_words;
     if (!dense)
         for (int w = 0; w < words; ++w) g.words.push_back(g.R());
@@ -200,7 +223,8 @@ std::string gen_kernel(const bc_model& m, bool dense, int threads, int min_block
     s += "    .reg .pred %p<" + I(g.np + 1) + ">;\n    .reg .pred %pfm, %pdone;\n";
     s += "    .reg .f32 %f<" + I(g.nf + 1) + ">;\n    .reg .b32 %r<" + I(g.nr + 1) + ">;\n";
     s += "    .reg .b32 %t0, %t1, %t2, %t3, %t4;\n";
-    s += "    .reg .b64 %rdesc, %rstride, %rfmask, %rout, %rnq, %rq, %rstep, %rtmp, %rrow;\n";
+    s += "    .reg .b64 %rdesc, %rstride, %rfmask, %rout, %rnq, %rq, %rstep, %rtmp, %rrow, %rqb, %rqc;\n";
+    s += "    .reg .pred %pvalid;\n";
     auto e = [&](const std::string& x) { s += "    " + x + "\n"; };
     e("ld.param.u64 %rdesc, [p_desc];");
     e("ld.param.u64 %rstride, [p_stride];");
@@ -225,16 +249,28 @@ std::string gen_kernel(const bc_model& m, bool dense, int threads, int min_block
     e("cvt.u64.u32 %rtmp, %t0;");
     e("add.u64 %rq, %rq, %rtmp;");
     e("mul.wide.u32 %rstep, %t2, %t3;");
+    if (sync_every > 0) e("mul.wide.u32 %rqb, %t1, 32;");  // first query of the CTA's first warp slot
     s += "LOOP:\n";
-    e("setp.ge.u64 %pdone, %rq, %rnq;");
-    e("@%pdone bra DONE;");
-    e("mad.lo.u64 %rrow, %rq, %rstride, %rdesc;");
+    if (sync_every > 0) {
+        // bar.sync needs a CTA-uniform trip count: loop while the CTA's FIRST slot is in range; threads past the
+        // end recompute the last query and skip the store
+        e("setp.ge.u64 %pdone, %rqb, %rnq;");
+        e("@%pdone bra DONE;");
+        e("setp.lt.u64 %pvalid, %rq, %rnq;");
+        e("sub.u64 %rqc, %rnq, 1;");
+        e("min.u64 %rqc, %rqc, %rq;");
+        e("mad.lo.u64 %rrow, %rqc, %rstride, %rdesc;");
+    } else {
+        e("setp.ge.u64 %pdone, %rq, %rnq;");
+        e("@%pdone bra DONE;");
+        e("mad.lo.u64 %rrow, %rq, %rstride, %rdesc;");
+    }
     if (!dense)
         for (int w = 0; w < words; w += 4)
             e("ld.global.nc.v4.u32 {" + g.words[w] + ", " + g.words[w + 1] + ", " + g.words[w + 2] + ", " + g.words[w + 3] +
               "}, [%rrow+" + I(4LL * w) + "];");
     if (g.any_fan) {
-        e("mad.lo.u64 %rtmp, %rq, " + I(4LL * m.mask_words) + ", %rfmask;");
+        e(std::string("mad.lo.u64 %rtmp, ") + (sync_every > 0 ? "%rqc" : "%rq") + ", " + I(4LL * m.mask_words) + ", %rfmask;");
         for (int w = 0; w < m.mask_words; ++w) {
             e("mov.u32 " + g.fmw[w] + ", 0;");
             e("@%pfm ld.global.nc.u32 " + g.fmw[w] + ", [%rtmp+" + I(4LL * w) + "];");
@@ -243,8 +279,9 @@ std::string gen_kernel(const bc_model& m, bool dense, int threads, int min_block
     s += g.out;
     e("shl.b64 %rtmp, %rq, 2;");
     e("add.u64 %rtmp, %rtmp, %rout;");
-    e("st.global.f32 [%rtmp], " + res + ";");
+    e(std::string(sync_every > 0 ? "@%pvalid " : "") + "st.global.f32 [%rtmp], " + res + ";");
     e("add.u64 %rq, %rq, %rstep;");
+    if (sync_every > 0) e("add.u64 %rqb, %rqb, %rstep;");
     e("bra LOOP;");
     s += "DONE:\n    ret;\n}\n\n";
     return s;
@@ -262,6 +299,9 @@ void bc_spec_geometry(const bc_model& m, int* threads, int* min_blocks) {
     if (widest <= 40) { *threads = 256; *min_blocks = 3; }
     else if (widest <= 110) { *threads = 128; *min_blocks = 2; }
     else { *threads = 128; *min_blocks = 3; }
+    const int t = env_int("BC_SPEC_THREADS", 0), b = env_int("BC_SPEC_MIN_BLOCKS", 0);
+    if (t >= 32 && t <= 1024 && t % 32 == 0) *threads = t;
+    if (b >= 1 && b <= 16) *min_blocks = b;
 }
 
 std::string bc_spec_generate(const bc_model& m) {
@@ -290,6 +330,8 @@ uint64_t bc_spec_hash_of(const bc_model& m) {
     };
     const int ver = BC_CODEGEN_VERSION;
     mix(&ver, sizeof(ver));
+    const int knobs[3] = {env_int("BC_SPEC_SYNC_EVERY", 0), env_int("BC_SPEC_THREADS", 0), env_int("BC_SPEC_MIN_BLOCKS", 0)};
+    if (knobs[0] || knobs[1] || knobs[2]) mix(knobs, sizeof(knobs));
     mix(&m.n, sizeof(m.n));
     for (const BcNodeRec& r : m.nodes) mix(&r, sizeof(r));
     mix(m.arena.data(), m.arena.size() * sizeof(float));
