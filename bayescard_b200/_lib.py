@@ -16,6 +16,7 @@ SPEC_CACHE_DIR = os.path.join(_HERE, "_spec_cache")
 
 BC_OK = 0
 DESC_RANGE_U8, DESC_RANGE_U16, DESC_DENSE_F32, DESC_BITS = 0, 1, 2, 3
+SQLC_BITS, SQLC_DENSE, SQLC_ZERO, SQLC_PYTHON, SQLC_OVERFLOW = 0, 1, 2, 3, 4
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_SPEC, KERNEL_GEMM, KERNEL_GEMM_SIMT = 0, 1, 2, 3, 4
 
 _lib = None
@@ -70,6 +71,17 @@ _SIGS = {
                                        C.c_void_p]),
     "bc_gen_range_queries_host": (C.c_int, [C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_size_t, C.c_int,
                                             C.c_int, C.c_void_p]),
+    "bc_sqlc_create": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "bc_sqlc_destroy": (None, [C.c_void_p]),
+    "bc_sqlc_bits_stride": (C.c_int64, [C.c_void_p]),
+    "bc_sqlc_dense_width": (C.c_int64, [C.c_void_p]),
+    "bc_sqlc_add_categorical": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                          C.c_void_p]),
+    "bc_sqlc_add_continuous": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_void_p,
+                                         C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "bc_sqlc_compile": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                  C.c_void_p, C.POINTER(C.c_size_t)]),
     "bc_measure_fp32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "bc_launch_count": (C.c_uint64, []),
     "bc_last_error": (C.c_char_p, []),

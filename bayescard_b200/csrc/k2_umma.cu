@@ -456,8 +456,11 @@ int bc_k2_umma_edge(bc_model* m, const uint8_t* desc, size_t dstride, int fmt, s
     EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(u->encode);
     // Variant: the widest tile the edge fills.  Letters select the same kernels by hand (BC_K2_UMMA_VARIANT, for
     // the sweeps in profiles/): A = 128x256 tile, 32-float stages (2 stages); B = 128x256, 16-float stages (4);
-    // C = 128x128, 16-float stages (6); D = 128x128, 32-float stages (3).
-    char variant = N > 128 ? 'B' : N > 64 ? 'D' : N > 32 ? 'E' : 'F';
+    // C = 128x128, 16-float stages (6); D = 128x128, 32-float stages (3).  Measured (profiles/r1_k2_umma_v3_variants.txt):
+    // B == A at 1000 bins (L2 resident operands) and 19 % slower at 10k bins (64-byte rows from HBM), so the deeper
+    // pipeline is not what the kernel waits for -- ncu puts the tensor pipe at 56 % with both operands read from
+    // shared memory 3x per k-step (96 B/clk of UMMA reads + 62 B/clk of TMA writes against 128 B/clk of shared memory).
+    char variant = N > 128 ? 'A' : N > 64 ? 'D' : N > 32 ? 'E' : 'F';
     if (const char* e = std::getenv("BC_K2_UMMA_VARIANT"))
         if (*e >= 'A' && *e <= 'D' && N > 64) variant = *e;
     const float *bh = u->d_tt_hi[v], *bl = u->d_tt_lo[v];

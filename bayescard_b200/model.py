@@ -142,7 +142,27 @@ class Bayescard_BN:
             out[np.asarray(keep)] = res
         return out if return_prob else out * self.nrows
 
+    def query_sql_batch(self, sqls: Sequence[str], return_prob: bool = False) -> np.ndarray:
+        """SQL texts (``SELECT COUNT(*) FROM t WHERE ...``, the language of ``parse_query_single_table``) ->
+        cardinalities.  Parsing, decoding and descriptor packing of the whole batch happen in one native call
+        (``bayescard_b200.sqlc``); the results equal ``[self.query(parse_query_single_table(s, self)) for s in sqls]``."""
+        m = self._machine()
+        if getattr(self, "_sqlc", None) is None:
+            from .sqlc import SqlBatchCompiler
+
+            self._sqlc = SqlBatchCompiler(self.tree, m.compiler)
+        bits_idx, bits_rows, dense_idx, dense_rows, _zero = self._sqlc.compile(sqls)
+        out = np.zeros(len(sqls), dtype=np.float64)
+        if len(bits_idx):
+            out[bits_idx] = m.dev.run_host(bits_rows, L.DESC_BITS, None, m.kernel)
+        if len(dense_idx):
+            out[dense_idx] = m.dev.run_host(dense_rows, L.DESC_DENSE_F32, None, m.kernel)
+        return out if return_prob else out * self.nrows
+
     def close(self):
+        if getattr(self, "_sqlc", None) is not None:
+            self._sqlc.close()
+            self._sqlc = None
         if self.infer_machine is not None:
             self.infer_machine.close()
             self.infer_machine = None

@@ -168,6 +168,45 @@ BC_API int bc_gen_range_queries_host(int n_nodes, const int32_t* card, uint64_t 
 BC_API int bc_gen_sparse_queries_host(int n_nodes, const int32_t* card, uint64_t seed, uint64_t first, size_t n,
                                int kmin, int kmax, uint32_t* row_off, uint32_t* entries, size_t* n_entries);
 
+/* ---- batched SQL -> descriptor compiler (HOST only, no GPU) -------------------------
+ * Replaces the per-query Python in front of the hot path: parse_query_single_table
+ * (Evaluation/cardinality_estimation.py:22-119) followed by Bayescard_BN.query_decoding
+ * (Models/Bayescard_BN.py:279-325, with realign :53-72, continuous_range_map :180-239 and
+ * BN_single_model.apply_encoding_to_value / apply_ndistinct_to_value :98-139), for a BATCH of SQL texts, writing the
+ * descriptor rows bc_query_batch* read.  The column tables are handed over once per model:
+ *   categorical / boolean column: the encoding dict as parallel arrays in dict order (original value, numeric or
+ *     string, -> bin and n_in_bin weight) and BN.domain[attr] in stored order (inequalities are evaluated on it);
+ *   continuous column: BN.domain[attr] = (lo, hi), the bin edges of BN.mapping[attr] and n_distinct_mapping[attr].
+ *   node = topological index of the column in the tree, or -1 for a column of the table that the tree does not hold
+ *   (still decoded -- an undecodable predicate on it zeroes the estimate -- but it constrains nothing).
+ * bc_sqlc_compile classifies every query:
+ *   BC_SQLC_BITS    every weight is 1: BITS row written to bits_rows + i * bc_sqlc_bits_stride()
+ *   BC_SQLC_DENSE   fractional n_distinct weights: DENSE_F32 row appended to dense_rows, dense_index[k] = i
+ *   BC_SQLC_ZERO    undecodable predicate or no reachable column: the estimate is 0 (Bayescard_BN.py:517-521,
+ *                   ExactInference.py:197); no row is written
+ *   BC_SQLC_PYTHON  a predicate shape this compiler does not restate (anything the reference raises on, operands whose
+ *                   Python parsing is subtle): the caller evaluates the query through the Python mirror
+ *   BC_SQLC_OVERFLOW  a DENSE query that did not fit dense_capacity rows: compile it again with more room */
+#define BC_SQLC_BITS 0
+#define BC_SQLC_DENSE 1
+#define BC_SQLC_ZERO 2
+#define BC_SQLC_PYTHON 3
+#define BC_SQLC_OVERFLOW 4
+typedef struct bc_sqlc bc_sqlc;
+BC_API int bc_sqlc_create(int n_nodes, const int32_t* card, bc_sqlc** out);
+BC_API void bc_sqlc_destroy(bc_sqlc* c);
+BC_API int64_t bc_sqlc_bits_stride(const bc_sqlc* c);   /* bytes per BITS row   (== bc_model_desc_stride(BITS))   */
+BC_API int64_t bc_sqlc_dense_width(const bc_sqlc* c);   /* floats per DENSE row (== bc_model_dense_width())       */
+BC_API int bc_sqlc_add_categorical(bc_sqlc* c, const char* name, int node, int has_encoding, int n_enc,
+                                   const uint8_t* enc_is_str, const double* enc_num, const char* const* enc_str,
+                                   const int32_t* enc_bin, const double* enc_weight, int n_dom,
+                                   const uint8_t* dom_is_str, const double* dom_num, const char* const* dom_str);
+BC_API int bc_sqlc_add_continuous(bc_sqlc* c, const char* name, int node, double dom_lo, double dom_hi, int n_bins,
+                                  const double* edge_lo, const double* edge_hi, int n_ndmap, const double* nd_key,
+                                  const double* nd_mult);
+BC_API int bc_sqlc_compile(const bc_sqlc* c, size_t n_queries, const char* const* sql, uint8_t* kind, void* bits_rows,
+                           float* dense_rows, size_t dense_capacity, uint32_t* dense_index, size_t* n_dense);
+
 /* Measured FP32 FFMA peak of the device (TFLOP/s), the roofline denominator SURVEY.md section 8d
  * asks to measure in the same run rather than quote. */
 BC_API int bc_measure_fp32_peak(int device, double* tflops, double* sm_clock_mhz);

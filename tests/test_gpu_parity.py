@@ -306,6 +306,10 @@ def test_workload_end_to_end_through_dropin_api(name):
     batch = bn.query_batch(parsed_all)
     ref_all = np.asarray([np.asarray(r["card"]["value"]).reshape(-1)[0] for r in rows], dtype=np.float64)
     assert_close(batch, ref_all, name + " batch")
+    # ... and so does the SQL-text batch entry point (native parse + decode + pack, one launch per descriptor kind)
+    sql_batch = bn.query_sql_batch([r["sql"] for r in rows])
+    assert_close(sql_batch, ref_all, name + " sql batch")
+    assert np.array_equal(sql_batch, batch)
     bn.close()
 
 

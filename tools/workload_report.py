@@ -64,6 +64,18 @@ def config1(name, reps=3):
         batch = bn.query_batch(parsed)
         tb.append(time.perf_counter() - t)
     rel_b = np.abs(batch - ref) / np.maximum(np.abs(ref), 1e-300)
+    sqls = [r["sql"] for r in rows]
+    bn.query_sql_batch(sqls)
+    ts = []
+    for _ in range(reps):
+        t = time.perf_counter()
+        sql_batch = bn.query_sql_batch(sqls)
+        ts.append(time.perf_counter() - t)
+    rel_s = np.abs(sql_batch - ref) / np.maximum(np.abs(ref), 1e-300)
+    big = sqls * (200000 // len(sqls) + 1)
+    t = time.perf_counter()
+    bn.query_sql_batch(big)
+    big_s = time.perf_counter() - t
     # CPU: the oracle port of Bayescard_BN.query (decode + VariableEliminationJIT.query), one process
     tm = bn.tree
     t = time.perf_counter()
@@ -81,6 +93,10 @@ def config1(name, reps=3):
                                     "mean": float(np.mean(lat) * 1e6), "note": "Bayescard_BN.query: decode + H2D + kernel + D2H, B=1"},
         "scalar_queries_per_s": len(rows) / float(np.sum(lat)),
         "batch_api_s": float(np.median(tb)), "batch_api_queries_per_s": len(rows) / float(np.median(tb)),
+        "sql_text_batch_api": {"s": float(np.median(ts)), "queries_per_s": len(rows) / float(np.median(ts)),
+                               "max_rel_diff_vs_reference_estimates": float(rel_s.max()),
+                               "queries_per_s_at_%d" % len(big): len(big) / big_s, "host_threads": os.cpu_count(),
+                               "note": "SQL text -> native parse/decode/pack (bc_sqlc_compile) -> H2D -> kernel -> D2H"},
         "sql_parse_us_per_query": parse_s / len(rows) * 1e6,
         "cpu_oracle_port": {"queries_per_s": len(rows) / cpu_s, "ms_per_query": cpu_s / len(rows) * 1e3, "cores": 1,
                             "max_rel_diff_vs_reference_estimates": float(np.max(np.abs(np.asarray(cpu) - ref) / np.maximum(np.abs(ref), 1e-300)))},
