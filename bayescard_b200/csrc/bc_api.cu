@@ -179,6 +179,8 @@ extern "C" int bc_model_create(int device, int n_nodes, const int32_t* parent, c
         CK(cudaMemcpy(m->d_nodes, m->nodes.data(), m->nodes.size() * sizeof(BcNodeRec), cudaMemcpyHostToDevice));
         CK(cudaMalloc(&m->d_bits, m->bits.size() * sizeof(BcBitsRec)));
         CK(cudaMemcpy(m->d_bits, m->bits.data(), m->bits.size() * sizeof(BcBitsRec), cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&m->d_spec_ctr, BC_SPEC_CTR_SLOTS * 16));
+        CK(cudaMemset(m->d_spec_ctr, 0, BC_SPEC_CTR_SLOTS * 16));
         CK(cudaMalloc(&m->d_bits_default, m->bits_default.size() * 4));
         CK(cudaMemcpy(m->d_bits_default, m->bits_default.data(), m->bits_default.size() * 4, cudaMemcpyHostToDevice));
         CK(cudaMalloc(&m->d_ent_node, m->ent_node.size() * sizeof(uint16_t)));
@@ -202,6 +204,7 @@ extern "C" void bc_model_destroy(bc_model* m) {
         cudaFree(m->d_nodes);
         cudaFree(m->d_bits);
         cudaFree(m->d_bits_default);
+        cudaFree(m->d_spec_ctr);
         cudaFree(m->d_ent_node);
     }
     delete m;

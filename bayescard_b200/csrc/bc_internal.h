@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -13,7 +14,8 @@
 #include "../../include/bayescard_b200.h"
 
 #define BC_VERSION_STRING "bayescard_b200 0.1.0 (sm_100a)"
-#define BC_CODEGEN_VERSION 8
+#define BC_CODEGEN_VERSION 9
+#define BC_SPEC_CTR_SLOTS 256
 
 // One record per node, copied to the device and (by K1) into shared memory.  32 bytes.
 struct BcNodeRec {
@@ -79,6 +81,11 @@ struct bc_model {
     int spec_qpt = 1;                // queries per thread per loop trip
     int spec_blocks_bits = 1, spec_blocks_dense = 1, spec_blocks_range8 = 1;  // resident CTAs per SM
     std::vector<uint32_t> bits_default;
+    // work counters of the dynamically scheduled specialised kernels: a ring of {u64 next query, u32 CTAs done, pad}
+    // slots (one per launch, so launches of one model on different streams never share a counter); each kernel
+    // leaves its slot zeroed
+    uint64_t* d_spec_ctr = nullptr;
+    std::atomic<uint32_t> spec_ctr_next{0};
     BcK2Plan* k2 = nullptr;
     std::mutex k2_mu;                // guards the lazy construction of k2 (pipe_mu may already be held)
     BcHostPipe* pipe = nullptr;

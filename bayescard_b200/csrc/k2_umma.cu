@@ -303,6 +303,219 @@ k2_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Two-CTA variant (cta_group::2): a cluster of two CTAs on an SM pair computes a 256-query x 256-state tile.
+//
+// Why: the single-CTA kernel above is bound by SHARED MEMORY bandwidth, not by the tensor pipe (ncu: tensor 56 %).
+// Each of the three products of a k-step re-reads A (4 KB) and B (8 KB) from shared memory -- 96 B/clk of UMMA
+// reads next to 62 B/clk of TMA writes, against 128 B/clk.  With cta_group::2 every CTA stages its own 128 rows of A
+// and only HALF of the B tile (128 of the 256 parent states); the instruction reads both halves across the pair,
+// so per CTA the UMMA reads drop to 64 B/clk and the TMA writes to 43 B/clk.
+//
+//   * both CTAs run the TMA producer for their own operands; every load completes on the LEADER's (rank 0) full
+//     barrier (cp.async.bulk.tensor ... .cta_group::2 with the barrier address mapped to rank 0);
+//   * the leader's MMA thread issues tcgen05.mma.cta_group::2 (M = 256: rows 0-127 accumulate in the leader's TMEM,
+//     rows 128-255 in the peer's) and signals with tcgen05.commit ... .multicast::cluster to BOTH CTAs: empty[s]
+//     frees the stage in both producers, acc_full[b] releases a chunk sum to both epilogues;
+//   * each CTA's epilogue warps drain their own TMEM into RN registers (same chunked accumulation as above) and
+//     arrive on the leader's acc_empty[b] (remote mbarrier arrive for the peer).
+constexpr int k2S_BN = 256, k2S_BK = 32, k2S_STAGES = 3, k2S_EC = 128, k2S_EPI_WARPS = 8, k2S_THREADS = 64 + 32 * k2S_EPI_WARPS;
+constexpr int k2S_A_BYTES = kBM * k2S_BK * 4, k2S_BH_BYTES = (k2S_BN / 2) * k2S_BK * 4;
+constexpr int k2S_STAGE = 2 * k2S_A_BYTES + 2 * k2S_BH_BYTES;   // per CTA: 64 KB
+constexpr size_t k2S_SMEM = (size_t)k2S_STAGES * k2S_STAGE + 1024 + 256;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t leader_bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(leader_bar)
+        : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_c),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {  // arrives on `bar` (same offset) in both CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+
+template <int KS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2S_THREADS, 1)
+k2_umma2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, int rows, int N,
+                int num_kb, int n_col_tiles, int n_row_tiles, float* __restrict__ lam_pa, int ld_pa, int accumulate) {
+    constexpr int BN = k2S_BN, kBK = k2S_BK, A_BYTES = k2S_A_BYTES, B_BYTES = k2S_BH_BYTES, STAGE = k2S_STAGE, kStg = k2S_STAGES;
+    constexpr int CHUNKS_PER_KB = (kBK / 8) / KS;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStg * STAGE);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStg + 4);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kStg);
+    const uint32_t acc_full0 = smem_u32(bars + 2 * kStg), acc_empty0 = smem_u32(bars + 2 * kStg + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    // tile order as in the single-CTA kernel, in units of 256-row pair tiles (n_row_tiles counts those)
+    int tile = blockIdx.x >> 1;
+    const int group_cols = 8;
+    const int group = tile / (group_cols * n_row_tiles);
+    const int first_col = group * group_cols;
+    const int cols_here = n_col_tiles - first_col < group_cols ? n_col_tiles - first_col : group_cols;
+    tile -= group * group_cols * n_row_tiles;
+    const int m0 = (tile / cols_here) * (2 * kBM) + (int)rank * kBM;  // this CTA's 128 rows
+    const int n0 = (first_col + tile % cols_here) * BN;                // the pair's 256 parent states
+    const int nb0 = n0 + (int)rank * (BN / 2);                         // this CTA's half of the B tile
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStg; ++s) {
+            mbar_init(full0 + 8 * s, 1);     // used in the leader: one arrive.expect_tx for the bytes of BOTH CTAs
+            mbar_init(empty0 + 8 * s, 1);    // one multicast commit
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(acc_full0 + 8 * b, 1);                      // one multicast commit
+            mbar_init(acc_empty0 + 8 * b, 2 * k2S_EPI_WARPS);     // used in the leader: epilogue warps of both CTAs
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // both CTAs, same warp: 2 x 256 accumulator columns = all of TMEM
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();  // the peer's barriers exist before anything signals them
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ---- TMA producer (both CTAs)
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % kStg;
+                mbar_wait(empty0 + 8 * s, ((kb / kStg) & 1) ^ 1);
+                const uint32_t base = smem_u32(smem + s * STAGE);
+                const uint32_t bar = mapa_rank(full0 + 8 * s, 0);
+                if (leader) mbar_expect_tx(full0 + 8 * s, 2 * STAGE);
+                tma_load_2d_2sm(base, &tm_a_hi, kb * kBK, m0, bar);
+                tma_load_2d_2sm(base + A_BYTES, &tm_a_lo, kb * kBK, m0, bar);
+                tma_load_2d_2sm(base + 2 * A_BYTES, &tm_b_hi, kb * kBK, nb0, bar);
+                tma_load_2d_2sm(base + 2 * A_BYTES + B_BYTES, &tm_b_lo, kb * kBK, nb0, bar);
+            }
+        }
+    } else if (warp == 1) {
+        if (leader && lane == 0) {  // ---- MMA issuer (leader only)
+            // D = F32, A = B = TF32, K-major, N = 256, M = 256 (two CTAs x 128)
+            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * kBM) >> 4) << 24);
+            int chunk = 0;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % kStg;
+                mbar_wait(full0 + 8 * s, (kb / kStg) & 1);
+                const uint32_t base = smem_u32(smem + s * STAGE);
+                const uint64_t a_hi = umma_desc<kBK>(base), a_lo = umma_desc<kBK>(base + A_BYTES);
+                const uint64_t b_hi = umma_desc<kBK>(base + 2 * A_BYTES), b_lo = umma_desc<kBK>(base + 2 * A_BYTES + B_BYTES);
+#pragma unroll
+                for (int c = 0; c < CHUNKS_PER_KB; ++c, ++chunk) {
+                    const int buf = chunk & 1;
+                    mbar_wait(acc_empty0 + 8 * buf, ((chunk >> 1) & 1) ^ 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t d = tmem + (uint32_t)(buf * BN);
+#pragma unroll
+                    for (int kk = c * KS; kk < (c + 1) * KS; ++kk) {
+                        const uint64_t o = (uint64_t)(kk * 2);
+                        umma_tf32_2sm(d, a_lo + o, b_hi + o, idesc, kk != c * KS);
+                        umma_tf32_2sm(d, a_hi + o, b_lo + o, idesc, 1);
+                    }
+#pragma unroll
+                    for (int kk = c * KS; kk < (c + 1) * KS; ++kk) {
+                        const uint64_t o = (uint64_t)(kk * 2);
+                        umma_tf32_2sm(d, a_hi + o, b_hi + o, idesc, 1);
+                    }
+                    umma_commit_2sm(acc_full0 + 8 * buf);
+                }
+                umma_commit_2sm(empty0 + 8 * s);
+            }
+        }
+    } else {  // ---- epilogue warps (both CTAs): lane quarter = warp % 4, column group = (warp - 2) / 4
+        constexpr int EC = k2S_EC;
+        const int quarter = warp & 3, cgrp = (warp - 2) >> 2;
+        const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cgrp * EC);
+        float acc[EC];
+#pragma unroll
+        for (int j = 0; j < EC; ++j) acc[j] = 0.f;
+        const int n_chunks = num_kb * CHUNKS_PER_KB;
+        for (int chunk = 0; chunk < n_chunks; ++chunk) {
+            const int buf = chunk & 1;
+            mbar_wait(acc_full0 + 8 * buf, (chunk >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t src = lane_base + (uint32_t)(buf * BN);
+            float v0[32], v1[32];
+            tmem_ld32_nowait(src, v0);
+#pragma unroll
+            for (int c0 = 0; c0 < EC; c0 += 64) {
+                tmem_ld_wait();
+                tmem_ld32_nowait(src + (uint32_t)(c0 + 32), v1);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[c0 + j] += v0[j];
+                tmem_ld_wait();
+                if (c0 + 64 < EC) tmem_ld32_nowait(src + (uint32_t)(c0 + 64), v0);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[c0 + 32 + j] += v1[j];
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_rank(acc_empty0 + 8 * buf, 0));
+        }
+        const int r = m0 + quarter * 32 + lane;
+        if (r < rows) {
+            float* dst_row = lam_pa + (size_t)r * ld_pa + n0 + cgrp * EC;
+#pragma unroll
+            for (int j = 0; j < EC; j += 4) {
+                const int n = n0 + cgrp * EC + j;
+                float* d = dst_row + j;
+                if (n + 3 < N) {
+                    float4 x = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+                    if (accumulate) {
+                        const float4 o = *reinterpret_cast<const float4*>(d);
+                        x.x *= o.x; x.y *= o.y; x.z *= o.z; x.w *= o.w;
+                    }
+                    *reinterpret_cast<float4*>(d) = x;
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+                        if (n + t < N) d[t] = accumulate ? d[t] * acc[j + t] : acc[j + t];
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    cluster_sync_all();  // neither CTA leaves (or frees TMEM) while the other can still signal it or read its operands
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+    }
+}
+
 // Lambda_v: apply the range mask of column v, clear the padding columns, split into hi (in place) / lo
 template <int FMT>
 __global__ void __launch_bounds__(256) k2_split_kernel(const uint8_t* __restrict__ desc, size_t dstride, size_t q0, int rows,
@@ -398,6 +611,30 @@ int launch_edge(EncodeTiledFn fn, const float* a_hi, const float* a_lo, int ld_a
     return BC_OK;
 }
 
+template <int KS>
+int launch_edge_2sm(EncodeTiledFn fn, const float* a_hi, const float* a_lo, int ld_a, const float* b_hi, const float* b_lo, int ldk,
+                    int rows, int N, float* lam_pa, int ld_pa, int accumulate, cudaStream_t st) {
+    static bool attr_set[64] = {};
+    int dev = 0;
+    BC_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        BC_CUDA_CHECK(cudaFuncSetAttribute(k2_umma2_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2S_SMEM));
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    CUtensorMap maps[4];
+    int rc;
+    if ((rc = encode_map(fn, &maps[0], a_hi, (uint64_t)ldk, (uint64_t)rows, (uint64_t)ld_a, kBM, k2S_BK))) return rc;
+    if ((rc = encode_map(fn, &maps[1], a_lo, (uint64_t)ldk, (uint64_t)rows, (uint64_t)ld_a, kBM, k2S_BK))) return rc;
+    if ((rc = encode_map(fn, &maps[2], b_hi, (uint64_t)ldk, (uint64_t)N, (uint64_t)ldk, (uint32_t)(k2S_BN / 2), k2S_BK))) return rc;
+    if ((rc = encode_map(fn, &maps[3], b_lo, (uint64_t)ldk, (uint64_t)N, (uint64_t)ldk, (uint32_t)(k2S_BN / 2), k2S_BK))) return rc;
+    const int n_col_tiles = (N + k2S_BN - 1) / k2S_BN, n_pair_tiles = (rows + 2 * kBM - 1) / (2 * kBM);
+    k2_umma2_kernel<KS><<<2 * n_col_tiles * n_pair_tiles, k2S_THREADS, k2S_SMEM, st>>>(
+        maps[0], maps[1], maps[2], maps[3], rows, N, ldk / k2S_BK, n_col_tiles, n_pair_tiles, lam_pa, ld_pa, accumulate);
+    BC_CUDA_CHECK(cudaGetLastError());
+    bc_count_launch();
+    return BC_OK;
+}
+
 int umma_prepare(bc_model* m) {
     BcK2Plan* k2 = m->k2;
     if (k2->umma) return k2->umma->failed ? BC_ELIMIT : BC_OK;
@@ -462,9 +699,10 @@ int bc_k2_umma_edge(bc_model* m, const uint8_t* desc, size_t dstride, int fmt, s
     // shared memory 3x per k-step (96 B/clk of UMMA reads + 62 B/clk of TMA writes against 128 B/clk of shared memory).
     char variant = N > 128 ? 'A' : N > 64 ? 'D' : N > 32 ? 'E' : 'F';
     if (const char* e = std::getenv("BC_K2_UMMA_VARIANT"))
-        if (*e >= 'A' && *e <= 'D' && N > 64) variant = *e;
+        if (((*e >= 'A' && *e <= 'D') || *e == 'T') && N > 64) variant = *e;
     const float *bh = u->d_tt_hi[v], *bl = u->d_tt_lo[v];
     switch (variant) {
+        case 'T': return launch_edge_2sm<2>(fn, lam_v, lam_lo, ld_v, bh, bl, ldk, rows, N, lam_pa, ld_pa, accumulate, st);
         case 'A': return launch_edge<UmmaCfg<256, 32, 2, 128, 1>>(fn, lam_v, lam_lo, ld_v, bh, bl, ldk, rows, N, lam_pa, ld_pa, accumulate, st);
         case 'B': return launch_edge<UmmaCfg<256, 16, 2, 128, 1>>(fn, lam_v, lam_lo, ld_v, bh, bl, ldk, rows, N, lam_pa, ld_pa, accumulate, st);
         case 'C': return launch_edge<UmmaCfg<128, 16, 2, 128, 1>>(fn, lam_v, lam_lo, ld_v, bh, bl, ldk, rows, N, lam_pa, ld_pa, accumulate, st);

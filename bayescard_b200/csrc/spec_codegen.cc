@@ -50,6 +50,9 @@ inline std::string I(long long x) { return std::to_string(x); }
 //                          a big tree is a straight line of 100-400 KB, larger than the SM's instruction cache;
 //                          warps that drift apart each stream it from L2 on their own, warps kept within one
 //                          cache-sized window of each other share the fetched lines.
+//   BC_SPEC_DYNAMIC=1      CTAs take their rounds of ntid queries from a global counter (p_ctr) instead of a fixed
+//                          stride: SMs do not all run this fetch-bound code at the same speed (ncu: 510-679 k active
+//                          cycles per SM on DMV), and with a static split the slowest SM sets the time.
 //   BC_SPEC_THREADS / BC_SPEC_MIN_BLOCKS   override the CTA geometry chosen by bc_spec_geometry.
 int env_int(const char* name, int dflt) {
     const char* e = std::getenv(name);
@@ -215,16 +218,19 @@ std::string gen_kernel(const bc_model& m, bool dense, int threads, int min_block
     const std::string res = g.message(0)[0];
     if (n_fma) *n_fma = g.n_fma;
 
+    const bool dynamic = env_int("BC_SPEC_DYNAMIC", 0) != 0;
     std::string s;
     const char* name = dense ? "bc_spec_dense" : "bc_spec_bits";
     s += std::string(".visible .entry ") + name +
          "(\n    .param .u64 p_desc,\n    .param .u64 p_stride,\n    .param .u64 p_fmask,\n    .param .u64 p_out,\n"
-         "    .param .u64 p_nq\n)\n.maxntid " + I(threads) + ", 1, 1\n.minnctapersm " + I(min_blocks) + "\n{\n";
+         "    .param .u64 p_nq,\n    .param .u64 p_ctr\n)\n.maxntid " + I(threads) + ", 1, 1\n.minnctapersm " + I(min_blocks) + "\n{\n";
     s += "    .reg .pred %p<" + I(g.np + 1) + ">;\n    .reg .pred %pfm, %pdone;\n";
     s += "    .reg .f32 %f<" + I(g.nf + 1) + ">;\n    .reg .b32 %r<" + I(g.nr + 1) + ">;\n";
     s += "    .reg .b32 %t0, %t1, %t2, %t3, %t4;\n";
     s += "    .reg .b64 %rdesc, %rstride, %rfmask, %rout, %rnq, %rq, %rstep, %rtmp, %rrow, %rqb, %rqc;\n";
-    s += "    .reg .pred %pvalid;\n";
+    s += "    .reg .b64 %rctr, %rnext, %rnt, %rtid;\n";
+    s += "    .reg .pred %pvalid, %pt0, %plast;\n";
+    if (dynamic) s += "    .shared .align 8 .b64 bc_slot[2];\n";
     auto e = [&](const std::string& x) { s += "    " + x + "\n"; };
     e("ld.param.u64 %rdesc, [p_desc];");
     e("ld.param.u64 %rstride, [p_stride];");
@@ -235,34 +241,66 @@ std::string gen_kernel(const bc_model& m, bool dense, int threads, int min_block
     e("cvta.to.global.u64 %rout, %rout;");
     e("setp.ne.u64 %pfm, %rfmask, 0;");
     e("@%pfm cvta.to.global.u64 %rfmask, %rfmask;");
-    // query index of round k:  ((k * warps_per_cta + warp) * n_cta + cta) * 32 + lane.
-    // Consecutive warp slots belong to DIFFERENT CTAs, so the last, partial round is spread over all
-    // CTAs (and SMs) instead of filling the first ones only.
-    e("mov.u32 %t0, %tid.x;");
-    e("mov.u32 %t1, %ctaid.x;");
-    e("mov.u32 %t2, %ntid.x;");
-    e("mov.u32 %t3, %nctaid.x;");
-    e("shr.u32 %t4, %t0, 5;");
-    e("mad.lo.u32 %t4, %t4, %t3, %t1;");
-    e("and.b32 %t0, %t0, 31;");
-    e("mul.wide.u32 %rq, %t4, 32;");
-    e("cvt.u64.u32 %rtmp, %t0;");
-    e("add.u64 %rq, %rq, %rtmp;");
-    e("mul.wide.u32 %rstep, %t2, %t3;");
-    if (sync_every > 0) e("mul.wide.u32 %rqb, %t1, 32;");  // first query of the CTA's first warp slot
-    s += "LOOP:\n";
-    if (sync_every > 0) {
-        // bar.sync needs a CTA-uniform trip count: loop while the CTA's FIRST slot is in range; threads past the
-        // end recompute the last query and skip the store
+    const bool clamp = dynamic || sync_every > 0;  // threads past the end recompute the last query and skip the store
+    if (dynamic) {
+        // Round k of a CTA = ntid consecutive queries starting at the value its thread 0 drew from the global
+        // counter; the draw for round k+1 is issued at the start of round k-1 (its latency hides behind a whole
+        // round) and handed over through a two-slot shared-memory mailbox, one bar.sync per round.
+        e("ld.param.u64 %rctr, [p_ctr];");
+        e("cvta.to.global.u64 %rctr, %rctr;");
+        e("mov.u32 %t0, %tid.x;");
+        e("mov.u32 %t2, %ntid.x;");
+        e("cvt.u64.u32 %rtid, %t0;");
+        e("cvt.u64.u32 %rnt, %t2;");
+        e("setp.eq.u32 %pt0, %t0, 0;");
+        e("mov.u32 %t4, bc_slot;");
+        e("@%pt0 atom.global.add.u64 %rnext, [%rctr], %rnt;");
+        e("@%pt0 st.shared.u64 [%t4], %rnext;");
+        e("@%pt0 atom.global.add.u64 %rnext, [%rctr], %rnt;");
+        s += "LOOP:\n";
+        e("bar.sync 0;");
+        e("ld.shared.u64 %rqb, [%t4];");
         e("setp.ge.u64 %pdone, %rqb, %rnq;");
         e("@%pdone bra DONE;");
+        e("mov.u32 %t1, bc_slot;");
+        e("sub.u32 %t3, %t4, %t1;");
+        e("xor.b32 %t3, %t3, 8;");
+        e("add.u32 %t4, %t1, %t3;");
+        e("@%pt0 st.shared.u64 [%t4], %rnext;");
+        e("@%pt0 atom.global.add.u64 %rnext, [%rctr], %rnt;");
+        e("add.u64 %rq, %rqb, %rtid;");
+    } else {
+        // query index of round k:  ((k * warps_per_cta + warp) * n_cta + cta) * 32 + lane.
+        // Consecutive warp slots belong to DIFFERENT CTAs, so the last, partial round is spread over all
+        // CTAs (and SMs) instead of filling the first ones only.
+        e("mov.u32 %t0, %tid.x;");
+        e("mov.u32 %t1, %ctaid.x;");
+        e("mov.u32 %t2, %ntid.x;");
+        e("mov.u32 %t3, %nctaid.x;");
+        e("shr.u32 %t4, %t0, 5;");
+        e("mad.lo.u32 %t4, %t4, %t3, %t1;");
+        e("and.b32 %t0, %t0, 31;");
+        e("mul.wide.u32 %rq, %t4, 32;");
+        e("cvt.u64.u32 %rtmp, %t0;");
+        e("add.u64 %rq, %rq, %rtmp;");
+        e("mul.wide.u32 %rstep, %t2, %t3;");
+        if (sync_every > 0) e("mul.wide.u32 %rqb, %t1, 32;");  // first query of the CTA's first warp slot
+        s += "LOOP:\n";
+        if (sync_every > 0) {
+            // bar.sync needs a CTA-uniform trip count: loop while the CTA's FIRST slot is in range
+            e("setp.ge.u64 %pdone, %rqb, %rnq;");
+            e("@%pdone bra DONE;");
+        } else {
+            e("setp.ge.u64 %pdone, %rq, %rnq;");
+            e("@%pdone bra DONE;");
+        }
+    }
+    if (clamp) {
         e("setp.lt.u64 %pvalid, %rq, %rnq;");
         e("sub.u64 %rqc, %rnq, 1;");
         e("min.u64 %rqc, %rqc, %rq;");
         e("mad.lo.u64 %rrow, %rqc, %rstride, %rdesc;");
     } else {
-        e("setp.ge.u64 %pdone, %rq, %rnq;");
-        e("@%pdone bra DONE;");
         e("mad.lo.u64 %rrow, %rq, %rstride, %rdesc;");
     }
     if (!dense)
@@ -270,7 +308,7 @@ std::string gen_kernel(const bc_model& m, bool dense, int threads, int min_block
             e("ld.global.nc.v4.u32 {" + g.words[w] + ", " + g.words[w + 1] + ", " + g.words[w + 2] + ", " + g.words[w + 3] +
               "}, [%rrow+" + I(4LL * w) + "];");
     if (g.any_fan) {
-        e(std::string("mad.lo.u64 %rtmp, ") + (sync_every > 0 ? "%rqc" : "%rq") + ", " + I(4LL * m.mask_words) + ", %rfmask;");
+        e(std::string("mad.lo.u64 %rtmp, ") + (clamp ? "%rqc" : "%rq") + ", " + I(4LL * m.mask_words) + ", %rfmask;");
         for (int w = 0; w < m.mask_words; ++w) {
             e("mov.u32 " + g.fmw[w] + ", 0;");
             e("@%pfm ld.global.nc.u32 " + g.fmw[w] + ", [%rtmp+" + I(4LL * w) + "];");
@@ -279,10 +317,29 @@ std::string gen_kernel(const bc_model& m, bool dense, int threads, int min_block
     s += g.out;
     e("shl.b64 %rtmp, %rq, 2;");
     e("add.u64 %rtmp, %rtmp, %rout;");
-    e(std::string(sync_every > 0 ? "@%pvalid " : "") + "st.global.f32 [%rtmp], " + res + ";");
-    e("add.u64 %rq, %rq, %rstep;");
-    if (sync_every > 0) e("add.u64 %rqb, %rqb, %rstep;");
+    e(std::string(clamp ? "@%pvalid " : "") + "st.global.f32 [%rtmp], " + res + ";");
+    if (!dynamic) {
+        e("add.u64 %rq, %rq, %rstep;");
+        if (sync_every > 0) e("add.u64 %rqb, %rqb, %rstep;");
+    }
     e("bra LOOP;");
+    if (dynamic) {
+        // The last CTA to leave zeroes the counter for the next launch.  Thread 0 first consumes its outstanding
+        // draw (the shift is 0 for any real counter value, but the address now depends on it), so no draw of any
+        // CTA can land after the reset.
+        s += "DONE:\n";
+        e("@!%pt0 bra OUT;");
+        e("shr.u64 %rtmp, %rnext, 63;");
+        e("add.u64 %rctr, %rctr, %rtmp;");
+        e("mov.u32 %t3, %nctaid.x;");
+        e("sub.u32 %t3, %t3, 1;");
+        e("atom.global.inc.u32 %t1, [%rctr+8], %t3;");
+        e("setp.eq.u32 %plast, %t1, %t3;");
+        e("mov.b64 %rtmp, 0;");
+        e("@%plast st.global.u64 [%rctr], %rtmp;");
+        s += "OUT:\n    ret;\n}\n\n";
+        return s;
+    }
     s += "DONE:\n    ret;\n}\n\n";
     return s;
 }
@@ -330,8 +387,9 @@ uint64_t bc_spec_hash_of(const bc_model& m) {
     };
     const int ver = BC_CODEGEN_VERSION;
     mix(&ver, sizeof(ver));
-    const int knobs[3] = {env_int("BC_SPEC_SYNC_EVERY", 0), env_int("BC_SPEC_THREADS", 0), env_int("BC_SPEC_MIN_BLOCKS", 0)};
-    if (knobs[0] || knobs[1] || knobs[2]) mix(knobs, sizeof(knobs));
+    const int knobs[4] = {env_int("BC_SPEC_SYNC_EVERY", 0), env_int("BC_SPEC_THREADS", 0), env_int("BC_SPEC_MIN_BLOCKS", 0),
+                          env_int("BC_SPEC_DYNAMIC", 0)};
+    if (knobs[0] || knobs[1] || knobs[2] || knobs[3]) mix(knobs, sizeof(knobs));
     mix(&m.n, sizeof(m.n));
     for (const BcNodeRec& r : m.nodes) mix(&r, sizeof(r));
     mix(m.arena.data(), m.arena.size() * sizeof(float));

@@ -104,7 +104,12 @@ int bc_spec_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint
     const unsigned char* d = static_cast<const unsigned char*>(desc);
     unsigned long long stride = (unsigned long long)bc_model_desc_stride(m, fmt);
     unsigned long long n = nq;
-    void* args[] = {(void*)&d, (void*)&stride, (void*)&fan_mask, (void*)&out, (void*)&n};
+    if (!m->d_spec_ctr) {
+        bc_set_error("model has no work-counter ring (host-only model?)");
+        return BC_EINVAL;
+    }
+    uint64_t* ctr = m->d_spec_ctr + 2 * (m->spec_ctr_next.fetch_add(1) % BC_SPEC_CTR_SLOTS);
+    void* args[] = {(void*)&d, (void*)&stride, (void*)&fan_mask, (void*)&out, (void*)&n, (void*)&ctr};
     const int threads = m->spec_threads;
     const size_t per_cta = (size_t)threads * m->spec_qpt;
     const int resident = fmt == BC_DESC_DENSE_F32 ? m->spec_blocks_dense : fmt == BC_DESC_BITS ? m->spec_blocks_bits : m->spec_blocks_range8;
