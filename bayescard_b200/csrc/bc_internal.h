@@ -14,7 +14,7 @@
 #include "../../include/bayescard_b200.h"
 
 #define BC_VERSION_STRING "bayescard_b200 0.1.0 (sm_100a)"
-#define BC_CODEGEN_VERSION 9
+#define BC_CODEGEN_VERSION 10
 #define BC_SPEC_CTR_SLOTS 256
 
 // One record per node, copied to the device and (by K1) into shared memory.  32 bytes.

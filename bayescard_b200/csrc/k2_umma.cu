@@ -702,7 +702,12 @@ int bc_k2_umma_edge(bc_model* m, const uint8_t* desc, size_t dstride, int fmt, s
         if (((*e >= 'A' && *e <= 'D') || *e == 'T') && N > 64) variant = *e;
     const float *bh = u->d_tt_hi[v], *bl = u->d_tt_lo[v];
     switch (variant) {
-        case 'T': return launch_edge_2sm<2>(fn, lam_v, lam_lo, ld_v, bh, bl, ldk, rows, N, lam_pa, ld_pa, accumulate, st);
+        case 'T': {
+            const char* ks = std::getenv("BC_K2_UMMA_KS");
+            if (ks && std::atoi(ks) == 4)
+                return launch_edge_2sm<4>(fn, lam_v, lam_lo, ld_v, bh, bl, ldk, rows, N, lam_pa, ld_pa, accumulate, st);
+            return launch_edge_2sm<2>(fn, lam_v, lam_lo, ld_v, bh, bl, ldk, rows, N, lam_pa, ld_pa, accumulate, st);
+        }
         case 'A': return launch_edge<UmmaCfg<256, 32, 2, 128, 1>>(fn, lam_v, lam_lo, ld_v, bh, bl, ldk, rows, N, lam_pa, ld_pa, accumulate, st);
         case 'B': return launch_edge<UmmaCfg<256, 16, 2, 128, 1>>(fn, lam_v, lam_lo, ld_v, bh, bl, ldk, rows, N, lam_pa, ld_pa, accumulate, st);
         case 'C': return launch_edge<UmmaCfg<128, 16, 2, 128, 1>>(fn, lam_v, lam_lo, ld_v, bh, bl, ldk, rows, N, lam_pa, ld_pa, accumulate, st);

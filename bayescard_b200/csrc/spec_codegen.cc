@@ -50,9 +50,11 @@ inline std::string I(long long x) { return std::to_string(x); }
 //                          a big tree is a straight line of 100-400 KB, larger than the SM's instruction cache;
 //                          warps that drift apart each stream it from L2 on their own, warps kept within one
 //                          cache-sized window of each other share the fetched lines.
-//   BC_SPEC_DYNAMIC=1      CTAs take their rounds of ntid queries from a global counter (p_ctr) instead of a fixed
-//                          stride: SMs do not all run this fetch-bound code at the same speed (ncu: 510-679 k active
-//                          cycles per SM on DMV), and with a static split the slowest SM sets the time.
+//   BC_SPEC_DYNAMIC=0      back to the static split.  By DEFAULT the CTAs take their rounds of ntid queries from a global
+//                          counter (p_ctr) instead of a fixed stride: SMs do not all run this fetch-bound code at the
+//                          same speed (ncu: 510-679 k active cycles per SM on DMV), and with a static split the
+//                          slowest SM sets the time.  Measured (profiles/r1_spec_dynamic.txt): DMV 3.00 -> 3.55e9 q/s
+//                          (63 -> 75 % of the FP32 peak), Census 9.8 -> 10.8e9 (60 -> 66 %), IMDB unchanged.
 //   BC_SPEC_THREADS / BC_SPEC_MIN_BLOCKS   override the CTA geometry chosen by bc_spec_geometry.
 int env_int(const char* name, int dflt) {
     const char* e = std::getenv(name);
@@ -140,15 +142,16 @@ struct Gen {
         order.push_back(seed);
         for (int c = 0; c < card; ++c)
             if (c != seed) order.push_back(c);
-        // dense rows: weights of this node, round_up(card,4)/4 vector loads
-        std::vector<std::string> wreg;
-        if (dense) {
-            for (int j = 0; j < (card + 3) / 4; ++j) {
-                std::string a = F(), b = F(), c2 = F(), d = F();
-                line("ld.global.nc.v4.f32 {" + a + ", " + b + ", " + c2 + ", " + d + "}, [%rrow+" + I(4LL * (nd.lam_off + 4 * j)) + "];");
-                wreg.push_back(a); wreg.push_back(b); wreg.push_back(c2); wreg.push_back(d);
-            }
-        }
+        // dense rows: the weights of this node are loaded four at a time, right before the first state of the group
+        // is folded in (loading the whole node up front keeps up to card more registers live and spills on IMDB)
+        std::vector<std::string> wreg(dense ? ((card + 3) / 4) * 4 : 0);
+        auto need_weight = [&](int c) {
+            const int j = c / 4;
+            if (!wreg[4 * j].empty()) return;
+            std::string a = F(), b = F(), c2 = F(), d = F();
+            line("ld.global.nc.v4.f32 {" + a + ", " + b + ", " + c2 + ", " + d + "}, [%rrow+" + I(4LL * (nd.lam_off + 4 * j)) + "];");
+            wreg[4 * j] = a; wreg[4 * j + 1] = b; wreg[4 * j + 2] = c2; wreg[4 * j + 3] = d;
+        };
         for (int c : order) {
             bool any = false;
             for (int p = 0; p < cols; ++p) any |= Tat(c, p) != 0.f;
@@ -165,6 +168,7 @@ struct Gen {
                 }
             }
             if (dense) {
+                need_weight(c);
                 std::string u = wreg[c];
                 if (!lc.empty()) {
                     u = F();
@@ -218,7 +222,7 @@ std::string gen_kernel(const bc_model& m, bool dense, int threads, int min_block
     const std::string res = g.message(0)[0];
     if (n_fma) *n_fma = g.n_fma;
 
-    const bool dynamic = env_int("BC_SPEC_DYNAMIC", 0) != 0;
+    const bool dynamic = env_int("BC_SPEC_DYNAMIC", 1) != 0;
     std::string s;
     const char* name = dense ? "bc_spec_dense" : "bc_spec_bits";
     s += std::string(".visible .entry ") + name +
@@ -388,8 +392,8 @@ uint64_t bc_spec_hash_of(const bc_model& m) {
     const int ver = BC_CODEGEN_VERSION;
     mix(&ver, sizeof(ver));
     const int knobs[4] = {env_int("BC_SPEC_SYNC_EVERY", 0), env_int("BC_SPEC_THREADS", 0), env_int("BC_SPEC_MIN_BLOCKS", 0),
-                          env_int("BC_SPEC_DYNAMIC", 0)};
-    if (knobs[0] || knobs[1] || knobs[2] || knobs[3]) mix(knobs, sizeof(knobs));
+                          env_int("BC_SPEC_DYNAMIC", 1)};
+    if (knobs[0] || knobs[1] || knobs[2] || knobs[3] != 1) mix(knobs, sizeof(knobs));
     mix(&m.n, sizeof(m.n));
     for (const BcNodeRec& r : m.nodes) mix(&r, sizeof(r));
     mix(m.arena.data(), m.arena.size() * sizeof(float));

@@ -236,8 +236,13 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="")
     ap.add_argument("--factors", type=int, default=262144)
+    ap.add_argument("--only", default="", choices=["", "config1", "config3"])
     args = ap.parse_args()
-    rep = {"config1": [config1("dmv"), config1("census")], "config3": config3(args.factors)}
+    rep = {}
+    if args.only != "config3":
+        rep["config1"] = [config1("dmv"), config1("census")]
+    if args.only != "config1":
+        rep["config3"] = config3(args.factors)
     print(json.dumps(rep, indent=1))
     if args.out:
         with open(args.out, "w") as f:
