@@ -337,8 +337,11 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank)
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Remote arrive on the leader's barrier.  RELAXED: the only data the arrival publishes are TMEM reads that have
+// completed (tcgen05.wait::ld) and are ordered by tcgen05.fence::before_thread_sync; a release at cluster scope costs
+// a full memory barrier per chunk and per warp (ncu: `membar` was the top stall of the first version).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t leader_bar) {
     asm volatile(
@@ -463,6 +466,7 @@ k2_umma2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
 #pragma unroll
         for (int j = 0; j < EC; ++j) acc[j] = 0.f;
         const int n_chunks = num_kb * CHUNKS_PER_KB;
+        const uint32_t leader_acc_empty = mapa_rank(acc_empty0, 0);
         for (int chunk = 0; chunk < n_chunks; ++chunk) {
             const int buf = chunk & 1;
             mbar_wait(acc_full0 + 8 * buf, (chunk >> 1) & 1);
@@ -483,7 +487,10 @@ k2_umma2_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(mapa_rank(acc_empty0 + 8 * buf, 0));
+            if (lane == 0) {
+                if (leader) mbar_arrive(acc_empty0 + 8 * buf);  // local, CTA scope
+                else mbar_arrive_cluster(leader_acc_empty + 8 * buf);
+            }
         }
         const int r = m0 + quarter * 32 + lane;
         if (r < rows) {

@@ -207,6 +207,25 @@ BC_API int bc_sqlc_add_continuous(bc_sqlc* c, const char* name, int node, double
 BC_API int bc_sqlc_compile(const bc_sqlc* c, size_t n_queries, const char* const* sql, uint8_t* kind, void* bits_rows,
                            float* dense_rows, size_t dense_capacity, uint32_t* dense_index, size_t* n_dense);
 
+/* ---- CPT fitting for a fixed tree --------------------------------------------------
+ * Replaces `self.model.fit(discrete_table)` (Models/Bayescard_BN.py:108-110): BayesianModel.fit
+ * (Pgmpy/models/BayesianModel.py:278-323) -> MaximumLikelihoodEstimator.estimate_cpd (Pgmpy/estimators/MLE.py:61-104)
+ * -> state_counts (Pgmpy/estimators/base.py:63-135).  One pass over the discretised table counts, for every node v,
+ * how often (state of v, state of parent(v)) occurs:
+ *   table_dev   DEVICE pointer, n_rows rows of bin ids, row-major, column v = topological node v, elements of
+ *               elem_bytes (1: uint8, card <= 256; 2: uint16), row stride row_stride_elems (>= n_nodes) elements
+ *   counts_dev  DEVICE pointer to n_counters + 1 64-bit counters: n_counters = sum_v card[v] * card[parent(v)] (root:
+ *               card[0]), node after node in topological order, counter of (c, p) at off_v + c * card[parent(v)] + p
+ *               -- the layout of TabularCPD.values -- followed by ONE extra counter, the number of skipped rows;
+ *               zeroed by the call
+ *   bad_rows_host  (nullable) number of rows skipped because a bin id was >= card; reading it synchronises the stream
+ * The column normalisation (all-zero column -> uniform, MLE.py:77-79; values / values.sum(axis=0), CPD.normalize) is a
+ * few thousand fp64 divisions and is left to the caller (bayescard_b200/fit.py), which keeps the CPTs bit-identical to
+ * the reference's. */
+BC_API int bc_fit_counts(int device, int n_nodes, const int32_t* parent, const int32_t* card, const void* table_dev,
+                         int elem_bytes, size_t n_rows, size_t row_stride_elems, unsigned long long* counts_dev,
+                         size_t n_counters, uint32_t* bad_rows_host, void* stream);
+
 /* Measured FP32 FFMA peak of the device (TFLOP/s), the roofline denominator SURVEY.md section 8d
  * asks to measure in the same run rather than quote. */
 BC_API int bc_measure_fp32_peak(int device, double* tflops, double* sm_clock_mhz);

@@ -508,3 +508,39 @@ def q_error(pred, true):
     elif true == 0:
         true = 1
     return max(pred / true, true / pred)
+
+
+# --------------------------------------------------------------------------------------------
+# 6. CPT fitting for a fixed tree  (Pgmpy/estimators/MLE.py:61-104, Pgmpy/estimators/base.py:63-135)
+# --------------------------------------------------------------------------------------------
+
+
+def fit_counts(parent, card, table):
+    """``state_counts`` for every node: counts[v][c, p] = #rows with column v == c and column parent(v) == p
+    (base.py:101-135; the reference reaches it through a pandas group-by).  Rows holding an id >= card are skipped."""
+    table = np.asarray(table).astype(np.int64)
+    card = np.asarray(card, dtype=np.int64)
+    ok = (table < card[None, :]).all(axis=1) if table.size else np.zeros(0, dtype=bool)
+    t = table[ok]
+    out = []
+    for v in range(len(card)):
+        if parent[v] < 0:
+            out.append(np.bincount(t[:, v], minlength=int(card[v])).astype(np.uint64))
+        else:
+            cp = int(card[parent[v]])
+            flat = np.bincount(t[:, v] * cp + t[:, parent[v]], minlength=int(card[v]) * cp)
+            out.append(flat.reshape(int(card[v]), cp).astype(np.uint64))
+    return out, int((~ok).sum())
+
+
+def fit_cpts(parent, card, table):
+    """``MaximumLikelihoodEstimator.estimate_cpd`` (MLE.py:61-104): counts, all-zero columns -> ones (:77-79),
+    ``cpd.normalize()`` = values / values.sum(axis=0)."""
+    counts, _ = fit_counts(parent, card, table)
+    cpts = []
+    for v, c in enumerate(counts):
+        t = c.astype(np.float64).reshape(int(card[v]), -1)
+        t[:, (t == 0).all(axis=0)] = 1.0
+        t = t / t.sum(axis=0)
+        cpts.append(t.reshape(-1) if parent[v] < 0 else t)
+    return cpts
