@@ -36,6 +36,7 @@ struct BcBitsRec {
 
 struct BcHostPipe;  // bc_api.cu
 struct BcUmmaPlan;  // k2_umma.cu
+struct BcK3Plan;    // k3_fused.cu
 
 // State of the batched large-domain path (K2), built on first use.
 struct BcK2Plan {
@@ -88,6 +89,8 @@ struct bc_model {
     std::atomic<uint32_t> spec_ctr_next{0};
     BcK2Plan* k2 = nullptr;
     std::mutex k2_mu;                // guards the lazy construction of k2 (pipe_mu may already be held)
+    BcK3Plan* k3 = nullptr;          // fused tensor-core tree kernel: edge schedule, TMEM columns, operand images
+    std::mutex k3_mu;
     BcHostPipe* pipe = nullptr;
     std::mutex pipe_mu;
 };
@@ -121,6 +124,9 @@ void bc_k2_free(bc_model* m);
 int bc_k2_umma_edge(bc_model* m, const uint8_t* desc, size_t dstride, int fmt, size_t q0, int rows, int v, float* lam_v,
                     float* lam_v_lo, int ld_v, float* lam_pa, int ld_pa, int accumulate, cudaStream_t stream);
 void bc_k2_umma_free(bc_model* m);
+// k3_fused.cu: whole tree per 128-query tile on the tensor cores (BITS / DENSE_F32 rows); BC_ELIMIT = model not served
+int bc_k3_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32_t* fan_mask, float* out, cudaStream_t stream);
+void bc_k3_free(bc_model* m);
 // spec_codegen.cc
 std::string bc_spec_generate(const bc_model& m);
 uint64_t bc_spec_hash_of(const bc_model& m);

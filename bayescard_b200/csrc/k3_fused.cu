@@ -1,0 +1,570 @@
+// K3 -- fused whole-tree sum-product on the tensor cores: one CTA carries a tile of 128 queries through EVERY edge
+// of the tree without leaving the SM.
+//
+//     out[q] = sum_x prod_v w_v[x_v] * T_v[x_v, x_pa(v)]        (VariableEliminationJIT.query / .expectation,
+//                                                                 reference Pgmpy/inference/ExactInference.py:112-287)
+//
+// evaluated leaf -> root as one small GEMM per edge v -> pa(v):
+//
+//     D[128 x N]  = U_v[128 x K] . T_v[K x N]        U_v = w_v (*) Lambda_v,  K = card(v), N = card(pa)
+//     Lambda_pa  *= D
+//
+// Why it exists: the per-model straight-line kernel (K-spec) keeps the CPTs in the instruction stream and is
+// instruction-fetch bound once a model has more than ~10k CPT entries (IMDB: 45 % of the FP32 peak with unit
+// weights, 19 % with fractional weights / fan-out expectations); K2 runs one launch per edge and moves every Lambda
+// through HBM.  Here the messages never leave the SM:
+//
+//   * Lambda_v of every live internal node sits in TENSOR MEMORY (one fp32 column per state, one lane per query);
+//     the columns are assigned on the host by first fit over the nodes' lifetimes in the edge schedule;
+//   * per edge and per block of 16 child states the 128 threads (thread = query = TMEM lane) read Lambda_v with
+//     tcgen05.ld, apply the query's weights (BITS mask, dense n_distinct weights, fan-out vector), split the product
+//     into TF32 hi + lo and write both as the K-major, 64-byte-swizzled A operand straight into shared memory;
+//   * the matching block of T_v^T (hi and lo, pre-split, pre-swizzled once per model) arrives by ONE TMA bulk copy
+//     (cp.async.bulk ... mbarrier::complete_tx) into the same ring slot, prefetched one step ahead;
+//   * one thread issues tcgen05.mma.cta_group::1.kind::tf32, error compensated: A_lo.B_hi + A_hi.B_lo + A_hi.B_hi
+//     (the small products first; A_lo = 0 and is skipped for unit-weight leaves) into a TMEM accumulator;
+//     tcgen05.commit frees the ring slot and, after the edge's last block, releases the accumulator;
+//   * the epilogue multiplies the accumulator into Lambda_pa with tcgen05.ld / tcgen05.st -- no shared memory, no
+//     HBM traffic; the root is a dot product with T_root in registers.
+//   * two CTAs per SM (256 TMEM columns and ~93 KB of shared memory each) overlap one tile's operand building and
+//     epilogue with the other's MMAs.
+//
+// Algorithmic work per query = flops_dense(model) (every CPT entry once); HBM traffic = descriptor row + 4 B.
+#include <algorithm>
+#include <cstring>
+
+#include "bc_internal.h"
+
+struct K3Edge {            // 64 bytes, copied to shared memory
+    int32_t v, K, N, n_pad;
+    int32_t lam_off;       // first float of column v in a DENSE row
+    int32_t bit_off;       // first bit of column v in a BITS row
+    int32_t fan_off;       // fanouts[v] in the fan arena, -1 if none
+    int32_t col_v;         // TMEM column of Lambda_v, -1 for a leaf
+    int32_t col_pa;        // TMEM column of Lambda_pa
+    int32_t first;         // this edge is the first message into Lambda_pa
+    int32_t nkb;           // blocks of 16 child states
+    uint32_t idesc;        // tcgen05 instruction descriptor (M = 128, N = n_pad, TF32 x TF32 -> F32, K-major)
+    uint64_t bimg_off;     // byte offset of the edge's operand images
+    int32_t pad[2];
+};
+static_assert(sizeof(K3Edge) == 64, "K3Edge layout");
+
+struct BcK3Plan {
+    int failed = 0;
+    std::vector<K3Edge> edges;
+    K3Edge* d_edges = nullptr;
+    uint8_t* d_bimg = nullptr;
+    size_t bimg_bytes = 0;
+    int npad_max = 16;
+    int tmem_cols = 32;    // power of two
+    int d_col = 0;
+    int root_col = 0;
+    int ctas_per_sm = 1;
+    size_t smem = 0;
+};
+
+namespace {
+
+constexpr int kTile = 128;    // queries per CTA tile = TMEM lanes = UMMA M
+constexpr int kBK = 16;       // child states per ring step: one 64-byte swizzle row
+constexpr int kStages = 3;
+constexpr int kABytes = kTile * kBK * 4;   // 8 KB per half (hi or lo)
+
+struct K3Params {
+    const K3Edge* edges;
+    int n_edges;
+    const uint8_t* bimg;
+    const uint8_t* desc;
+    size_t dstride;
+    const uint32_t* fan_mask;
+    const float* fan;
+    const float* root_T;       // T_root in the arena
+    int root_card, root_col, root_bit_off, root_lam_off, root_fan_off, root_has_children;
+    float* out;
+    size_t nq;
+    long long n_tiles;
+    int bits_words;
+    int slot_bytes;            // 2 * kABytes + 2 * npad_max * 64
+    int d_col;
+    int tmem_cols;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, unsigned parity) {
+    asm volatile(
+        "{\n.reg .pred p;\nWAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, unsigned bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+// K-major operand, 64-byte swizzle: rows of 64 B, 8-row groups 512 B apart (SBO), layout type 4, version 1 (sm_100)
+__device__ __forceinline__ uint64_t umma_desc64(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_c),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
+    const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+                 "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// x = hi + lo, hi = x rounded to the nearest TF32 number (ties away from zero: two integer instructions); lo = x - hi is
+// exact in fp32 and symmetric around zero, so the tensor core's truncation of its low bits is unbiased
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+    lo = x - hi;
+}
+
+// weights of 8 consecutive states [c0, c0 + 8) of column `e` for this thread's query
+template <int FMT>
+__device__ __forceinline__ void load_weights8(const K3Params& P, const uint32_t* s_bits, const float* drow, uint32_t fm, int v,
+                                              int lam_off, int bit_off, int fan_off, int card, int c0, float* w) {
+    if (FMT == BC_DESC_BITS) {
+        const int b0 = bit_off + c0, idx = b0 >> 5, sh = b0 & 31;
+        const uint32_t w0 = s_bits[idx * kTile];
+        const uint32_t w1 = s_bits[(idx + 1 < P.bits_words ? idx + 1 : idx) * kTile];
+        const uint32_t m = __funnelshift_r(w0, w1, sh);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w[j] = (c0 + j < card && ((m >> j) & 1u)) ? 1.f : 0.f;
+    } else {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(drow + lam_off + c0));
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c0 + 4 < card) b = __ldg(reinterpret_cast<const float4*>(drow + lam_off + c0 + 4));
+        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (c0 + j >= card) w[j] = 0.f;   // padding entries of a DENSE row never contribute
+    }
+    if (fan_off >= 0 && ((fm >> v) & 1u)) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (c0 + j < card) w[j] *= __ldg(P.fan + fan_off + c0 + j);
+    }
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(kTile, 2) k3_kernel(const K3Params P) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int tid = threadIdx.x, warp = tid >> 5;
+    uint8_t* p = smem + (size_t)kStages * P.slot_bytes;
+    uint32_t* s_bits = reinterpret_cast<uint32_t*>(p);                    // [word][thread]
+    p += (FMT == BC_DESC_BITS ? (size_t)P.bits_words * kTile * 4 : 0);
+    K3Edge* s_edges = reinterpret_cast<K3Edge*>(p);
+    p += (size_t)P.n_edges * sizeof(K3Edge);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(p);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kStages), dfull = smem_u32(bars + 2 * kStages);
+    const uint32_t slot0 = smem_u32(smem);
+
+    {   // edge table -> shared memory
+        const uint4* src = reinterpret_cast<const uint4*>(P.edges);
+        uint4* dst = reinterpret_cast<uint4*>(s_edges);
+        for (int i = tid; i < P.n_edges * 4; i += kTile) dst[i] = src[i];
+    }
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        mbar_init(dfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(P.tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);   // this warp's TMEM lane quarter
+
+    uint32_t it = 0;        // ring step counter (runs on across tiles)
+    uint32_t dphase = 0;
+    // B-operand prefetch cursor (thread 0): the step sequence (edge, block) repeats for every tile
+    int pf_e = 0, pf_kb = 0;
+    uint32_t pf_it = 0;
+    long long pf_tiles_left = 0;
+    for (long long t = blockIdx.x; t < P.n_tiles; t += gridDim.x) ++pf_tiles_left;
+    auto prefetch_one = [&]() {   // thread 0 only
+        if (pf_tiles_left == 0) return;
+        const K3Edge& E = s_edges[pf_e];
+        const uint32_t s = pf_it % kStages, par = (pf_it / kStages) & 1u;
+        mbar_wait(empty0 + 8 * s, par ^ 1u);
+        const unsigned bytes = (unsigned)E.n_pad * 128u;   // hi + lo, 64 B per row each
+        mbar_expect_tx(full0 + 8 * s, bytes);
+        tma_bulk_g2s(slot0 + s * P.slot_bytes + 2 * kABytes, P.bimg + E.bimg_off + (size_t)pf_kb * bytes, bytes, full0 + 8 * s);
+        ++pf_it;
+        if (++pf_kb == E.nkb) {
+            pf_kb = 0;
+            if (++pf_e == P.n_edges) {
+                pf_e = 0;
+                --pf_tiles_left;
+            }
+        }
+    };
+    if (tid == 0) prefetch_one();
+
+    for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+        const size_t q = (size_t)tile * kTile + tid;
+        const size_t qc = q < P.nq ? q : P.nq - 1;
+        const uint32_t fm = P.fan_mask ? P.fan_mask[qc] : 0u;
+        const float* drow = reinterpret_cast<const float*>(P.desc + qc * P.dstride);
+        if (FMT == BC_DESC_BITS) {
+            const uint32_t* grow = reinterpret_cast<const uint32_t*>(P.desc + qc * P.dstride);
+            for (int w4 = 0; w4 < P.bits_words; w4 += 4) {   // bits_words is a multiple of 4
+                const uint4 x = __ldg(reinterpret_cast<const uint4*>(grow + w4));
+                s_bits[(w4 + 0) * kTile + tid] = x.x;
+                s_bits[(w4 + 1) * kTile + tid] = x.y;
+                s_bits[(w4 + 2) * kTile + tid] = x.z;
+                s_bits[(w4 + 3) * kTile + tid] = x.w;
+            }
+        }
+        const uint32_t* my_bits = s_bits + tid;
+
+        for (int e = 0; e < P.n_edges; ++e) {
+            const K3Edge E = s_edges[e];
+            const bool a_exact = FMT == BC_DESC_BITS && E.col_v < 0 && !(E.fan_off >= 0 && P.fan_mask != nullptr);
+            for (int kb = 0; kb < E.nkb; ++kb, ++it) {
+                const uint32_t s = it % kStages, par = (it / kStages) & 1u;
+                const uint32_t slot = slot0 + s * P.slot_bytes;
+                if (tid == 0) prefetch_one();                 // B of the NEXT step
+                mbar_wait(empty0 + 8 * s, par ^ 1u);           // the MMAs that read this slot's A are done
+                // ---- build 16 states of U_v = w_v (*) Lambda_v for this thread's query
+                const int c0 = kb * kBK;
+                const int ks = (E.K - c0 > 8) ? 2 : 1;         // k-steps of 8 in this block
+                float u[16];
+                if (E.col_v >= 0) {
+                    tmem_ld8(tlane + (uint32_t)(E.col_v + c0), u);
+                    if (ks == 2) tmem_ld8(tlane + (uint32_t)(E.col_v + c0 + 8), u + 8);
+                    tmem_ld_wait();
+                }
+                {
+                    float w[8];
+                    load_weights8<FMT>(P, my_bits, drow, fm, E.v, E.lam_off, E.bit_off, E.fan_off, E.K, c0, w);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) u[j] = E.col_v >= 0 ? u[j] * w[j] : w[j];
+                    if (ks == 2) {
+                        load_weights8<FMT>(P, my_bits, drow, fm, E.v, E.lam_off, E.bit_off, E.fan_off, E.K, c0 + 8, w);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) u[8 + j] = E.col_v >= 0 ? u[8 + j] * w[j] : w[j];
+                    }
+                }
+                // states >= K inside the last k-step must be exact zeros (Lambda columns there are stale)
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (c0 + j >= E.K) u[j] = 0.f;
+                // 64-byte swizzle: 16-byte chunk j of row r lives at r * 64 + ((j ^ ((r >> 1) & 3)) << 4)
+                const uint32_t row = slot + (uint32_t)tid * 64u;
+                const uint32_t sw = ((uint32_t)tid >> 1) & 3u;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (j < 2 * ks) {
+                        float h[4], l[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) split_tf32(u[4 * j + i], h[i], l[i]);
+                        const uint32_t a = row + (((uint32_t)j ^ sw) << 4);
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(h[0]), "f"(h[1]), "f"(h[2]), "f"(h[3]) : "memory");
+                        if (!a_exact)
+                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a + kABytes), "f"(l[0]), "f"(l[1]), "f"(l[2]), "f"(l[3]) : "memory");
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+                tc_fence_before();
+                __syncthreads();
+                if (tid == 0) {
+                    mbar_wait(full0 + 8 * s, par);   // T_v^T block has landed
+                    tc_fence_after();
+                    const uint64_t a_hi = umma_desc64(slot), a_lo = umma_desc64(slot + kABytes);
+                    const uint64_t b_hi = umma_desc64(slot + 2 * kABytes), b_lo = umma_desc64(slot + 2 * kABytes + (uint32_t)E.n_pad * 64u);
+                    const uint32_t d = tmem + (uint32_t)P.d_col;
+                    uint32_t acc = kb != 0;
+                    for (int kk = 0; kk < ks; ++kk) {   // 8 TF32 = 32 bytes per k-step: +2 in the 16-byte address field
+                        const uint64_t o = (uint64_t)(kk * 2);
+                        if (!a_exact) {
+                            umma_tf32(d, a_lo + o, b_hi + o, E.idesc, acc);
+                            acc = 1;
+                        }
+                        umma_tf32(d, a_hi + o, b_lo + o, E.idesc, acc);
+                        acc = 1;
+                    }
+                    for (int kk = 0; kk < ks; ++kk) {
+                        const uint64_t o = (uint64_t)(kk * 2);
+                        umma_tf32(d, a_hi + o, b_hi + o, E.idesc, 1);
+                    }
+                    umma_commit(empty0 + 8 * s);
+                    if (kb == E.nkb - 1) umma_commit(dfull);
+                }
+            }
+            // ---- epilogue: Lambda_pa (*)= D, all in tensor memory
+            mbar_wait(dfull, dphase);
+            dphase ^= 1u;
+            tc_fence_after();
+            const int n8 = (E.N + 7) & ~7;
+            for (int j = 0; j < n8; j += 8) {
+                float dv[8], lv[8];
+                tmem_ld8(tlane + (uint32_t)(P.d_col + j), dv);
+                if (!E.first) tmem_ld8(tlane + (uint32_t)(E.col_pa + j), lv);
+                tmem_ld_wait();
+                if (!E.first) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) dv[i] *= lv[i];
+                }
+                tmem_st8(tlane + (uint32_t)(E.col_pa + j), dv);
+            }
+            tmem_st_wait();
+            tc_fence_before();   // ordered before the __syncthreads that precedes the next MMA into D
+        }
+
+        // ---- root: sum_c w_0[c] * Lambda_0[c] * T_0[c]
+        float res = 0.f;
+        for (int c0 = 0; c0 < P.root_card; c0 += 8) {
+            float lv[8], w[8];
+            if (P.root_has_children) {
+                tmem_ld8(tlane + (uint32_t)(P.root_col + c0), lv);
+                tmem_ld_wait();
+            }
+            load_weights8<FMT>(P, my_bits, drow, fm, 0, P.root_lam_off, P.root_bit_off, P.root_fan_off, P.root_card, c0, w);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (c0 + j < P.root_card) res = fmaf(P.root_has_children ? lv[j] * w[j] : w[j], __ldg(P.root_T + c0 + j), res);
+        }
+        if (q < P.nq) P.out[q] = res;
+        tc_fence_before();
+        __syncthreads();   // s_bits and the root's TMEM columns are rewritten by the next tile
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(P.tmem_cols) : "memory");
+    }
+}
+
+uint32_t host_tf32_hi(float x) {
+    uint32_t b;
+    std::memcpy(&b, &x, 4);
+    return (b + 0x1000u) & 0xFFFFE000u;
+}
+
+int k3_prepare(bc_model* m) {
+    if (m->k3) return m->k3->failed ? BC_ELIMIT : BC_OK;
+    BcK3Plan* k = new BcK3Plan();
+    m->k3 = k;
+    auto fail = [&](const char* why) {
+        k->failed = 1;
+        bc_set_error("fused tensor-core kernel (K3) does not serve this model: %s", why);
+        return BC_ELIMIT;
+    };
+    const int n = m->n;
+    if (n < 2) return fail("single-node model");
+    if (n > 32) return fail("more than 32 columns (one fan-out mask word per query)");
+    if (m->arena.empty()) return fail("no host copy of the CPT arena");
+    // ---- edge schedule: reverse topological order (children before parents)
+    std::vector<int> first_child_edge(n, -1), own_edge(n, -1);
+    for (int v = n - 1, e = 0; v >= 1; --v, ++e) {
+        own_edge[v] = e;
+        const int pa = m->nodes[v].parent;
+        if (first_child_edge[pa] < 0) first_child_edge[pa] = e;
+    }
+    const int n_edges = n - 1;
+    int npad_max = 16;
+    for (int v = 1; v < n; ++v) {
+        const int np = (int)bc_round_up(m->nodes[v].card_pa, 16);
+        if (np > 256) return fail("a parent domain exceeds 256 states");
+        if (np > npad_max) npad_max = np;
+    }
+    // ---- TMEM columns: accumulator D first, then Lambda of every internal node by first fit over lifetimes
+    //      [edge of its first child, its own edge] (the root lives to the end), in units of 8 columns
+    const int units_total = 512 / 8;
+    std::vector<int> busy_until(units_total, -1);   // last edge index that uses the unit
+    const int d_units = npad_max / 8;
+    for (int u = 0; u < d_units; ++u) busy_until[u] = 1 << 30;
+    std::vector<int> col(n, -1);
+    int units_used = d_units;
+    std::vector<int> order;   // internal nodes by start of lifetime
+    for (int v = 0; v < n; ++v)
+        if (first_child_edge[v] >= 0) order.push_back(v);
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return first_child_edge[a] < first_child_edge[b]; });
+    for (int v : order) {
+        const int need = (int)bc_round_up(m->nodes[v].card, 8) / 8;
+        const int start = first_child_edge[v], end = v == 0 ? (1 << 30) : own_edge[v];
+        int at = -1;
+        for (int u0 = 0; u0 + need <= units_total && at < 0; ++u0) {
+            bool ok = true;
+            for (int u = u0; u < u0 + need; ++u)
+                if (busy_until[u] >= start) { ok = false; break; }
+            if (ok) at = u0;
+        }
+        if (at < 0) return fail("live messages exceed the 512 columns of tensor memory");
+        for (int u = at; u < at + need; ++u) busy_until[u] = end;
+        col[v] = at * 8;
+        if (at + need > units_used) units_used = at + need;
+    }
+    int tmem_cols = 32;
+    while (tmem_cols < units_used * 8) tmem_cols <<= 1;
+    k->tmem_cols = tmem_cols;
+    k->npad_max = npad_max;
+    k->d_col = 0;
+    k->root_col = col[0];
+    // ---- operand images: per edge and block of 16 child states, T_v^T hi then lo, 64-byte swizzled rows
+    size_t total = 0;
+    k->edges.resize(n_edges);
+    for (int v = n - 1, e = 0; v >= 1; --v, ++e) {
+        const BcNodeRec& nd = m->nodes[v];
+        K3Edge& E = k->edges[e];
+        std::memset(&E, 0, sizeof(E));
+        E.v = v;
+        E.K = nd.card;
+        E.N = nd.card_pa;
+        E.n_pad = (int)bc_round_up(nd.card_pa, 16);
+        E.lam_off = nd.lam_off;
+        E.bit_off = m->bits[v].bit_off;
+        E.fan_off = nd.fan_off;
+        E.col_v = col[v];
+        E.col_pa = col[nd.parent];
+        E.first = first_child_edge[nd.parent] == e;
+        E.nkb = (nd.card + kBK - 1) / kBK;
+        E.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(E.n_pad >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
+        E.bimg_off = total;
+        total += (size_t)E.nkb * E.n_pad * 128;
+    }
+    std::vector<uint8_t> img(total, 0);
+    for (const K3Edge& E : k->edges) {
+        const BcNodeRec& nd = m->nodes[E.v];
+        const float* T = m->arena.data() + nd.cpt_off;
+        for (int kb = 0; kb < E.nkb; ++kb) {
+            uint8_t* hi = img.data() + E.bimg_off + (size_t)kb * E.n_pad * 128;
+            uint8_t* lo = hi + (size_t)E.n_pad * 64;
+            for (int p = 0; p < E.N; ++p)
+                for (int kk = 0; kk < kBK; ++kk) {
+                    const int c = kb * kBK + kk;
+                    if (c >= E.K) continue;
+                    const float x = T[(size_t)c * nd.stride + p];
+                    const uint32_t hb = host_tf32_hi(x);
+                    float h;
+                    std::memcpy(&h, &hb, 4);
+                    const float l = x - h;
+                    const uint32_t lb = host_tf32_hi(l);
+                    const size_t off = (size_t)p * 64 + ((size_t)((kk >> 2) ^ ((p >> 1) & 3)) << 4) + (size_t)(kk & 3) * 4;
+                    std::memcpy(hi + off, &hb, 4);
+                    std::memcpy(lo + off, &lb, 4);
+                }
+        }
+    }
+    k->bimg_bytes = total;
+    // ---- shared memory / residency
+    const size_t slot = 2 * kABytes + (size_t)npad_max * 128;
+    const size_t fixed = (size_t)m->bits_words * kTile * 4 + (size_t)n_edges * sizeof(K3Edge) + 128 /* barriers */ + 1024 /* alignment */;
+    k->smem = kStages * slot + fixed;
+    if (k->smem > (size_t)m->smem_optin) return fail("ring slots exceed shared memory");
+    k->ctas_per_sm = (tmem_cols <= 256 && 2 * (k->smem + 1024) <= 228 * 1024) ? 2 : 1;
+    if (k->ctas_per_sm == 1) k->smem = (size_t)m->smem_optin;   // a second CTA would only spin in tcgen05.alloc
+    BC_CUDA_CHECK(cudaMalloc(&k->d_edges, sizeof(K3Edge) * n_edges));
+    BC_CUDA_CHECK(cudaMemcpy(k->d_edges, k->edges.data(), sizeof(K3Edge) * n_edges, cudaMemcpyHostToDevice));
+    BC_CUDA_CHECK(cudaMalloc(&k->d_bimg, total));
+    BC_CUDA_CHECK(cudaMemcpy(k->d_bimg, img.data(), total, cudaMemcpyHostToDevice));
+    return BC_OK;
+}
+
+template <int FMT>
+int k3_launch_fmt(bc_model* m, const K3Params& P, int grid, cudaStream_t st) {
+    static bool attr_set[64] = {};
+    int dev = 0;
+    BC_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        BC_CUDA_CHECK(cudaFuncSetAttribute(k3_kernel<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_optin));
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    k3_kernel<FMT><<<grid, kTile, m->k3->smem, st>>>(P);
+    BC_CUDA_CHECK(cudaGetLastError());
+    bc_count_launch();
+    return BC_OK;
+}
+
+}  // namespace
+
+int bc_k3_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32_t* fan_mask, float* out, cudaStream_t st) {
+    if (nq == 0) return BC_OK;
+    if (fmt != BC_DESC_BITS && fmt != BC_DESC_DENSE_F32) {
+        bc_set_error("the fused kernel reads BITS or DENSE_F32 rows (convert range rows with bc_convert_desc)");
+        return BC_EINVAL;
+    }
+    {
+        std::lock_guard<std::mutex> g(m->k3_mu);
+        int rc = k3_prepare(m);
+        if (rc) return rc;
+    }
+    const BcK3Plan* k = m->k3;
+    K3Params P{};
+    P.edges = k->d_edges;
+    P.n_edges = (int)k->edges.size();
+    P.bimg = k->d_bimg;
+    P.desc = static_cast<const uint8_t*>(desc);
+    P.dstride = (size_t)bc_model_desc_stride(m, fmt);
+    P.fan_mask = fan_mask;
+    P.fan = m->d_fan;
+    const BcNodeRec& r = m->nodes[0];
+    P.root_T = m->d_arena + r.cpt_off;
+    P.root_card = r.card;
+    P.root_col = k->root_col;
+    P.root_bit_off = m->bits[0].bit_off;
+    P.root_lam_off = r.lam_off;
+    P.root_fan_off = r.fan_off;
+    P.root_has_children = k->root_col >= 0;
+    P.out = out;
+    P.nq = nq;
+    P.n_tiles = (long long)((nq + kTile - 1) / kTile);
+    P.bits_words = m->bits_words;
+    P.slot_bytes = 2 * kABytes + k->npad_max * 128;
+    P.d_col = k->d_col;
+    P.tmem_cols = k->tmem_cols;
+    long long grid = (long long)m->sm_count * k->ctas_per_sm;
+    if (grid > P.n_tiles) grid = P.n_tiles;
+    if (fmt == BC_DESC_BITS) return k3_launch_fmt<BC_DESC_BITS>(m, P, (int)grid, st);
+    return k3_launch_fmt<BC_DESC_DENSE_F32>(m, P, (int)grid, st);
+}
+
+void bc_k3_free(bc_model* m) {
+    if (!m->k3) return;
+    cudaFree(m->k3->d_edges);
+    cudaFree(m->k3->d_bimg);
+    delete m->k3;
+    m->k3 = nullptr;
+}

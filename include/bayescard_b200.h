@@ -84,6 +84,8 @@ extern "C" {
 #define BC_KERNEL_GEMM 3     /* K2: per-edge batched path for large domains, tcgen05 3xTF32 GEMM
                                 where the edge shape allows, FP32 SIMT GEMM otherwise; RANGE_* rows */
 #define BC_KERNEL_GEMM_SIMT 4 /* K2 with the FP32 SIMT GEMM only (the comparator for K2)      */
+#define BC_KERNEL_FUSED 5    /* K3: whole tree per 128-query tile on the tensor cores (tcgen05 3xTF32), messages in
+                                tensor memory; models of <= 32 columns with domains <= 256 states, else BC_ELIMIT */
 
 typedef struct bc_model bc_model;
 
