@@ -53,12 +53,11 @@ static_assert(sizeof(K3Edge) == 64, "K3Edge layout");
 struct BcK3Plan {
     int failed = 0;
     std::vector<K3Edge> edges;
-    K3Edge* d_edges = nullptr;
     uint8_t* d_bimg = nullptr;
     size_t bimg_bytes = 0;
     int npad_max = 16;
     int tmem_cols = 32;    // power of two
-    int d_col = 0;
+    int d_col = 0, n_dbuf = 1;
     int root_col = 0;
     int ctas_per_sm = 1;
     size_t smem = 0;
@@ -68,25 +67,30 @@ namespace {
 
 constexpr int kTile = 128;    // queries per CTA tile = TMEM lanes = UMMA M
 constexpr int kBK = 16;       // child states per ring step: one 64-byte swizzle row
-constexpr int kStages = 3;
+constexpr int kStagesA = 3;   // A ring: U_v blocks written by the producer warps
+constexpr int kStagesB = 4;   // B ring: T_v^T blocks fetched by TMA (deeper: an L2 round trip is longer than a step)
 constexpr int kABytes = kTile * kBK * 4;   // 8 KB per half (hi or lo)
+constexpr int kProducerWarps = 4;
+constexpr int kThreads = 32 * (kProducerWarps + 2);   // + MMA issuer warp + TMA warp
 
 struct K3Params {
-    const K3Edge* edges;
+    K3Edge edge[31];           // in the kernel parameter bank: uniform loads, warp-uniform control flow
     int n_edges;
     const uint8_t* bimg;
     const uint8_t* desc;
     size_t dstride;
     const uint32_t* fan_mask;
     const float* fan;
+    int fan_floats;            // multiple of 4 (shared-memory copy, zero padded)
+    int fan_n;                 // floats in the fan arena
     const float* root_T;       // T_root in the arena
     int root_card, root_col, root_bit_off, root_lam_off, root_fan_off, root_has_children;
     float* out;
     size_t nq;
     long long n_tiles;
     int bits_words;
-    int slot_bytes;            // 2 * kABytes + 2 * npad_max * 64
-    int d_col;
+    int b_slot_bytes;          // 2 * npad_max * 64
+    int d_col, d_stride, n_dbuf;
     int tmem_cols;
 };
 
@@ -96,6 +100,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, unsigned count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, unsigned parity) {
     asm volatile(
@@ -109,15 +116,15 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, unsi
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
-// K-major operand, 64-byte swizzle: rows of 64 B, 8-row groups 512 B apart (SBO), layout type 4, version 1 (sm_100)
-__device__ __forceinline__ uint64_t umma_desc64(uint32_t smem_addr) {
-    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+// K-major operands, 64-byte swizzle: rows of 64 B, 8-row groups 512 B apart (SBO), layout type 4, version 1 (sm_100).
+// descriptors as 32-bit halves: the high word (SBO, version, swizzle mode) is the same for every operand
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint32_t a_lo32, uint32_t b_lo32, uint32_t desc_hi32, uint32_t idesc,
+                                          uint32_t accumulate) {
     asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_c),
-        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        "{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %5, 0;\n"
+        "mov.b64 da, {%1, %3};\nmov.b64 db, {%2, %3};\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n}\n" ::"r"(tmem_c),
+        "r"(a_lo32), "r"(b_lo32), "r"(desc_hi32), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -140,6 +147,9 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z, float w) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
 
 // x = hi + lo, hi = x rounded to the nearest TF32 number (ties away from zero: two integer instructions); lo = x - hi is
 // exact in fp32 and symmetric around zero, so the tensor core's truncation of its low bits is unbiased
@@ -148,17 +158,23 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     lo = x - hi;
 }
 
-// weights of 8 consecutive states [c0, c0 + 8) of column `e` for this thread's query
+// selection bits of states [c0, c0 + 16) of a column for this thread's query (bits past the domain cleared)
+__device__ __forceinline__ uint32_t bits16(const uint32_t* my_bits, int bits_words, int bit_off, int card, int c0) {
+    const int b0 = bit_off + c0, idx = b0 >> 5, sh = b0 & 31;
+    const uint32_t w0 = my_bits[idx * kTile];
+    const uint32_t w1 = my_bits[(idx + 1 < bits_words ? idx + 1 : idx) * kTile];
+    const int valid = card - c0;
+    return __funnelshift_r(w0, w1, sh) & (valid >= 16 ? 0xFFFFu : ((1u << valid) - 1u));
+}
+
+// weights of 8 consecutive states [c0, c0 + 8) of a column (root only: the edges have their own code below)
 template <int FMT>
-__device__ __forceinline__ void load_weights8(const K3Params& P, const uint32_t* s_bits, const float* drow, uint32_t fm, int v,
-                                              int lam_off, int bit_off, int fan_off, int card, int c0, float* w) {
+__device__ __forceinline__ void load_weights8(const uint32_t* my_bits, int bits_words, const float* drow, const float* s_fan, uint32_t fm,
+                                              int v, int lam_off, int bit_off, int fan_off, int card, int c0, float* w) {
     if (FMT == BC_DESC_BITS) {
-        const int b0 = bit_off + c0, idx = b0 >> 5, sh = b0 & 31;
-        const uint32_t w0 = s_bits[idx * kTile];
-        const uint32_t w1 = s_bits[(idx + 1 < P.bits_words ? idx + 1 : idx) * kTile];
-        const uint32_t m = __funnelshift_r(w0, w1, sh);
+        const uint32_t m = bits16(my_bits, bits_words, bit_off, card, c0);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) w[j] = (c0 + j < card && ((m >> j) & 1u)) ? 1.f : 0.f;
+        for (int j = 0; j < 8; ++j) w[j] = ((m >> j) & 1u) ? 1.f : 0.f;
     } else {
         const float4 a = __ldg(reinterpret_cast<const float4*>(drow + lam_off + c0));
         float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -171,36 +187,47 @@ __device__ __forceinline__ void load_weights8(const K3Params& P, const uint32_t*
     if (fan_off >= 0 && ((fm >> v) & 1u)) {
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-            if (c0 + j < card) w[j] *= __ldg(P.fan + fan_off + c0 + j);
+            if (c0 + j < card) w[j] *= s_fan[fan_off + c0 + j];
     }
 }
 
 template <int FMT>
-__global__ void __launch_bounds__(kTile, 2) k3_kernel(const K3Params P) {
+__global__ void __launch_bounds__(kThreads, 2) k3_kernel(const __grid_constant__ K3Params P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int tid = threadIdx.x, warp = tid >> 5;
-    uint8_t* p = smem + (size_t)kStages * P.slot_bytes;
-    uint32_t* s_bits = reinterpret_cast<uint32_t*>(p);                    // [word][thread]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // carve-up: A ring | B ring | BITS rows of the tile [word][query] | fan arena | nibble table | barriers
+    uint8_t* p = smem + (size_t)kStagesA * 2 * kABytes;
+    const uint32_t a_ring = smem_u32(smem), b_ring = smem_u32(p);
+    p += (size_t)kStagesB * P.b_slot_bytes;
+    uint32_t* s_bits = reinterpret_cast<uint32_t*>(p);
     p += (FMT == BC_DESC_BITS ? (size_t)P.bits_words * kTile * 4 : 0);
-    K3Edge* s_edges = reinterpret_cast<K3Edge*>(p);
-    p += (size_t)P.n_edges * sizeof(K3Edge);
+    float* s_fan = reinterpret_cast<float*>(p);
+    p += (size_t)P.fan_floats * 4;
+    float4* s_tab = reinterpret_cast<float4*>(p);   // nibble -> four 0/1 floats
+    p += 256;
     uint64_t* bars = reinterpret_cast<uint64_t*>(p);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
-    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kStages), dfull = smem_u32(bars + 2 * kStages);
-    const uint32_t slot0 = smem_u32(smem);
+    const uint32_t a_full0 = smem_u32(bars), a_empty0 = a_full0 + 8 * kStagesA, b_full0 = a_empty0 + 8 * kStagesA,
+                   b_empty0 = b_full0 + 8 * kStagesB, d_full0 = b_empty0 + 8 * kStagesB, d_empty0 = d_full0 + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStagesA + 2 * kStagesB + 4);
 
-    {   // edge table -> shared memory
-        const uint4* src = reinterpret_cast<const uint4*>(P.edges);
-        uint4* dst = reinterpret_cast<uint4*>(s_edges);
-        for (int i = tid; i < P.n_edges * 4; i += kTile) dst[i] = src[i];
+    {   // tables -> shared memory
+        for (int i = tid; i < P.fan_floats; i += kThreads) s_fan[i] = i < P.fan_n ? P.fan[i] : 0.f;
+        if (tid < 16) s_tab[tid] = make_float4(tid & 1 ? 1.f : 0.f, tid & 2 ? 1.f : 0.f, tid & 4 ? 1.f : 0.f, tid & 8 ? 1.f : 0.f);
     }
     if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) {
-            mbar_init(full0 + 8 * s, 1);
-            mbar_init(empty0 + 8 * s, 1);
+        for (int s = 0; s < kStagesA; ++s) {
+            mbar_init(a_full0 + 8 * s, kProducerWarps);
+            mbar_init(a_empty0 + 8 * s, 1);
         }
-        mbar_init(dfull, 1);
+        for (int s = 0; s < kStagesB; ++s) {
+            mbar_init(b_full0 + 8 * s, 1);
+            mbar_init(b_empty0 + 8 * s, 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(d_full0 + 8 * b, 1);
+            mbar_init(d_empty0 + 8 * b, kProducerWarps);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -211,162 +238,206 @@ __global__ void __launch_bounds__(kTile, 2) k3_kernel(const K3Params P) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
-    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);   // this warp's TMEM lane quarter
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform for the compiler: tcgen05 operands live in uniform registers
 
-    uint32_t it = 0;        // ring step counter (runs on across tiles)
-    uint32_t dphase = 0;
-    // B-operand prefetch cursor (thread 0): the step sequence (edge, block) repeats for every tile
-    int pf_e = 0, pf_kb = 0;
-    uint32_t pf_it = 0;
-    long long pf_tiles_left = 0;
-    for (long long t = blockIdx.x; t < P.n_tiles; t += gridDim.x) ++pf_tiles_left;
-    auto prefetch_one = [&]() {   // thread 0 only
-        if (pf_tiles_left == 0) return;
-        const K3Edge& E = s_edges[pf_e];
-        const uint32_t s = pf_it % kStages, par = (pf_it / kStages) & 1u;
-        mbar_wait(empty0 + 8 * s, par ^ 1u);
-        const unsigned bytes = (unsigned)E.n_pad * 128u;   // hi + lo, 64 B per row each
-        mbar_expect_tx(full0 + 8 * s, bytes);
-        tma_bulk_g2s(slot0 + s * P.slot_bytes + 2 * kABytes, P.bimg + E.bimg_off + (size_t)pf_kb * bytes, bytes, full0 + 8 * s);
-        ++pf_it;
-        if (++pf_kb == E.nkb) {
-            pf_kb = 0;
-            if (++pf_e == P.n_edges) {
-                pf_e = 0;
-                --pf_tiles_left;
-            }
+    if (warp == kProducerWarps + 1) {
+        // ================= TMA warp: keeps the B ring full; the (edge, block) sequence repeats for every tile
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x)
+                for (int e = 0; e < P.n_edges; ++e) {
+                    const K3Edge& E = P.edge[e];
+                    const unsigned bytes = (unsigned)E.n_pad * 128u;   // hi + lo, 64 B per row each
+                    for (int kb = 0; kb < E.nkb; ++kb, ++it) {
+                        const uint32_t s = it % kStagesB, par = (it / kStagesB) & 1u;
+                        mbar_wait(b_empty0 + 8 * s, par ^ 1u);
+                        mbar_expect_tx(b_full0 + 8 * s, bytes);
+                        tma_bulk_g2s(b_ring + s * P.b_slot_bytes, P.bimg + E.bimg_off + (size_t)kb * bytes, bytes, b_full0 + 8 * s);
+                    }
+                }
         }
-    };
-    if (tid == 0) prefetch_one();
-
-    for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-        const size_t q = (size_t)tile * kTile + tid;
-        const size_t qc = q < P.nq ? q : P.nq - 1;
-        const uint32_t fm = P.fan_mask ? P.fan_mask[qc] : 0u;
-        const float* drow = reinterpret_cast<const float*>(P.desc + qc * P.dstride);
-        if (FMT == BC_DESC_BITS) {
-            const uint32_t* grow = reinterpret_cast<const uint32_t*>(P.desc + qc * P.dstride);
-            for (int w4 = 0; w4 < P.bits_words; w4 += 4) {   // bits_words is a multiple of 4
-                const uint4 x = __ldg(reinterpret_cast<const uint4*>(grow + w4));
-                s_bits[(w4 + 0) * kTile + tid] = x.x;
-                s_bits[(w4 + 1) * kTile + tid] = x.y;
-                s_bits[(w4 + 2) * kTile + tid] = x.z;
-                s_bits[(w4 + 3) * kTile + tid] = x.w;
+    } else if (warp == kProducerWarps) {
+        // ================= MMA issuer warp: the whole warp runs the (uniform) loop, one elected lane issues
+        uint32_t it = 0, ed = 0;   // ring step, edge counter (D buffer = ed % n_dbuf)
+        const uint32_t desc_hi = (uint32_t)(512 >> 4) | (1u << 14) | (4u << 29);   // SBO, version 1, 64-byte swizzle
+        for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x)
+            for (int e = 0; e < P.n_edges; ++e, ++ed) {
+                const K3Edge& E = P.edge[e];
+                const bool a_exact = FMT == BC_DESC_BITS && E.col_v < 0 && !(E.fan_off >= 0 && P.fan_mask != nullptr);
+                const uint32_t db = P.n_dbuf == 2 ? (ed & 1u) : 0u, dpar = (P.n_dbuf == 2 ? (ed >> 1) : ed) & 1u;
+                const uint32_t d = tmem + (uint32_t)(P.d_col + (int)db * P.d_stride);
+                const uint32_t idesc = E.idesc, b_lo_off = (uint32_t)E.n_pad * 4u;   // n_pad * 64 B in 16-byte units
+                const int K = E.K, nkb = E.nkb;
+                mbar_wait(d_empty0 + 8 * db, dpar ^ 1u);   // the epilogue of the edge that used this accumulator is done
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const uint32_t sa = it % kStagesA, pa = (it / kStagesA) & 1u;
+                    const uint32_t sb = it % kStagesB, pb = (it / kStagesB) & 1u;
+                    // low words of the four operand descriptors: start address >> 4 | LBO = 1
+                    const uint32_t a_hi = (((a_ring + sa * 2 * kABytes) & 0x3FFFFu) >> 4) | (1u << 16), a_lo = a_hi + (kABytes >> 4);
+                    const uint32_t b_hi = (((b_ring + sb * P.b_slot_bytes) & 0x3FFFFu) >> 4) | (1u << 16), b_lo = b_hi + b_lo_off;
+                    const bool two = K - kb * kBK > 8;
+                    mbar_wait(b_full0 + 8 * sb, pb);
+                    mbar_wait(a_full0 + 8 * sa, pa);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        // error-compensated product, the small terms first; 8 TF32 = 32 bytes per k-step: +2 in the address field
+                        if (!a_exact) {
+                            umma_tf32(d, a_lo, b_hi, desc_hi, idesc, kb != 0);
+                            umma_tf32(d, a_hi, b_lo, desc_hi, idesc, 1);
+                            if (two) {
+                                umma_tf32(d, a_lo + 2, b_hi + 2, desc_hi, idesc, 1);
+                                umma_tf32(d, a_hi + 2, b_lo + 2, desc_hi, idesc, 1);
+                            }
+                        } else {
+                            umma_tf32(d, a_hi, b_lo, desc_hi, idesc, kb != 0);
+                            if (two) umma_tf32(d, a_hi + 2, b_lo + 2, desc_hi, idesc, 1);
+                        }
+                        umma_tf32(d, a_hi, b_hi, desc_hi, idesc, 1);
+                        if (two) umma_tf32(d, a_hi + 2, b_hi + 2, desc_hi, idesc, 1);
+                        umma_commit(a_empty0 + 8 * sa);
+                        umma_commit(b_empty0 + 8 * sb);
+                        if (kb == nkb - 1) umma_commit(d_full0 + 8 * db);
+                    }
+                    __syncwarp();
+                }
             }
-        }
+    } else {
+        // ================= producer / epilogue warps: thread = query = TMEM lane
+        const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+        const uint32_t sw = ((uint32_t)tid >> 1) & 3u;    // 64-byte swizzle: chunk j of row r lives at r * 64 + ((j ^ ((r >> 1) & 3)) << 4)
         const uint32_t* my_bits = s_bits + tid;
+        uint32_t it = 0, ed = 0;
+        for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+            const size_t q = (size_t)tile * kTile + tid;
+            const size_t qc = q < P.nq ? q : P.nq - 1;
+            const uint32_t fm = P.fan_mask ? P.fan_mask[qc] : 0u;
+            const float* drow = reinterpret_cast<const float*>(P.desc + qc * P.dstride);
+            if (FMT == BC_DESC_BITS) {
+                const uint32_t* grow = reinterpret_cast<const uint32_t*>(P.desc + qc * P.dstride);
+                for (int w4 = 0; w4 < P.bits_words; w4 += 4) {   // bits_words is a multiple of 4
+                    const uint4 x = __ldg(reinterpret_cast<const uint4*>(grow + w4));
+                    s_bits[(w4 + 0) * kTile + tid] = x.x;
+                    s_bits[(w4 + 1) * kTile + tid] = x.y;
+                    s_bits[(w4 + 2) * kTile + tid] = x.z;
+                    s_bits[(w4 + 3) * kTile + tid] = x.w;
+                }
+            }
+            for (int e = 0; e < P.n_edges; ++e, ++ed) {
+                const K3Edge& E = P.edge[e];
+                const bool leaf = E.col_v < 0;
+                const bool fan_on = E.fan_off >= 0 && ((fm >> E.v) & 1u);
+                const bool a_exact = FMT == BC_DESC_BITS && leaf && !(E.fan_off >= 0 && P.fan_mask != nullptr);
+                for (int kb = 0; kb < E.nkb; ++kb, ++it) {
+                    const uint32_t sa = it % kStagesA, pa = (it / kStagesA) & 1u;
+                    const uint32_t row = a_ring + sa * 2 * kABytes + (uint32_t)tid * 64u;
+                    const int c0 = kb * kBK;
+                    const int ks = (E.K - c0 > 8) ? 2 : 1;
+                    if (a_exact) {
+                        // unit weights on a leaf: U is a 0/1 matrix, exact in TF32 -- four states per table lookup, no lo half
+                        const uint32_t m = bits16(my_bits, P.bits_words, E.bit_off, E.K, c0);
+                        mbar_wait(a_empty0 + 8 * sa, pa ^ 1u);   // the MMAs that read this slot are done
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (j < 2 * ks) {
+                                const float4 t = s_tab[(m >> (4 * j)) & 15u];
+                                sts128(row + (((uint32_t)j ^ sw) << 4), t.x, t.y, t.z, t.w);
+                            }
+                    } else {
+                        float u[16];
+                        if (FMT == BC_DESC_BITS) {
+                            const uint32_t m = bits16(my_bits, P.bits_words, E.bit_off, E.K, c0);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) u[j] = ((m >> j) & 1u) ? 1.f : 0.f;
+                        } else {
+                            const float4* src = reinterpret_cast<const float4*>(drow + E.lam_off + c0);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (c0 + 4 * j < E.K) t = __ldg(src + j);
+                                u[4 * j] = t.x; u[4 * j + 1] = t.y; u[4 * j + 2] = t.z; u[4 * j + 3] = t.w;
+                            }
+                        }
+                        if (fan_on) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                if (c0 + 4 * j < E.K) {
+                                    const float4 f = *reinterpret_cast<const float4*>(s_fan + E.fan_off + c0 + 4 * j);
+                                    u[4 * j] *= f.x; u[4 * j + 1] *= f.y; u[4 * j + 2] *= f.z; u[4 * j + 3] *= f.w;
+                                }
+                        }
+                        if (!leaf) {
+                            float lv[16];
+                            tmem_ld8(tlane + (uint32_t)(E.col_v + c0), lv);
+                            if (ks == 2) tmem_ld8(tlane + (uint32_t)(E.col_v + c0 + 8), lv + 8);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) u[j] *= lv[j];
+                        }
+                        if (c0 + kBK > E.K) {   // last block: states >= K must be exact zeros (stale Lambda columns, row padding)
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (c0 + j >= E.K) u[j] = 0.f;
+                        }
+                        mbar_wait(a_empty0 + 8 * sa, pa ^ 1u);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (j < 2 * ks) {
+                                float h[4], l[4];
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) split_tf32(u[4 * j + i], h[i], l[i]);
+                                const uint32_t a = row + (((uint32_t)j ^ sw) << 4);
+                                sts128(a, h[0], h[1], h[2], h[3]);
+                                sts128(a + kABytes, l[0], l[1], l[2], l[3]);
+                            }
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(a_full0 + 8 * sa);
+                }
+                // ---- epilogue: Lambda_pa (*)= D, all in tensor memory
+                const uint32_t db = P.n_dbuf == 2 ? (ed & 1u) : 0u, dpar = (P.n_dbuf == 2 ? (ed >> 1) : ed) & 1u;
+                const uint32_t dcol = tlane + (uint32_t)(P.d_col + (int)db * P.d_stride), pcol = tlane + (uint32_t)E.col_pa;
+                mbar_wait(d_full0 + 8 * db, dpar);
+                tc_fence_after();
+                const int n8 = (E.N + 7) & ~7;
+                for (int j = 0; j < n8; j += 16) {
+                    float dv[16], lv[16];
+                    const bool two = j + 8 < n8;
+                    tmem_ld8(dcol + (uint32_t)j, dv);
+                    if (two) tmem_ld8(dcol + (uint32_t)(j + 8), dv + 8);
+                    if (!E.first) {
+                        tmem_ld8(pcol + (uint32_t)j, lv);
+                        if (two) tmem_ld8(pcol + (uint32_t)(j + 8), lv + 8);
+                    }
+                    tmem_ld_wait();
+                    if (!E.first) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) dv[i] *= lv[i];
+                    }
+                    tmem_st8(pcol + (uint32_t)j, dv);
+                    if (two) tmem_st8(pcol + (uint32_t)(j + 8), dv + 8);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(d_empty0 + 8 * db);   // the accumulator may be overwritten
+                tmem_st_wait();
+            }
 
-        for (int e = 0; e < P.n_edges; ++e) {
-            const K3Edge E = s_edges[e];
-            const bool a_exact = FMT == BC_DESC_BITS && E.col_v < 0 && !(E.fan_off >= 0 && P.fan_mask != nullptr);
-            for (int kb = 0; kb < E.nkb; ++kb, ++it) {
-                const uint32_t s = it % kStages, par = (it / kStages) & 1u;
-                const uint32_t slot = slot0 + s * P.slot_bytes;
-                if (tid == 0) prefetch_one();                 // B of the NEXT step
-                mbar_wait(empty0 + 8 * s, par ^ 1u);           // the MMAs that read this slot's A are done
-                // ---- build 16 states of U_v = w_v (*) Lambda_v for this thread's query
-                const int c0 = kb * kBK;
-                const int ks = (E.K - c0 > 8) ? 2 : 1;         // k-steps of 8 in this block
-                float u[16];
-                if (E.col_v >= 0) {
-                    tmem_ld8(tlane + (uint32_t)(E.col_v + c0), u);
-                    if (ks == 2) tmem_ld8(tlane + (uint32_t)(E.col_v + c0 + 8), u + 8);
+            // ---- root: sum_c w_0[c] * Lambda_0[c] * T_0[c]
+            float res = 0.f;
+            for (int c0 = 0; c0 < P.root_card; c0 += 8) {
+                float lv[8], w[8];
+                if (P.root_has_children) {
+                    tmem_ld8(tlane + (uint32_t)(P.root_col + c0), lv);
                     tmem_ld_wait();
                 }
-                {
-                    float w[8];
-                    load_weights8<FMT>(P, my_bits, drow, fm, E.v, E.lam_off, E.bit_off, E.fan_off, E.K, c0, w);
+                load_weights8<FMT>(my_bits, P.bits_words, drow, s_fan, fm, 0, P.root_lam_off, P.root_bit_off, P.root_fan_off, P.root_card, c0, w);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) u[j] = E.col_v >= 0 ? u[j] * w[j] : w[j];
-                    if (ks == 2) {
-                        load_weights8<FMT>(P, my_bits, drow, fm, E.v, E.lam_off, E.bit_off, E.fan_off, E.K, c0 + 8, w);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) u[8 + j] = E.col_v >= 0 ? u[8 + j] * w[j] : w[j];
-                    }
-                }
-                // states >= K inside the last k-step must be exact zeros (Lambda columns there are stale)
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (c0 + j >= E.K) u[j] = 0.f;
-                // 64-byte swizzle: 16-byte chunk j of row r lives at r * 64 + ((j ^ ((r >> 1) & 3)) << 4)
-                const uint32_t row = slot + (uint32_t)tid * 64u;
-                const uint32_t sw = ((uint32_t)tid >> 1) & 3u;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (j < 2 * ks) {
-                        float h[4], l[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) split_tf32(u[4 * j + i], h[i], l[i]);
-                        const uint32_t a = row + (((uint32_t)j ^ sw) << 4);
-                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(h[0]), "f"(h[1]), "f"(h[2]), "f"(h[3]) : "memory");
-                        if (!a_exact)
-                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a + kABytes), "f"(l[0]), "f"(l[1]), "f"(l[2]), "f"(l[3]) : "memory");
-                    }
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
-                tc_fence_before();
-                __syncthreads();
-                if (tid == 0) {
-                    mbar_wait(full0 + 8 * s, par);   // T_v^T block has landed
-                    tc_fence_after();
-                    const uint64_t a_hi = umma_desc64(slot), a_lo = umma_desc64(slot + kABytes);
-                    const uint64_t b_hi = umma_desc64(slot + 2 * kABytes), b_lo = umma_desc64(slot + 2 * kABytes + (uint32_t)E.n_pad * 64u);
-                    const uint32_t d = tmem + (uint32_t)P.d_col;
-                    uint32_t acc = kb != 0;
-                    for (int kk = 0; kk < ks; ++kk) {   // 8 TF32 = 32 bytes per k-step: +2 in the 16-byte address field
-                        const uint64_t o = (uint64_t)(kk * 2);
-                        if (!a_exact) {
-                            umma_tf32(d, a_lo + o, b_hi + o, E.idesc, acc);
-                            acc = 1;
-                        }
-                        umma_tf32(d, a_hi + o, b_lo + o, E.idesc, acc);
-                        acc = 1;
-                    }
-                    for (int kk = 0; kk < ks; ++kk) {
-                        const uint64_t o = (uint64_t)(kk * 2);
-                        umma_tf32(d, a_hi + o, b_hi + o, E.idesc, 1);
-                    }
-                    umma_commit(empty0 + 8 * s);
-                    if (kb == E.nkb - 1) umma_commit(dfull);
-                }
+                for (int j = 0; j < 8; ++j)
+                    if (c0 + j < P.root_card) res = fmaf(P.root_has_children ? lv[j] * w[j] : w[j], __ldg(P.root_T + c0 + j), res);
             }
-            // ---- epilogue: Lambda_pa (*)= D, all in tensor memory
-            mbar_wait(dfull, dphase);
-            dphase ^= 1u;
-            tc_fence_after();
-            const int n8 = (E.N + 7) & ~7;
-            for (int j = 0; j < n8; j += 8) {
-                float dv[8], lv[8];
-                tmem_ld8(tlane + (uint32_t)(P.d_col + j), dv);
-                if (!E.first) tmem_ld8(tlane + (uint32_t)(E.col_pa + j), lv);
-                tmem_ld_wait();
-                if (!E.first) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) dv[i] *= lv[i];
-                }
-                tmem_st8(tlane + (uint32_t)(E.col_pa + j), dv);
-            }
-            tmem_st_wait();
-            tc_fence_before();   // ordered before the __syncthreads that precedes the next MMA into D
+            if (q < P.nq) P.out[q] = res;
         }
-
-        // ---- root: sum_c w_0[c] * Lambda_0[c] * T_0[c]
-        float res = 0.f;
-        for (int c0 = 0; c0 < P.root_card; c0 += 8) {
-            float lv[8], w[8];
-            if (P.root_has_children) {
-                tmem_ld8(tlane + (uint32_t)(P.root_col + c0), lv);
-                tmem_ld_wait();
-            }
-            load_weights8<FMT>(P, my_bits, drow, fm, 0, P.root_lam_off, P.root_bit_off, P.root_fan_off, P.root_card, c0, w);
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (c0 + j < P.root_card) res = fmaf(P.root_has_children ? lv[j] * w[j] : w[j], __ldg(P.root_T + c0 + j), res);
-        }
-        if (q < P.nq) P.out[q] = res;
-        tc_fence_before();
-        __syncthreads();   // s_bits and the root's TMEM columns are rewritten by the next tile
     }
 
     tc_fence_before();
@@ -410,38 +481,56 @@ int k3_prepare(bc_model* m) {
         if (np > 256) return fail("a parent domain exceeds 256 states");
         if (np > npad_max) npad_max = np;
     }
-    // ---- TMEM columns: accumulator D first, then Lambda of every internal node by first fit over lifetimes
-    //      [edge of its first child, its own edge] (the root lives to the end), in units of 8 columns
-    const int units_total = 512 / 8;
-    std::vector<int> busy_until(units_total, -1);   // last edge index that uses the unit
-    const int d_units = npad_max / 8;
-    for (int u = 0; u < d_units; ++u) busy_until[u] = 1 << 30;
+    // ---- TMEM columns: accumulator buffer(s) D first, then Lambda of every internal node by first fit over lifetimes
+    //      [edge of its first child, its own edge] (the root lives to the end), in units of 8 columns.  Two accumulator
+    //      buffers let the MMAs of the next edge start while the epilogue of this one runs; one buffer if that is
+    //      what keeps a tile within 256 columns (two CTAs per SM).
     std::vector<int> col(n, -1);
-    int units_used = d_units;
     std::vector<int> order;   // internal nodes by start of lifetime
     for (int v = 0; v < n; ++v)
         if (first_child_edge[v] >= 0) order.push_back(v);
     std::sort(order.begin(), order.end(), [&](int a, int b) { return first_child_edge[a] < first_child_edge[b]; });
-    for (int v : order) {
-        const int need = (int)bc_round_up(m->nodes[v].card, 8) / 8;
-        const int start = first_child_edge[v], end = v == 0 ? (1 << 30) : own_edge[v];
-        int at = -1;
-        for (int u0 = 0; u0 + need <= units_total && at < 0; ++u0) {
-            bool ok = true;
-            for (int u = u0; u < u0 + need; ++u)
-                if (busy_until[u] >= start) { ok = false; break; }
-            if (ok) at = u0;
+    auto assign = [&](int n_dbuf) -> int {   // columns used, or -1
+        const int units_total = 512 / 8;
+        std::vector<int> busy_until(units_total, -1);   // last edge index that uses the unit
+        const int d_units = n_dbuf * npad_max / 8;
+        if (d_units > units_total) return -1;
+        for (int u = 0; u < d_units; ++u) busy_until[u] = 1 << 30;
+        int units_used = d_units;
+        for (int v : order) {
+            const int need = (int)bc_round_up(m->nodes[v].card, 8) / 8;
+            const int start = first_child_edge[v], end = v == 0 ? (1 << 30) : own_edge[v];
+            int at = -1;
+            for (int u0 = 0; u0 + need <= units_total && at < 0; ++u0) {
+                bool ok = true;
+                for (int u = u0; u < u0 + need; ++u)
+                    if (busy_until[u] >= start) { ok = false; break; }
+                if (ok) at = u0;
+            }
+            if (at < 0) return -1;
+            for (int u = at; u < at + need; ++u) busy_until[u] = end;
+            col[v] = at * 8;
+            if (at + need > units_used) units_used = at + need;
         }
-        if (at < 0) return fail("live messages exceed the 512 columns of tensor memory");
-        for (int u = at; u < at + need; ++u) busy_until[u] = end;
-        col[v] = at * 8;
-        if (at + need > units_used) units_used = at + need;
+        return units_used * 8;
+    };
+    int n_dbuf = 2, used = assign(2);
+    if (used < 0 || used > 256) {
+        const int used1 = assign(1);
+        if (used1 < 0) return fail("live messages exceed the 512 columns of tensor memory");
+        if (used1 <= 256 || used < 0) { n_dbuf = 1; used = used1; }
+        else used = assign(2);
+    }
+    if (const char* e = std::getenv("BC_K3_DBUF")) {   // experiments
+        const int want = std::atoi(e);
+        if ((want == 1 || want == 2) && assign(want) > 0) { n_dbuf = want; used = assign(want); }
     }
     int tmem_cols = 32;
-    while (tmem_cols < units_used * 8) tmem_cols <<= 1;
+    while (tmem_cols < used) tmem_cols <<= 1;
     k->tmem_cols = tmem_cols;
     k->npad_max = npad_max;
     k->d_col = 0;
+    k->n_dbuf = n_dbuf;
     k->root_col = col[0];
     // ---- operand images: per edge and block of 16 child states, T_v^T hi then lo, 64-byte swizzled rows
     size_t total = 0;
@@ -490,14 +579,12 @@ int k3_prepare(bc_model* m) {
     }
     k->bimg_bytes = total;
     // ---- shared memory / residency
-    const size_t slot = 2 * kABytes + (size_t)npad_max * 128;
-    const size_t fixed = (size_t)m->bits_words * kTile * 4 + (size_t)n_edges * sizeof(K3Edge) + 128 /* barriers */ + 1024 /* alignment */;
-    k->smem = kStages * slot + fixed;
-    if (k->smem > (size_t)m->smem_optin) return fail("ring slots exceed shared memory");
+    const size_t fan_floats = (size_t)bc_round_up((int64_t)m->fan.size(), 4);
+    const size_t fixed = (size_t)m->bits_words * kTile * 4 + fan_floats * 4 + 256 /* nibble table */ +                          256 /* barriers */ + 1024 /* alignment */;
+    k->smem = (size_t)kStagesA * 2 * kABytes + (size_t)kStagesB * npad_max * 128 + fixed;
+    if (k->smem > (size_t)m->smem_optin) return fail("operand rings exceed shared memory");
     k->ctas_per_sm = (tmem_cols <= 256 && 2 * (k->smem + 1024) <= 228 * 1024) ? 2 : 1;
     if (k->ctas_per_sm == 1) k->smem = (size_t)m->smem_optin;   // a second CTA would only spin in tcgen05.alloc
-    BC_CUDA_CHECK(cudaMalloc(&k->d_edges, sizeof(K3Edge) * n_edges));
-    BC_CUDA_CHECK(cudaMemcpy(k->d_edges, k->edges.data(), sizeof(K3Edge) * n_edges, cudaMemcpyHostToDevice));
     BC_CUDA_CHECK(cudaMalloc(&k->d_bimg, total));
     BC_CUDA_CHECK(cudaMemcpy(k->d_bimg, img.data(), total, cudaMemcpyHostToDevice));
     return BC_OK;
@@ -512,7 +599,7 @@ int k3_launch_fmt(bc_model* m, const K3Params& P, int grid, cudaStream_t st) {
         BC_CUDA_CHECK(cudaFuncSetAttribute(k3_kernel<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_optin));
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
-    k3_kernel<FMT><<<grid, kTile, m->k3->smem, st>>>(P);
+    k3_kernel<FMT><<<grid, kThreads, m->k3->smem, st>>>(P);
     BC_CUDA_CHECK(cudaGetLastError());
     bc_count_launch();
     return BC_OK;
@@ -533,13 +620,15 @@ int bc_k3_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32
     }
     const BcK3Plan* k = m->k3;
     K3Params P{};
-    P.edges = k->d_edges;
     P.n_edges = (int)k->edges.size();
+    std::memcpy(P.edge, k->edges.data(), sizeof(K3Edge) * k->edges.size());
     P.bimg = k->d_bimg;
     P.desc = static_cast<const uint8_t*>(desc);
     P.dstride = (size_t)bc_model_desc_stride(m, fmt);
     P.fan_mask = fan_mask;
     P.fan = m->d_fan;
+    P.fan_floats = (int)bc_round_up((int64_t)m->fan.size(), 4);
+    P.fan_n = (int)m->fan.size();
     const BcNodeRec& r = m->nodes[0];
     P.root_T = m->d_arena + r.cpt_off;
     P.root_card = r.card;
@@ -552,8 +641,10 @@ int bc_k3_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32
     P.nq = nq;
     P.n_tiles = (long long)((nq + kTile - 1) / kTile);
     P.bits_words = m->bits_words;
-    P.slot_bytes = 2 * kABytes + k->npad_max * 128;
+    P.b_slot_bytes = k->npad_max * 128;
     P.d_col = k->d_col;
+    P.d_stride = k->npad_max;
+    P.n_dbuf = k->n_dbuf;
     P.tmem_cols = k->tmem_cols;
     long long grid = (long long)m->sm_count * k->ctas_per_sm;
     if (grid > P.n_tiles) grid = P.n_tiles;
@@ -563,7 +654,6 @@ int bc_k3_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32
 
 void bc_k3_free(bc_model* m) {
     if (!m->k3) return;
-    cudaFree(m->k3->d_edges);
     cudaFree(m->k3->d_bimg);
     delete m->k3;
     m->k3 = nullptr;
