@@ -117,18 +117,23 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, unsi
                  : "memory");
 }
 // K-major operands, 64-byte swizzle: rows of 64 B, 8-row groups 512 B apart (SBO), layout type 4, version 1 (sm_100).
-// descriptors as 32-bit halves: the high word (SBO, version, swizzle mode) is the same for every operand
+// descriptors as 32-bit halves: the high word (SBO, version, swizzle mode) is the same for every operand.  Called by the
+// WHOLE (converged) issuer warp; elect.sync inside picks the lane, so ptxas keeps every operand in uniform registers
+// instead of wrapping each instruction in a divergence (ELECT / R2UR / BRA.U.ANY) loop.
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint32_t a_lo32, uint32_t b_lo32, uint32_t desc_hi32, uint32_t idesc,
                                           uint32_t accumulate) {
     asm volatile(
-        "{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %5, 0;\n"
+        "{\n.reg .pred p, q;\n.reg .b64 da, db;\nelect.sync _|q, 0xffffffff;\nsetp.ne.b32 p, %5, 0;\n"
         "mov.b64 da, {%1, %3};\nmov.b64 db, {%2, %3};\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n}\n" ::"r"(tmem_c),
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n}\n" ::"r"(tmem_c),
         "r"(a_lo32), "r"(b_lo32), "r"(desc_hi32), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+__device__ __forceinline__ void umma_commit(uint32_t bar) {   // whole warp, one elected lane
+    asm volatile(
+        "{\n.reg .pred q;\nelect.sync _|q, 0xffffffff;\n"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n" ::"r"(bar)
+        : "memory");
 }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
     uint32_t* r = reinterpret_cast<uint32_t*>(v);
@@ -195,7 +200,8 @@ template <int FMT>
 __global__ void __launch_bounds__(kThreads, 2) k3_kernel(const __grid_constant__ K3Params P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler (role dispatch without divergence)
     // carve-up: A ring | B ring | BITS rows of the tile [word][query] | fan arena | nibble table | barriers
     uint8_t* p = smem + (size_t)kStagesA * 2 * kABytes;
     const uint32_t a_ring = smem_u32(smem), b_ring = smem_u32(p);
@@ -279,7 +285,7 @@ __global__ void __launch_bounds__(kThreads, 2) k3_kernel(const __grid_constant__
                     mbar_wait(b_full0 + 8 * sb, pb);
                     mbar_wait(a_full0 + 8 * sa, pa);
                     tc_fence_after();
-                    if (lane == 0) {
+                    {
                         // error-compensated product, the small terms first; 8 TF32 = 32 bytes per k-step: +2 in the address field
                         if (!a_exact) {
                             umma_tf32(d, a_lo, b_hi, desc_hi, idesc, kb != 0);
@@ -298,7 +304,6 @@ __global__ void __launch_bounds__(kThreads, 2) k3_kernel(const __grid_constant__
                         umma_commit(b_empty0 + 8 * sb);
                         if (kb == nkb - 1) umma_commit(d_full0 + 8 * db);
                     }
-                    __syncwarp();
                 }
             }
     } else {
@@ -322,49 +327,68 @@ __global__ void __launch_bounds__(kThreads, 2) k3_kernel(const __grid_constant__
                     s_bits[(w4 + 3) * kTile + tid] = x.w;
                 }
             }
+            // Inputs of ring step (e, kb) that do not depend on any message: for unit-weight leaves the finished hi chunks
+            // (0/1 floats from the nibble table), otherwise the weights w_v[c0 .. c0 + 16) (x fan-out).  They are fetched ONE
+            // STEP AHEAD (also across edges), so the LDS / LDG latency overlaps the previous block's stores and barriers.
+            auto fetch = [&](int e, int kb, float* pre) __attribute__((always_inline)) {
+                const K3Edge& E = P.edge[e];
+                const int c0 = kb * kBK;
+                const bool exact = FMT == BC_DESC_BITS && E.col_v < 0 && !(E.fan_off >= 0 && P.fan_mask != nullptr);
+                if (FMT == BC_DESC_BITS) {
+                    const uint32_t m = bits16(my_bits, P.bits_words, E.bit_off, E.K, c0);
+                    if (exact) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 t = s_tab[(m >> (4 * j)) & 15u];
+                            pre[4 * j] = t.x; pre[4 * j + 1] = t.y; pre[4 * j + 2] = t.z; pre[4 * j + 3] = t.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) pre[j] = ((m >> j) & 1u) ? 1.f : 0.f;
+                    }
+                } else {
+                    const float4* src = reinterpret_cast<const float4*>(drow + E.lam_off + c0);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (c0 + 4 * j < E.K) t = __ldg(src + j);
+                        pre[4 * j] = t.x; pre[4 * j + 1] = t.y; pre[4 * j + 2] = t.z; pre[4 * j + 3] = t.w;
+                    }
+                }
+                if (E.fan_off >= 0 && ((fm >> E.v) & 1u)) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (c0 + 4 * j < E.K) {
+                            const float4 f = *reinterpret_cast<const float4*>(s_fan + E.fan_off + c0 + 4 * j);
+                            pre[4 * j] *= f.x; pre[4 * j + 1] *= f.y; pre[4 * j + 2] *= f.z; pre[4 * j + 3] *= f.w;
+                        }
+                }
+            };
+            float pre[16];
+            fetch(0, 0, pre);
             for (int e = 0; e < P.n_edges; ++e, ++ed) {
                 const K3Edge& E = P.edge[e];
                 const bool leaf = E.col_v < 0;
-                const bool fan_on = E.fan_off >= 0 && ((fm >> E.v) & 1u);
                 const bool a_exact = FMT == BC_DESC_BITS && leaf && !(E.fan_off >= 0 && P.fan_mask != nullptr);
-                for (int kb = 0; kb < E.nkb; ++kb, ++it) {
+                const int K = E.K, nkb = E.nkb;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const uint32_t sa = it % kStagesA, pa = (it / kStagesA) & 1u;
                     const uint32_t row = a_ring + sa * 2 * kABytes + (uint32_t)tid * 64u;
                     const int c0 = kb * kBK;
-                    const int ks = (E.K - c0 > 8) ? 2 : 1;
+                    const int ks = (K - c0 > 8) ? 2 : 1;
+                    float u[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) u[j] = pre[j];
+                    // next step's inputs
+                    if (kb + 1 < nkb) fetch(e, kb + 1, pre);
+                    else if (e + 1 < P.n_edges) fetch(e + 1, 0, pre);
                     if (a_exact) {
-                        // unit weights on a leaf: U is a 0/1 matrix, exact in TF32 -- four states per table lookup, no lo half
-                        const uint32_t m = bits16(my_bits, P.bits_words, E.bit_off, E.K, c0);
+                        // unit weights on a leaf: U is a 0/1 matrix, exact in TF32 -- no lo half
                         mbar_wait(a_empty0 + 8 * sa, pa ^ 1u);   // the MMAs that read this slot are done
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
-                            if (j < 2 * ks) {
-                                const float4 t = s_tab[(m >> (4 * j)) & 15u];
-                                sts128(row + (((uint32_t)j ^ sw) << 4), t.x, t.y, t.z, t.w);
-                            }
+                            if (j < 2 * ks) sts128(row + (((uint32_t)j ^ sw) << 4), u[4 * j], u[4 * j + 1], u[4 * j + 2], u[4 * j + 3]);
                     } else {
-                        float u[16];
-                        if (FMT == BC_DESC_BITS) {
-                            const uint32_t m = bits16(my_bits, P.bits_words, E.bit_off, E.K, c0);
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) u[j] = ((m >> j) & 1u) ? 1.f : 0.f;
-                        } else {
-                            const float4* src = reinterpret_cast<const float4*>(drow + E.lam_off + c0);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                                if (c0 + 4 * j < E.K) t = __ldg(src + j);
-                                u[4 * j] = t.x; u[4 * j + 1] = t.y; u[4 * j + 2] = t.z; u[4 * j + 3] = t.w;
-                            }
-                        }
-                        if (fan_on) {
-#pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                if (c0 + 4 * j < E.K) {
-                                    const float4 f = *reinterpret_cast<const float4*>(s_fan + E.fan_off + c0 + 4 * j);
-                                    u[4 * j] *= f.x; u[4 * j + 1] *= f.y; u[4 * j + 2] *= f.z; u[4 * j + 3] *= f.w;
-                                }
-                        }
                         if (!leaf) {
                             float lv[16];
                             tmem_ld8(tlane + (uint32_t)(E.col_v + c0), lv);
@@ -373,49 +397,50 @@ __global__ void __launch_bounds__(kThreads, 2) k3_kernel(const __grid_constant__
 #pragma unroll
                             for (int j = 0; j < 16; ++j) u[j] *= lv[j];
                         }
-                        if (c0 + kBK > E.K) {   // last block: states >= K must be exact zeros (stale Lambda columns, row padding)
+                        if (c0 + kBK > K) {   // last block: states >= K must be exact zeros (stale Lambda columns, row padding)
 #pragma unroll
                             for (int j = 0; j < 16; ++j)
-                                if (c0 + j >= E.K) u[j] = 0.f;
+                                if (c0 + j >= K) u[j] = 0.f;
                         }
+                        float h[16], l[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) split_tf32(u[j], h[j], l[j]);
                         mbar_wait(a_empty0 + 8 * sa, pa ^ 1u);
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
                             if (j < 2 * ks) {
-                                float h[4], l[4];
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) split_tf32(u[4 * j + i], h[i], l[i]);
                                 const uint32_t a = row + (((uint32_t)j ^ sw) << 4);
-                                sts128(a, h[0], h[1], h[2], h[3]);
-                                sts128(a + kABytes, l[0], l[1], l[2], l[3]);
+                                sts128(a, h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+                                sts128(a + kABytes, l[4 * j], l[4 * j + 1], l[4 * j + 2], l[4 * j + 3]);
                             }
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
                     __syncwarp();
                     if (lane == 0) mbar_arrive(a_full0 + 8 * sa);
                 }
-                // ---- epilogue: Lambda_pa (*)= D, all in tensor memory
+                // ---- epilogue: Lambda_pa (*)= D, all in tensor memory, 32 columns per round trip
                 const uint32_t db = P.n_dbuf == 2 ? (ed & 1u) : 0u, dpar = (P.n_dbuf == 2 ? (ed >> 1) : ed) & 1u;
                 const uint32_t dcol = tlane + (uint32_t)(P.d_col + (int)db * P.d_stride), pcol = tlane + (uint32_t)E.col_pa;
+                const bool first = E.first;
                 mbar_wait(d_full0 + 8 * db, dpar);
                 tc_fence_after();
                 const int n8 = (E.N + 7) & ~7;
-                for (int j = 0; j < n8; j += 16) {
-                    float dv[16], lv[16];
-                    const bool two = j + 8 < n8;
-                    tmem_ld8(dcol + (uint32_t)j, dv);
-                    if (two) tmem_ld8(dcol + (uint32_t)(j + 8), dv + 8);
-                    if (!E.first) {
-                        tmem_ld8(pcol + (uint32_t)j, lv);
-                        if (two) tmem_ld8(pcol + (uint32_t)(j + 8), lv + 8);
-                    }
-                    tmem_ld_wait();
-                    if (!E.first) {
+                for (int j = 0; j < n8; j += 32) {
+                    float dv[32], lv[32];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) dv[i] *= lv[i];
+                    for (int c = 0; c < 4; ++c)
+                        if (j + 8 * c < n8) {
+                            tmem_ld8(dcol + (uint32_t)(j + 8 * c), dv + 8 * c);
+                            if (!first) tmem_ld8(pcol + (uint32_t)(j + 8 * c), lv + 8 * c);
+                        }
+                    tmem_ld_wait();
+                    if (!first) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) dv[i] *= lv[i];
                     }
-                    tmem_st8(pcol + (uint32_t)j, dv);
-                    if (two) tmem_st8(pcol + (uint32_t)(j + 8), dv + 8);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (j + 8 * c < n8) tmem_st8(pcol + (uint32_t)(j + 8 * c), dv + 8 * c);
                 }
                 tc_fence_before();
                 __syncwarp();
