@@ -286,6 +286,12 @@ extern "C" int bc_query_batch(bc_model* m, const void* desc, size_t nq, int fmt,
     const bool spec_direct = (fmt == BC_DESC_RANGE_U8 && m->spec_range8) || (fmt == BC_DESC_DENSE_F32 && m->spec_dense) ||
                              (fmt == BC_DESC_BITS && m->spec_bits);
     const bool spec_via_bits = is_range && !spec_direct && m->spec_bits;
+    // AUTO: models whose straight-line code outgrows the instruction caches (IMDB: > 20k CPT entries) are faster on the
+    // fused tensor-core kernel in every format (profiles/r1_k3_*.txt); it declines (BC_ELIMIT) what it cannot serve
+    if (kernel == BC_KERNEL_AUTO && m->flops_dense >= 30000 && m->n <= 32 && m->max_card <= 256) {
+        rc = bc_query_batch(m, desc, nq, fmt, fan_mask, out, BC_KERNEL_FUSED, stream);
+        if (rc != BC_ELIMIT) return rc;
+    }
     if (kernel == BC_KERNEL_SPEC && !spec_direct && !spec_via_bits) {
         bc_set_error("no specialised kernel attached for this model / format (call bc_model_specialize)");
         return BC_ECOMPILE;

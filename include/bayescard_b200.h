@@ -78,7 +78,8 @@ extern "C" {
 #define BC_DESC_BITS 3
 
 /* ---- kernel selection ------------------------------------------------------------------------- */
-#define BC_KERNEL_AUTO 0     /* specialised kernel if the model has one, else generic        */
+#define BC_KERNEL_AUTO 0     /* fused tensor-core kernel for models of > 15k CPT entries, else the
+                                specialised kernel if the model has one, else generic        */
 #define BC_KERNEL_GENERIC 1  /* K1: warp per query, CPT arena staged in shared memory by TMA  */
 #define BC_KERNEL_SPEC 2     /* K-spec: per-model straight-line kernel, thread per query      */
 #define BC_KERNEL_GEMM 3     /* K2: per-edge batched path for large domains, tcgen05 3xTF32 GEMM

@@ -62,6 +62,77 @@ def test_infer_cases_both_kernels(name, kernel):
         assert_close(got, ref, (name, kernel, force_dense))
 
 
+FUSED_MODELS = [n for n in G.MODEL_NAMES if n != "census"]  # K3 serves models of <= 32 columns
+
+
+@pytest.mark.parametrize("name", FUSED_MODELS)
+def test_infer_cases_fused_kernel(name):
+    """K3 (whole tree per 128-query tile on the tensor cores, 3xTF32): the golden query / expectation cases of the
+    unmodified reference through BITS rows, DENSE_F32 rows and the fan-out mask."""
+    m, dm = G.model(name), dev_model(name)
+    pc = PredicateCompiler(m)
+    cases = [r for r in G.load("infer_cases.json.gz")[name] if "error" not in r]
+    decoded = [({k: list(v) for k, v in r["bins"].items()}, {k: np.asarray(v) for k, v in r["weights"].items()})
+               for r in cases]
+    ref = np.asarray([np.asarray(r["p"]["value"]).reshape(-1)[0] for r in cases])
+    for force_dense in (False, True):
+        r_idx, r_desc, d_idx, d_desc, mask = pc.pack(decoded, [r["fanout"] for r in cases], force_dense=force_dense)
+        got = np.zeros(len(cases))
+        before = launch_count()
+        if len(r_idx):
+            got[r_idx] = dm.run_host(r_desc, L.DESC_BITS, mask[r_idx], L.KERNEL_FUSED)
+        if len(d_idx):
+            got[d_idx] = dm.run_host(d_desc, L.DESC_DENSE_F32, mask[d_idx], L.KERNEL_FUSED)
+        assert launch_count() > before, "no kernel was launched"
+        assert_close(got, ref, (name, "fused", force_dense))
+
+
+@pytest.mark.parametrize("name", ["dmv", "imdb1", "imdb3"])
+def test_fused_kernel_batch_vs_oracle_and_formats(name):
+    """A ragged batch (not a multiple of the 128-query tile, more tiles than CTAs) through K3: fp64 oracle on every
+    query; range rows, BITS rows and SPARSE rows give the same bits; AUTO picks K3 for the big models."""
+    import torch
+
+    m, dm = G.model(name), dev_model(name)
+    n = 148 * 2 * 128 * 2 + 77
+    kmax = min(m.n_nodes, 14)
+    host = dm.gen_range_queries_host(5, 9, n, 1, kmax)
+    lo, hi = unpack_ranges(m, host)
+    sub = np.random.default_rng(1).choice(n, 6000, replace=False)
+    sub[:300] = np.arange(n - 300, n)  # the ragged last tiles
+    ref = O.dense_tree(m, O.range_weights(m, lo[sub], hi[sub]))
+    got = dm.run_host(host, L.DESC_RANGE_U8, None, L.KERNEL_FUSED).astype(np.float64)
+    assert_close(got[sub], ref, (name, "fused ranges"))
+    pc = PredicateCompiler(m)
+    via_bits = dm.run_host(pc.pack_bits(lo, hi), L.DESC_BITS, None, L.KERNEL_FUSED).astype(np.float64)
+    assert np.array_equal(via_bits, got)
+    row_off, entries = pc.pack_sparse(lo, hi)
+    assert np.array_equal(dm.run_sparse_host(row_off, entries, None, L.KERNEL_FUSED).astype(np.float64), got)
+    # tiny batches: fewer queries than one tile, one query, none
+    for k in (1, 5, 127, 129):
+        assert np.array_equal(dm.run_host(host[:k], L.DESC_RANGE_U8, None, L.KERNEL_FUSED).astype(np.float64), got[:k])
+    assert dm.run_host(host[:0], L.DESC_RANGE_U8, None, L.KERNEL_FUSED).shape == (0,)
+    # unconstrained query: total mass 1; an empty range selects nothing
+    full = np.zeros((2, host.shape[1]), dtype=np.uint8)
+    full[:, 1:2 * m.n_nodes:2] = np.minimum(m.card - 1, 255)
+    full[1, 2 * 1], full[1, 2 * 1 + 1] = 3, 1
+    r = dm.run_host(full, L.DESC_RANGE_U8, None, L.KERNEL_FUSED)
+    assert abs(r[0] - 1.0) < 1e-5 and r[1] == 0.0
+    auto = dm.run_host(host[:4096], L.DESC_RANGE_U8, None, L.KERNEL_AUTO).astype(np.float64)
+    if dm.flops_dense >= 30000:
+        assert np.array_equal(auto, got[:4096])  # AUTO = K3 on the IMDB-sized models
+    else:
+        assert_close(auto, got[:4096], (name, "auto"))
+
+
+def test_fused_kernel_declines_wide_models():
+    dm = dev_model("census")  # 68 columns: one fan-out mask word per query is not enough
+    desc = dm.gen_range_queries_host(1, 0, 256, 1, 5)
+    with pytest.raises(L.BayesCardError, match="K3"):
+        dm.run_host(desc, L.DESC_RANGE_U8, None, L.KERNEL_FUSED)
+    assert dm.run_host(desc, L.DESC_RANGE_U8, None, L.KERNEL_AUTO).shape == (256,)
+
+
 @pytest.mark.parametrize("name", ["dmv", "census", "imdb1"])
 def test_synthetic_batch_generic_vs_spec_vs_oracle(name):
     """Config 2/5 generator: device == host twin bit for bit; both kernels vs the fp64 dense oracle."""

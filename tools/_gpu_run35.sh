@@ -1,0 +1,2 @@
+mkdir -p gpurun_out
+(timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -12) > gpurun_out/s35_pytest.log; tail -6 gpurun_out/s35_pytest.log
