@@ -44,6 +44,7 @@ _SIGS = {
     # name: (restype, argtypes)
     "bc_model_create": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "bc_model_create_from_file": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]),
     "bc_model_destroy": (None, [C.c_void_p]),
     "bc_model_n_nodes": (C.c_int, [C.c_void_p]),
     "bc_model_device": (C.c_int, [C.c_void_p]),

@@ -19,18 +19,23 @@ from .loader import TreeModel
 
 
 class DeviceModel:
-    def __init__(self, tm: TreeModel, device: int = 0, specialize: bool = True, cache_dir: Optional[str] = None):
+    def __init__(self, tm: TreeModel, device: int = 0, specialize: bool = True, cache_dir: Optional[str] = None,
+                 flat_file: Optional[str] = None):
         self.tm = tm
         self.device = device
         lib = L.lib()
-        arena, off, stride = tm.pack_arena()
-        fan, foff = tm.pack_fanouts()
-        parent = np.ascontiguousarray(tm.parent, dtype=np.int32)
-        card = np.ascontiguousarray(tm.card, dtype=np.int32)
         h = C.c_void_p()
-        L.check(lib.bc_model_create(device, tm.n_nodes, parent.ctypes.data, card.ctypes.data, off.ctypes.data,
-                                    stride.ctypes.data, arena.ctypes.data, arena.size, foff.ctypes.data,
-                                    fan.ctypes.data, fan.size, C.byref(h)))
+        card = np.ascontiguousarray(tm.card, dtype=np.int32)
+        if flat_file is not None:
+            # the library maps the file itself: no array of this model crosses the boundary from Python
+            L.check(lib.bc_model_create_from_file(device, os.fsencode(flat_file), C.byref(h)))
+        else:
+            arena, off, stride = tm.pack_arena()
+            fan, foff = tm.pack_fanouts()
+            parent = np.ascontiguousarray(tm.parent, dtype=np.int32)
+            L.check(lib.bc_model_create(device, tm.n_nodes, parent.ctypes.data, card.ctypes.data, off.ctypes.data,
+                                        stride.ctypes.data, arena.ctypes.data, arena.size, foff.ctypes.data,
+                                        fan.ctypes.data, fan.size, C.byref(h)))
         self._h = h
         self.n_nodes = tm.n_nodes
         self.mask_words = (tm.n_nodes + 31) // 32
@@ -45,6 +50,12 @@ class DeviceModel:
                 self.specialize(cache_dir)
             except L.BayesCardError as e:  # generic CUDA kernel keeps serving; remembered for diagnostics
                 self.spec_error = str(e)
+
+    @classmethod
+    def from_flat_file(cls, path: str, device: int = 0, specialize: bool = True) -> "DeviceModel":
+        """Serve from a flat model file (``TreeModel.save_flat``): decode tables through ``mmap``, CPTs through
+        ``bc_model_create_from_file`` -- nothing is unpickled."""
+        return cls(TreeModel.load_flat(path), device=device, specialize=specialize, flat_file=path)
 
     # ------------------------------------------------------------------ lifecycle
     def close(self):

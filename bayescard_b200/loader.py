@@ -217,7 +217,7 @@ class TreeModel:
         return arena, np.asarray(offs, dtype=np.int64)
 
     # ------------------------------------------------------------------ flat file format
-    def save(self, path: str) -> None:
+    def _meta(self) -> dict:
         meta = {
             "format_version": FORMAT_VERSION,
             "table_name": _jsonable(self.table_name),
@@ -247,6 +247,10 @@ class TreeModel:
             "n_bins": _jsonable(self.n_bins),
             "root": _jsonable(self.root),
         }
+        return meta
+
+    def save(self, path: str) -> None:
+        meta = self._meta()
         arrays = {"parent": self.parent.astype(np.int32), "card": self.card.astype(np.int32)}
         for v, t in enumerate(self.cpts):
             arrays[f"cpt_{v}"] = np.asarray(t, dtype=np.float64)
@@ -265,6 +269,10 @@ class TreeModel:
             card = z["card"].astype(np.int32)
             cpts = [z[f"cpt_{v}"] for v in range(len(parent))]
             fanouts = {k[4:]: z[k] for k in z.files if k.startswith("fan_")}
+        return TreeModel._from_meta(meta, parent, card, cpts, fanouts)
+
+    @staticmethod
+    def _from_meta(meta, parent, card, cpts, fanouts) -> "TreeModel":
         enc = {k: (None if v is None else {_unjson(a): int(b) for a, b in v}) for k, v in meta["encoding"].items()}
         nib = {k: None if v is None else {int(b): (d if isinstance(d, int) else {_unjson(a): float(w) for a, w in d}) for b, d in v}
                for k, v in meta["n_in_bin"].items()}
@@ -282,6 +290,87 @@ class TreeModel:
             fanout_attr_positive=meta["fanout_attr_positive"], max_parents=_unjson(meta["max_parents"]),
             n_mcv=_unjson(meta["n_mcv"]), n_bins=_unjson(meta["n_bins"]), root=_unjson(meta["root"]),
         )
+
+
+    # ------------------------------------------------------------------ flat, mmap-able model file (".bcm")
+    def save_flat(self, path: str) -> None:
+        """One flat, versioned, mmap-able file: what ``bc_model_create_from_file`` (csrc/bc_modelfile.cc, which documents
+        the layout) uploads without touching Python or pickle, plus the decode tables as a JSON section
+        (SURVEY.md section 8f item 4)."""
+        import struct
+
+        arena, off, stride = self.pack_arena()
+        fan, foff = self.pack_fanouts()
+        has_fan = bool((foff >= 0).any())
+        cpt64 = np.concatenate([np.asarray(t, dtype=np.float64).reshape(-1) for t in self.cpts])
+        meta = self._meta()
+        meta["fan_names"] = [k for k in self.fanouts]
+        meta["fan_sizes"] = [int(np.asarray(self.fanouts[k]).size) for k in self.fanouts]
+        meta["fan64"] = [np.asarray(self.fanouts[k], dtype=np.float64).reshape(-1).tolist() for k in self.fanouts]
+        mbytes = json.dumps(meta).encode("utf-8")
+        sections = [
+            (np.ascontiguousarray(self.parent, dtype="<i4").tobytes(), 64),
+            (np.ascontiguousarray(self.card, dtype="<i4").tobytes(), 64),
+            (np.ascontiguousarray(off, dtype="<i8").tobytes(), 64),
+            (np.ascontiguousarray(stride, dtype="<i4").tobytes(), 64),
+            (np.ascontiguousarray(foff, dtype="<i8").tobytes(), 64),
+            (np.ascontiguousarray(arena, dtype="<f4").tobytes(), 4096),
+            (np.ascontiguousarray(fan, dtype="<f4").tobytes() if has_fan else b"", 64),
+            (np.ascontiguousarray(cpt64, dtype="<f8").tobytes(), 64),
+            (mbytes, 64),
+        ]
+        offs, pos = [], 128
+        for data, align in sections:
+            pos = -(-pos // align) * align
+            offs.append(pos)
+            pos += len(data)
+        header = struct.pack("<8sII4Q9QQ", b"BCB200M\0", 1, self.n_nodes, arena.size, fan.size if has_fan else 0, cpt64.size,
+                             len(mbytes), *offs, pos)
+        assert len(header) == 128
+        with open(path, "wb") as f:
+            f.write(header)
+            at = 128
+            for (data, _), o in zip(sections, offs):
+                f.write(b"\0" * (o - at))
+                f.write(data)
+                at = o + len(data)
+
+    @staticmethod
+    def load_flat(path: str) -> "TreeModel":
+        """Host-side twin of ``bc_model_create_from_file``: the same file through ``mmap``, no pickle."""
+        import mmap
+        import struct
+
+        with open(path, "rb") as f:
+            mm = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
+        try:
+            if len(mm) < 128:
+                raise ValueError(f"{path}: not a flat model file (shorter than its header)")
+            (magic, version, n, arena_floats, fan_floats, n64, meta_bytes, o_parent, o_card, o_off, o_stride, o_foff, o_arena, o_fan,
+             o_cpt64, o_meta, file_bytes) = struct.unpack("<8sII4Q9QQ", mm[:128])
+            if magic != b"BCB200M\0":
+                raise ValueError(f"{path}: bad magic (not a bayescard_b200 flat model file)")
+            if version != 1:
+                raise ValueError(f"{path}: unsupported flat model file version {version}")
+            if file_bytes != len(mm):
+                raise ValueError(f"{path}: truncated or padded file (size differs from the header)")
+            for o, ln in ((o_parent, 4 * n), (o_card, 4 * n), (o_cpt64, 8 * n64), (o_meta, meta_bytes)):
+                if o + ln > len(mm):
+                    raise ValueError(f"{path}: a section lies outside the file")
+            parent = np.frombuffer(mm, dtype="<i4", count=n, offset=o_parent).astype(np.int32)
+            card = np.frombuffer(mm, dtype="<i4", count=n, offset=o_card).astype(np.int32)
+            cpt64 = np.frombuffer(mm, dtype="<f8", count=n64, offset=o_cpt64).copy()
+            meta = json.loads(bytes(mm[o_meta:o_meta + meta_bytes]).decode("utf-8"))
+        finally:
+            mm.close()
+        cpts, at = [], 0
+        for v in range(n):
+            shape = (int(card[v]),) if parent[v] < 0 else (int(card[v]), int(card[parent[v]]))
+            size = int(np.prod(shape))
+            cpts.append(cpt64[at:at + size].reshape(shape))
+            at += size
+        fanouts = {k: np.asarray(v, dtype=np.float64) for k, v in zip(meta["fan_names"], meta["fan64"])}
+        return TreeModel._from_meta(meta, parent, card, cpts, fanouts)
 
 
 def _jsonable(v):
@@ -468,9 +557,11 @@ def load_pickle(path_or_bytes) -> TreeModel:
 
 
 def load_model(path: str) -> TreeModel:
-    """Load either a reference pickle (``*.pkl``) or the flat ``.npz`` form."""
+    """Load a reference pickle (``*.pkl``), the ``.npz`` fixture form or the flat mmap-able ``.bcm`` file."""
     with open(path, "rb") as f:
-        magic = f.read(4)
+        magic = f.read(8)
+    if magic == b"BCB200M\0":
+        return TreeModel.load_flat(path)
     if magic[:2] == b"PK":
         return TreeModel.load(path)
     return load_pickle(path)

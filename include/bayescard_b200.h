@@ -102,6 +102,11 @@ BC_API int bc_model_create(int device, int n_nodes, const int32_t* parent, const
                     const int64_t* cpt_off, const int32_t* stride, const float* cpt_arena,
                     size_t arena_floats, const int64_t* fan_off, const float* fan_arena,
                     size_t fan_floats, bc_model** out);
+/* The same model from a flat, versioned, mmap-able file written once from the pickle (bayescard_b200/loader.py:
+ * TreeModel.save_flat; layout in csrc/bc_modelfile.cc): replaces `pickle.load` of the Bayescard_BN object
+ * (Models/BN_single_model.py:207-223) + init_inference_method (Models/Bayescard_BN.py:122-142) for a serving process
+ * that must not unpickle third-party classes.  Validates magic, version and every section bound. */
+BC_API int bc_model_create_from_file(int device, const char* path, bc_model** out);
 BC_API void bc_model_destroy(bc_model* m);
 
 BC_API int bc_model_n_nodes(const bc_model* m);

@@ -125,6 +125,19 @@ def test_fused_kernel_batch_vs_oracle_and_formats(name):
         assert_close(auto, got[:4096], (name, "auto"))
 
 
+def test_model_from_flat_file_equals_model_from_arrays(tmp_path):
+    """bc_model_create_from_file (mmap of the .bcm file, no pickle) serves the same bits as bc_model_create."""
+    for name in ("dmv", "imdb1"):
+        m, dm = G.model(name), dev_model(name)
+        path = str(tmp_path / (name + ".bcm"))
+        m.save_flat(path)
+        df = DeviceModel.from_flat_file(path, device=0, specialize=True)
+        desc = dm.gen_range_queries_host(3, 0, 5000, 1, min(m.n_nodes, 14))
+        for kernel in (L.KERNEL_GENERIC, L.KERNEL_SPEC, L.KERNEL_FUSED):
+            assert np.array_equal(df.run_host(desc, L.DESC_RANGE_U8, None, kernel), dm.run_host(desc, L.DESC_RANGE_U8, None, kernel))
+        df.close()
+
+
 def test_fused_kernel_declines_wide_models():
     dm = dev_model("census")  # 68 columns: one fan-out mask word per query is not enough
     desc = dm.gen_range_queries_host(1, 0, 256, 1, 5)

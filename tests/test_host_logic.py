@@ -242,6 +242,47 @@ def test_host_only_model_codegen_and_generator():
     dm.close()
 
 
+@pytest.mark.parametrize("name", G.MODEL_NAMES)
+def test_flat_model_file_round_trip(name, tmp_path):
+    """SURVEY 8f item 4: one mmap-able file instead of the pickle.  The Python reader gives back the same TreeModel;
+    the C reader (bc_model_create_from_file, host-only model: no GPU needed) builds the same model as the array entry
+    point -- equal code-generator hash means equal topology and equal fp32 arena bit for bit."""
+    tm = G.model(name)
+    path = str(tmp_path / (name + ".bcm"))
+    tm.save_flat(path)
+    back = TreeModel.load_flat(path)
+    assert np.array_equal(back.parent, tm.parent) and np.array_equal(back.card, tm.card)
+    assert all(np.array_equal(a, b) for a, b in zip(back.cpts, tm.cpts))
+    assert back._meta() == tm._meta()
+    assert set(back.fanouts) == set(tm.fanouts) and all(np.array_equal(back.fanouts[k], tm.fanouts[k]) for k in tm.fanouts)
+    a, b = DeviceModel(tm, device=-1, specialize=False), DeviceModel.from_flat_file(path, device=-1, specialize=False)
+    assert a.spec_hash() == b.spec_hash() and a.flops_dense == b.flops_dense and a.dense_width == b.dense_width
+    assert np.array_equal(a.bits_offset, b.bits_offset)
+    a.close()
+    b.close()
+
+
+def test_flat_model_file_rejects_damaged_files(tmp_path):
+    tm = G.model("dmv")
+    good = str(tmp_path / "dmv.bcm")
+    tm.save_flat(good)
+    raw = open(good, "rb").read()
+    cases = {"truncated": raw[:-100], "magic": b"NOTAMODL" + raw[8:], "version": raw[:8] + (7).to_bytes(4, "little") + raw[12:],
+             "short": raw[:64], "section": raw[:48] + (1 << 40).to_bytes(8, "little") + raw[56:]}
+    for what, data in cases.items():
+        bad = str(tmp_path / (what + ".bcm"))
+        open(bad, "wb").write(data)
+        h = ctypes.c_void_p()
+        rc = L.lib().bc_model_create_from_file(-1, os.fsencode(bad), ctypes.byref(h))
+        assert rc != 0 and not h.value, what
+        assert L.lib().bc_last_error()
+        if what != "section":  # (the Python reader does not touch the device-only sections)
+            with pytest.raises(ValueError):
+                TreeModel.load_flat(bad)
+    h = ctypes.c_void_p()
+    assert L.lib().bc_model_create_from_file(-1, os.fsencode(str(tmp_path / "missing.bcm")), ctypes.byref(h)) != 0
+
+
 def test_shard_split():
     assert ShardedModel.split(10, 4) == [(0, 2), (2, 4), (4, 6), (6, 10)]
     assert ShardedModel.split(3, 8)[-1] == (0, 3)
