@@ -66,6 +66,9 @@ _SIGS = {
     "bc_expand_sparse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "bc_query_batch_sparse_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
                                              C.c_int]),
+    "bc_expand_wsparse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "bc_query_batch_wsparse_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                              C.c_int]),
     "bc_gen_sparse_queries_host": (C.c_int, [C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_size_t, C.c_int, C.c_int,
                                              C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t)]),
     "bc_gen_range_queries": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_size_t, C.c_int, C.c_int, C.c_void_p,

@@ -42,6 +42,9 @@ struct BcHostPipe {
     uint32_t* h_rowoff[kSlots]{};
     uint32_t* h_entries[kSlots]{};
     size_t cap_sq = 0, cap_entries = 0;
+    // WSPARSE path: weighted runs in, DENSE_F32 rows built on the device
+    float* d_wdense[kSlots]{};
+    size_t cap_wq = 0;
 };
 
 static void pipe_free(BcHostPipe* p) {
@@ -54,6 +57,7 @@ static void pipe_free(BcHostPipe* p) {
         cudaFreeHost(p->h_mask[i]);
         cudaFreeHost(p->h_out[i]);
         cudaFree(p->d_rowoff[i]);
+        cudaFree(p->d_wdense[i]);
         cudaFree(p->d_entries[i]);
         cudaFree(p->d_bits[i]);
         cudaFreeHost(p->h_rowoff[i]);
@@ -183,6 +187,13 @@ extern "C" int bc_model_create(int device, int n_nodes, const int32_t* parent, c
         CK(cudaMemset(m->d_spec_ctr, 0, BC_SPEC_CTR_SLOTS * 16));
         CK(cudaMalloc(&m->d_bits_default, m->bits_default.size() * 4));
         CK(cudaMemcpy(m->d_bits_default, m->bits_default.data(), m->bits_default.size() * 4, cudaMemcpyHostToDevice));
+        {
+            std::vector<float> dd(m->lam_total, 0.f);
+            for (int v = 0; v < m->n; ++v)
+                for (int c = 0; c < m->nodes[v].card; ++c) dd[m->nodes[v].lam_off + c] = 1.f;
+            CK(cudaMalloc(&m->d_dense_default, dd.size() * sizeof(float)));
+            CK(cudaMemcpy(m->d_dense_default, dd.data(), dd.size() * sizeof(float), cudaMemcpyHostToDevice));
+        }
         CK(cudaMalloc(&m->d_ent_node, m->ent_node.size() * sizeof(uint16_t)));
         CK(cudaMemcpy(m->d_ent_node, m->ent_node.data(), m->ent_node.size() * sizeof(uint16_t),
                       cudaMemcpyHostToDevice));
@@ -205,6 +216,7 @@ extern "C" void bc_model_destroy(bc_model* m) {
         cudaFree(m->d_nodes);
         cudaFree(m->d_bits);
         cudaFree(m->d_bits_default);
+        cudaFree(m->d_dense_default);
         cudaFree(m->d_spec_ctr);
         cudaFree(m->d_ent_node);
     }
@@ -512,8 +524,8 @@ static int sparse_ensure(bc_model* m, size_t chunk_q, size_t chunk_entries) {
     return BC_OK;
 }
 
-extern "C" int bc_query_batch_sparse_host(bc_model* m, const uint32_t* row_off, const uint32_t* entries, size_t nq,
-                                          const uint32_t* fan_mask, float* out, int kernel) {
+static int sparse_host_impl(bc_model* m, const uint32_t* row_off, const uint32_t* entries, size_t nq, const uint32_t* fan_mask,
+                            float* out, int kernel, bool weighted) {
     if (!m || m->device < 0) { bc_set_error("model has no device (host-only model)"); return BC_EINVAL; }
     if (nq == 0) return BC_OK;
     if (!row_off || !out) { bc_set_error("row_off/out is NULL"); return BC_EINVAL; }
@@ -522,8 +534,8 @@ extern "C" int bc_query_batch_sparse_host(bc_model* m, const uint32_t* row_off, 
     // chunks of 1M queries (~30 MB of CSR): measured on B200 (profiles/r1_e2e_chunk_sweep.txt) every extra
     // chunk costs ~50 us of copy / event latency, more than the overlap wins back below a few million
     // queries; larger batches pipeline H2D | expand+infer | D2H over three slots (BC_SPARSE_CHUNK overrides)
-    size_t chunk = 1024 * 1024;
-    if (const char* env = std::getenv("BC_SPARSE_CHUNK")) {
+    size_t chunk = weighted ? 128 * 1024 : 1024 * 1024;   // weighted rows expand to 4 * sum(card) bytes each on the device
+    if (const char* env = std::getenv(weighted ? "BC_WSPARSE_CHUNK" : "BC_SPARSE_CHUNK")) {
         const long long v = std::atoll(env);
         if (v >= 1024) chunk = (size_t)v;
     }
@@ -540,6 +552,14 @@ extern "C" int bc_query_batch_sparse_host(bc_model* m, const uint32_t* row_off, 
     int rc = sparse_ensure(m, chunk, max_entries);
     if (rc) return rc;
     BcHostPipe* p = m->pipe;
+    if (weighted && chunk > p->cap_wq) {
+        for (int i = 0; i < BcHostPipe::kSlots; ++i) {
+            cudaFree(p->d_wdense[i]);
+            p->d_wdense[i] = nullptr;
+            BC_CUDA_CHECK(cudaMalloc(&p->d_wdense[i], chunk * (size_t)m->lam_total * 4));
+        }
+        p->cap_wq = chunk;
+    }
     const bool pin_off = is_pinned(row_off), pin_ent = !entries || is_pinned(entries), pin_out = is_pinned(out),
                pin_mask = !fan_mask || is_pinned(fan_mask);
     auto ensure_host = [&](void** h, size_t bytes) -> int {
@@ -585,9 +605,15 @@ extern "C" int bc_query_batch_sparse_host(bc_model* m, const uint32_t* row_off, 
         BC_CUDA_CHECK(cudaEventRecord(p->ev_in[s], p->s_in));
         BC_CUDA_CHECK(cudaStreamWaitEvent(p->s_k, p->ev_in[s], 0));
         // row_off values are absolute entry indices: bias the entries pointer instead of rewriting them
-        rc = bc_expand_sparse_launch(m, p->d_rowoff[s], p->d_entries[s] - e0, cq, p->d_bits[s], p->s_k);
-        if (rc) return rc;
-        rc = bc_query_batch(m, p->d_bits[s], cq, BC_DESC_BITS, dmask, p->d_out[s], kernel, p->s_k);
+        if (weighted) {
+            rc = bc_expand_wsparse_launch(m, p->d_rowoff[s], p->d_entries[s] - e0, cq, p->d_wdense[s], p->s_k);
+            if (rc) return rc;
+            rc = bc_query_batch(m, p->d_wdense[s], cq, BC_DESC_DENSE_F32, dmask, p->d_out[s], kernel, p->s_k);
+        } else {
+            rc = bc_expand_sparse_launch(m, p->d_rowoff[s], p->d_entries[s] - e0, cq, p->d_bits[s], p->s_k);
+            if (rc) return rc;
+            rc = bc_query_batch(m, p->d_bits[s], cq, BC_DESC_BITS, dmask, p->d_out[s], kernel, p->s_k);
+        }
         if (rc) return rc;
         BC_CUDA_CHECK(cudaEventRecord(p->ev_k[s], p->s_k));
         BC_CUDA_CHECK(cudaStreamWaitEvent(p->s_out, p->ev_k[s], 0));
@@ -610,6 +636,24 @@ extern "C" int bc_query_batch_sparse_host(bc_model* m, const uint32_t* row_off, 
         }
     }
     return BC_OK;
+}
+
+extern "C" int bc_query_batch_sparse_host(bc_model* m, const uint32_t* row_off, const uint32_t* entries, size_t nq,
+                                          const uint32_t* fan_mask, float* out, int kernel) {
+    return sparse_host_impl(m, row_off, entries, nq, fan_mask, out, kernel, false);
+}
+
+extern "C" int bc_query_batch_wsparse_host(bc_model* m, const uint32_t* row_off, const uint32_t* words, size_t nq,
+                                           const uint32_t* fan_mask, float* out, int kernel) {
+    return sparse_host_impl(m, row_off, words, nq, fan_mask, out, kernel, true);
+}
+
+extern "C" int bc_expand_wsparse(bc_model* m, const uint32_t* row_off, const uint32_t* words, size_t nq, float* dst_dense,
+                                 void* stream) {
+    if (!m || m->device < 0) { bc_set_error("model has no device (host-only model)"); return BC_EINVAL; }
+    if (nq && (!row_off || !dst_dense)) { bc_set_error("row_off/dst is NULL"); return BC_EINVAL; }
+    BC_CUDA_CHECK(cudaSetDevice(m->device));
+    return bc_expand_wsparse_launch(m, row_off, words, nq, dst_dense, static_cast<cudaStream_t>(stream));
 }
 
 // ------------------------------------------------------------------------------------ generator

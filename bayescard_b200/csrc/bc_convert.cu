@@ -141,6 +141,60 @@ int bc_convert_launch(bc_model* m, const void* src, int src_fmt, void* dst, int 
     return BC_OK;
 }
 
+// WSPARSE -> DENSE_F32: one warp per query.  A row is a list of runs, each a header word
+//   column (bits 0-14) | continuation (bit 15) | first state (bits 16-23) | count (bits 24-31)
+// followed by `count` fp32 weights for the states first .. first + count - 1.  The first run of a column clears the
+// column (unlisted states get weight 0, the meaning of a predicate); a continuation run adds more states to it.
+// Columns without a run keep weight 1 everywhere -- the shape of the reference's sparse (query, n_distinct) dicts
+// (Models/Bayescard_BN.py:279-325) with fractional weights, ~10-40x smaller than the DENSE row it expands to.
+__global__ void __launch_bounds__(256) wsparse_to_dense_kernel(const BcNodeRec* __restrict__ nodes, int n, const float* __restrict__ dflt,
+                                                                int lam_total, const uint32_t* __restrict__ row_off,
+                                                                const uint32_t* __restrict__ words, float* __restrict__ dst, size_t nq) {
+    const int lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t q = warp; q < nq; q += nwarps) {
+        float* row = dst + q * (size_t)lam_total;
+        for (int e = lane * 4; e < lam_total; e += 128)   // lam_total is a multiple of 4
+            *reinterpret_cast<float4*>(row + e) = *reinterpret_cast<const float4*>(dflt + e);
+        __syncwarp();
+        uint32_t i = row_off[q];
+        const uint32_t end = row_off[q + 1];
+        while (i < end) {
+            const uint32_t h = words[i];
+            const int col = (int)(h & 0x7fffu), first = (int)((h >> 16) & 0xffu), cnt = (int)(h >> 24);
+            if (col < n) {
+                const BcNodeRec nd = nodes[col];
+                if (!((h >> 15) & 1u)) {
+                    for (int c = lane; c < nd.card; c += 32) row[nd.lam_off + c] = 0.f;
+                    __syncwarp();
+                }
+                for (int j = lane; j < cnt; j += 32)
+                    if (first + j < nd.card && i + 1 + j < end) row[nd.lam_off + first + j] = __uint_as_float(words[i + 1 + j]);
+                __syncwarp();
+            }
+            i += 1 + (uint32_t)cnt;
+        }
+    }
+}
+
+int bc_expand_wsparse_launch(bc_model* m, const uint32_t* row_off, const uint32_t* words, size_t nq, float* dst_dense,
+                             cudaStream_t stream) {
+    if (nq == 0) return BC_OK;
+    if (m->max_card > 256 || m->n > 32767) {
+        bc_set_error("WSPARSE runs hold 8-bit state indices and 15-bit column ids (max domain %d, %d columns)", m->max_card, m->n);
+        return BC_ELIMIT;
+    }
+    const int threads = 256;
+    long long grid = (long long)((nq * 32 + threads - 1) / threads);
+    const long long cap = (long long)m->sm_count * 16;
+    if (grid > cap) grid = cap;
+    wsparse_to_dense_kernel<<<(int)grid, threads, 0, stream>>>(m->d_nodes, m->n, m->d_dense_default, m->lam_total, row_off, words,
+                                                               dst_dense, nq);
+    BC_CUDA_CHECK(cudaGetLastError());
+    bc_count_launch();
+    return BC_OK;
+}
+
 int bc_expand_sparse_launch(bc_model* m, const uint32_t* row_off, const uint32_t* entries, size_t nq, void* dst_bits,
                             cudaStream_t stream) {
     if (nq == 0) return BC_OK;

@@ -70,6 +70,7 @@ struct bc_model {
     BcNodeRec* d_nodes = nullptr;
     BcBitsRec* d_bits = nullptr;
     uint32_t* d_bits_default = nullptr;  // BITS row of the unconstrained query (every state selected)
+    float* d_dense_default = nullptr;    // DENSE_F32 row of the unconstrained query (1 on every state, 0 on row padding)
     uint16_t* d_ent_node = nullptr;
     int sm_count = 0;
     int smem_optin = 0;
@@ -116,6 +117,8 @@ int bc_k1_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32
 int bc_convert_launch(bc_model* m, const void* src, int src_fmt, void* dst, int dst_fmt, size_t nq, cudaStream_t stream);
 int bc_expand_sparse_launch(bc_model* m, const uint32_t* row_off, const uint32_t* entries, size_t nq, void* dst_bits,
                             cudaStream_t stream);
+int bc_expand_wsparse_launch(bc_model* m, const uint32_t* row_off, const uint32_t* words, size_t nq, float* dst_dense,
+                             cudaStream_t stream);
 // k2_batched.cu / k2_umma.cu
 int bc_k2_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32_t* fan_mask, float* out, int use_umma,
                  cudaStream_t stream);

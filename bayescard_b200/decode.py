@@ -332,6 +332,56 @@ class PredicateCompiler:
         return out
 
 
+def dense_to_wsparse(tm: TreeModel, dense: np.ndarray):
+    """DENSE_F32 rows -> WSPARSE (``include/bayescard_b200.h``): per row and constrained column ONE run covering the
+    states from the first to the last non-zero weight (zeros inside the run are sent as weights).  A column is
+    constrained when its segment differs from all-ones.  Vectorised over the batch; returns ``(row_off, words)`` uint32.
+    The expansion on the device reproduces ``dense`` bit for bit (row padding excepted, which no kernel reads)."""
+    dense = np.ascontiguousarray(dense, dtype=np.float32)
+    nq = dense.shape[0]
+    n = tm.n_nodes
+    off = np.zeros(n, dtype=np.int64)
+    acc = 0
+    for v in range(n):
+        off[v] = acc
+        acc += -(-int(tm.card[v]) // 4) * 4
+    if dense.shape[1] != acc:
+        raise ValueError(f"dense rows have {dense.shape[1]} floats, the model needs {acc}")
+    if int(tm.card.max()) > 256:
+        raise ValueError("WSPARSE runs hold 8-bit state indices")
+    first = np.zeros((nq, n), dtype=np.int64)
+    count = np.full((nq, n), -1, dtype=np.int64)  # -1: unconstrained (no run)
+    for v in range(n):
+        card = int(tm.card[v])
+        seg = dense[:, off[v]: off[v] + card]
+        con = np.any(seg != 1.0, axis=1)
+        nz = seg != 0.0
+        anynz = nz.any(axis=1)
+        f = np.where(anynz, nz.argmax(axis=1), 0)
+        l = np.where(anynz, card - 1 - nz[:, ::-1].argmax(axis=1), -1)
+        first[:, v] = f
+        count[:, v] = np.where(con, l - f + 1, -1)
+    run_words = np.where(count >= 0, count + 1, 0)                       # header + weights per (row, column)
+    row_len = run_words.sum(axis=1)
+    row_off = np.zeros(nq + 1, dtype=np.int64)
+    np.cumsum(row_len, out=row_off[1:])
+    if row_off[-1] >= 1 << 32:
+        raise ValueError("batch too large for 32-bit offsets: split it")
+    words = np.zeros(int(row_off[-1]), dtype=np.uint32)
+    col_start = row_off[:-1, None] + np.cumsum(run_words, axis=1) - run_words   # word index of each run's header
+    for v in range(n):
+        rows = np.nonzero(count[:, v] >= 0)[0]
+        if rows.size == 0:
+            continue
+        c, f, st = count[rows, v], first[rows, v], col_start[rows, v]
+        words[st] = (np.uint32(v) | (f.astype(np.uint32) << np.uint32(16)) | (c.astype(np.uint32) << np.uint32(24)))
+        seg = dense[:, off[v]: off[v] + int(tm.card[v])].view(np.uint32)
+        for j in range(int(c.max()) if c.size else 0):   # at most card(v) vectorised passes
+            m = c > j
+            words[st[m] + 1 + j] = seg[rows[m], f[m] + j]
+    return row_off.astype(np.uint32), words
+
+
 def unpack_ranges(tm: TreeModel, desc: np.ndarray):
     """Inverse of :meth:`PredicateCompiler.pack_ranges`: ``(lo, hi)`` int arrays ``[B, n_nodes]``."""
     n = tm.n_nodes

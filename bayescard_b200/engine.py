@@ -149,6 +149,25 @@ class DeviceModel:
     def expand_sparse_device(self, row_off_ptr: int, entries_ptr: int, n: int, dst_ptr: int, stream: int = 0) -> None:
         L.check(L.lib().bc_expand_sparse(self._h, row_off_ptr, entries_ptr, n, dst_ptr, stream or None))
 
+    def run_wsparse_host(self, row_off: np.ndarray, words: np.ndarray, mask: Optional[np.ndarray] = None,
+                         kernel: int = L.KERNEL_AUTO, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """WSPARSE rows (weighted runs, ``decode.dense_to_wsparse`` / ``PredicateCompiler.pack_wsparse``) from host
+        buffers: H2D, expand to DENSE_F32 on the device, infer, D2H -- pipelined in the library."""
+        row_off = np.ascontiguousarray(row_off, dtype=np.uint32)
+        words = np.ascontiguousarray(words, dtype=np.uint32)
+        n = row_off.size - 1
+        if n < 0 or (n > 0 and int(row_off[-1]) > words.size):
+            raise ValueError("row_off does not match the words array")
+        if mask is not None:
+            mask = np.ascontiguousarray(mask, dtype=np.uint32)
+            if mask.size != n * self.mask_words:
+                raise ValueError("fan-out mask has the wrong size")
+        if out is None:
+            out = np.empty(n, dtype=np.float32)
+        L.check(L.lib().bc_query_batch_wsparse_host(self._h, row_off.ctypes.data, words.ctypes.data if words.size else None, n,
+                                                    mask.ctypes.data if mask is not None else None, out.ctypes.data, kernel))
+        return out
+
     def run_sparse_host(self, row_off: np.ndarray, entries: np.ndarray, mask: Optional[np.ndarray] = None,
                         kernel: int = L.KERNEL_AUTO, out: Optional[np.ndarray] = None) -> np.ndarray:
         """SPARSE (CSR) queries from host buffers: H2D, expand to BITS, infer, D2H -- pipelined in the library."""

@@ -15,7 +15,7 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 
 from . import _lib as L
-from .decode import PredicateCompiler
+from .decode import dense_to_wsparse, PredicateCompiler
 from .engine import DeviceModel, ShardedModel
 from .loader import TreeModel
 
@@ -45,7 +45,13 @@ class VariableEliminationB200:
         if len(b_idx):
             out[b_idx] = self.dev.run_host(b_desc, L.DESC_BITS, None if mask is None else mask[b_idx], self.kernel)
         if len(d_idx):
-            out[d_idx] = self.dev.run_host(d_desc, L.DESC_DENSE_F32, None if mask is None else mask[d_idx], self.kernel)
+            # fractional weights cross PCIe as weighted runs (WSPARSE, ~20x smaller) and become DENSE rows on the device
+            dmask = None if mask is None else mask[d_idx]
+            if isinstance(self.dev, DeviceModel):
+                row_off, words = dense_to_wsparse(self.tm, d_desc)
+                out[d_idx] = self.dev.run_wsparse_host(row_off, words, dmask, self.kernel)
+            else:  # sharded over several GPUs: contiguous slices of DENSE rows
+                out[d_idx] = self.dev.run_host(d_desc, L.DESC_DENSE_F32, dmask, self.kernel)
         return out
 
     def query_batch(self, queries: Sequence[Dict[str, Sequence[int]]],

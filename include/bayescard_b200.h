@@ -162,6 +162,18 @@ BC_API int bc_expand_sparse(bc_model* m, const uint32_t* row_off, const uint32_t
 BC_API int bc_query_batch_sparse_host(bc_model* m, const uint32_t* row_off, const uint32_t* entries, size_t n_queries,
                                const uint32_t* fanout_mask, float* out_prob, int kernel);
 
+/* WSPARSE: the sparse (query, n_distinct) dicts of query_decoding (Models/Bayescard_BN.py:279-325) WITH fractional
+ * weights, as they cross PCIe: CSR over the batch, row q = words[row_off[q] .. row_off[q+1]), a list of runs
+ *   header = column (bits 0-14) | continuation (bit 15) | first state (bits 16-23) | count (bits 24-31)
+ * each followed by `count` fp32 weights for the states first .. first+count-1.  The first run of a column clears the
+ * column (states that are not listed get weight 0); continuation runs add states; columns without a run are
+ * unconstrained.  Expanded to DENSE_F32 rows on the device (bc_expand_wsparse: device buffers, stream ordered), then
+ * evaluated like bc_query_batch_host; the IMDB expectation factors shrink from 1.5-1.8 KB to ~50-100 B per factor. */
+BC_API int bc_expand_wsparse(bc_model* m, const uint32_t* row_off_dev, const uint32_t* words_dev, size_t n_queries,
+                      float* dst_dense_dev, void* stream);
+BC_API int bc_query_batch_wsparse_host(bc_model* m, const uint32_t* row_off, const uint32_t* words, size_t n_queries,
+                                const uint32_t* fan_mask, float* out_prob, int kernel);
+
 /* Synthetic workload generator (BASELINE.json configs 2 and 5): writes
  * RANGE_U8 descriptors for query indices [first, first+n) from a counter-based RNG keyed by
  * (seed, query index), so any query can be regenerated on the host for oracle spot checks

@@ -7,7 +7,7 @@ import pytest
 
 import golden_util as G
 from bayescard_b200 import _lib as L
-from bayescard_b200.decode import PredicateCompiler, unpack_ranges
+from bayescard_b200.decode import PredicateCompiler, dense_to_wsparse, unpack_ranges
 from bayescard_b200.engine import DeviceModel, ShardedModel, launch_count
 from bayescard_b200.ensemble import BN_ensemble
 from bayescard_b200.model import Bayescard_BN
@@ -136,6 +136,43 @@ def test_model_from_flat_file_equals_model_from_arrays(tmp_path):
         for kernel in (L.KERNEL_GENERIC, L.KERNEL_SPEC, L.KERNEL_FUSED):
             assert np.array_equal(df.run_host(desc, L.DESC_RANGE_U8, None, kernel), dm.run_host(desc, L.DESC_RANGE_U8, None, kernel))
         df.close()
+
+
+@pytest.mark.parametrize("name", ["dmv", "imdb0", "imdb3"])
+def test_wsparse_rows_expand_to_the_dense_rows(name):
+    """WSPARSE (weighted runs over PCIe) == the DENSE_F32 rows they stand for: device expansion bit for bit, results bit for
+    bit through every kernel, empty rows = unconstrained query, golden expectation cases through the public batch API."""
+    import torch
+
+    m, dm = G.model(name), dev_model(name)
+    pc = PredicateCompiler(m)
+    cases = [r for r in G.load("infer_cases.json.gz")[name] if "error" not in r]
+    decoded = [({k: list(v) for k, v in r["bins"].items()}, {k: np.asarray(v) for k, v in r["weights"].items()}) for r in cases]
+    _, _, d_idx, dense, mask = pc.pack(decoded, [r["fanout"] for r in cases], force_dense=True)
+    # a larger seeded batch with fractional weights on random ranges, all-zero columns and untouched columns
+    rng = np.random.default_rng(5)
+    big = np.repeat(dense, 40, axis=0)
+    big *= (rng.random(big.shape) < 0.9) * rng.uniform(0.1, 1.0, big.shape).astype(np.float32)
+    off = dm.dense_offset
+    for v in range(m.n_nodes):  # restore some columns to "unconstrained"
+        rows = rng.random(big.shape[0]) < 0.5
+        big[np.ix_(rows, np.arange(off[v], off[v] + int(m.card[v])))] = 1.0
+    for rows_dense, msk in ((dense, mask), (big.astype(np.float32), None)):
+        row_off, words = dense_to_wsparse(m, rows_dense)
+        assert words.nbytes < rows_dense.nbytes
+        d_off, d_words = torch.from_numpy(row_off.astype(np.int64)).to(torch.int32).cuda(), torch.from_numpy(words.astype(np.int64)).to(torch.int32).cuda()
+        d_dense = torch.empty(rows_dense.shape, dtype=torch.float32, device="cuda:0")
+        L.check(L.lib().bc_expand_wsparse(dm._h, d_off.data_ptr(), d_words.data_ptr(), rows_dense.shape[0], d_dense.data_ptr(), None))
+        torch.cuda.synchronize()
+        back = d_dense.cpu().numpy()
+        for v in range(m.n_nodes):  # row padding is never read by a kernel
+            assert np.array_equal(back[:, off[v]: off[v] + int(m.card[v])], rows_dense[:, off[v]: off[v] + int(m.card[v])])
+        for kernel in (L.KERNEL_GENERIC, L.KERNEL_SPEC, L.KERNEL_FUSED):
+            a = dm.run_wsparse_host(row_off, words, msk, kernel)
+            b = dm.run_host(rows_dense, L.DESC_DENSE_F32, msk, kernel)
+            assert np.array_equal(a, b), (name, kernel)
+    one = dm.run_wsparse_host(np.zeros(3, dtype=np.uint32), np.zeros(0, dtype=np.uint32))
+    assert np.all(np.abs(one - 1.0) < 1e-5)
 
 
 def test_fused_kernel_declines_wide_models():
