@@ -88,6 +88,9 @@ extern "C" {
 #define BC_KERNEL_FUSED 5    /* K3: whole tree per 128-query tile on the tensor cores (tcgen05 3xTF32), messages in
                                 tensor memory; models of <= 32 columns with domains <= 256 states, else BC_ELIMIT */
 
+#define BC_KERNEL_FUSED_1CTA 6 /* K3b: K3 scheduled as one CTA per SM (two accumulator chains, two issuer warps, three
+                                producer groups, [T_hi | T_lo] concatenated); domains <= 128 states */
+
 typedef struct bc_model bc_model;
 
 /* Replaces VariableEliminationJIT.__init__ + align_cpds_in_topological (ExactInference.py:25-40,

@@ -32,6 +32,7 @@ def main():
     from bayescard_b200.engine import DeviceModel
     from oracle import bayescard_oracle as O
 
+    FUSED = L.KERNEL_FUSED_1CTA if os.environ.get("K3B") else L.KERNEL_FUSED   # K3B=1: the single-CTA variant
     st = torch.cuda.current_stream().cuda_stream
     for name in args.models.split(","):
         tm = G.model(name)
@@ -47,9 +48,9 @@ def main():
                 got = np.zeros(len(cases))
                 try:
                     if len(r_idx):
-                        got[r_idx] = dm.run_host(r_desc, L.DESC_BITS, mask[r_idx], L.KERNEL_FUSED)
+                        got[r_idx] = dm.run_host(r_desc, L.DESC_BITS, mask[r_idx], FUSED)
                     if len(d_idx):
-                        got[d_idx] = dm.run_host(d_desc, L.DESC_DENSE_F32, mask[d_idx], L.KERNEL_FUSED)
+                        got[d_idx] = dm.run_host(d_desc, L.DESC_DENSE_F32, mask[d_idx], FUSED)
                 except L.BayesCardError as e:
                     rec["error"] = str(e)
                     break
@@ -89,7 +90,7 @@ def main():
                                       ("dense_fan", dense.data_ptr(), L.DESC_DENSE_F32, mask.data_ptr() if mask is not None else -1)):
             if mptr == -1:
                 continue
-            for kname, kernel in (("spec", L.KERNEL_SPEC), ("k3", L.KERNEL_FUSED)):
+            for kname, kernel in (("spec", L.KERNEL_SPEC), ("k3", FUSED)):
                 out = torch.empty(nq, dtype=torch.float32, device="cuda")
                 ts = []
                 for r in range(args.reps + 2):
