@@ -69,6 +69,9 @@ def main():
         small = card <= 256 and sum(-(-int(c) // 4) * 4 for c in m.card) * 4 < 40000 and float(rec["arena_MB"]) < 0.2
         if small:
             kernels.append(("k1", L.KERNEL_GENERIC))
+        if n_cols <= 32 and card <= 256:   # the fused tensor-core tree kernel (K3): Lambda stays in tensor memory
+            kernels.append(("fused", L.KERNEL_FUSED))
+        rec["flops_dense_per_query"] = dm.flops_dense
         for name, k in kernels:
             try:
                 for _ in range(2):  # warm-up: builds the prefix sums / transposed split CPTs on first use
@@ -86,7 +89,9 @@ def main():
                 results[name] = out.cpu().numpy().astype(np.float64)
                 rec[name + "_ms"] = round(ms, 3)
                 rec[name + "_qps"] = nq / (ms * 1e-3)
-                if name != "k1" and gemm_flop_q:
+                if name == "fused":
+                    rec["fused_tflops_dense"] = round(dm.flops_dense * nq / (ms * 1e-3) / 1e12, 2)
+                elif name != "k1" and gemm_flop_q:
                     rec[name + "_tflops_alg"] = round(gemm_flop_q * nq / (ms * 1e-3) / 1e12, 2)
             except Exception as e:  # noqa: BLE001
                 rec[name + "_error"] = str(e)[:200]
