@@ -151,6 +151,76 @@ def test_fused_kernel_batch_vs_oracle_and_formats(name):
         assert_close(auto, got[:4096], (name, "auto"))
 
 
+def test_fused_kernel_properties_full_batch():
+    """1 M fan-out weighted expectation factors on an IMDB BN through K3 (BASELINE config 3 at bench size): properties
+    that need no oracle -- permutation equivariance bit for bit, additivity of a split range, scaling linearity of the
+    weights, agreement with the straight-line kernel -- plus the fp64 oracle on a seeded sub-sample."""
+    import torch
+
+    name = "imdb2"
+    m, dm = G.model(name), dev_model(name)
+    n = 1_000_000
+    st = torch.cuda.current_stream().cuda_stream
+    host = dm.gen_range_queries_host(21, 0, n, 1, 4)
+    lo, hi = unpack_ranges(m, host)
+    rng = np.random.default_rng(9)
+    gen = torch.Generator(device="cuda:0").manual_seed(4)
+    d_lo, d_hi = torch.from_numpy(lo.astype(np.int32)).cuda(), torch.from_numpy(hi.astype(np.int32)).cuda()
+    dense = torch.zeros((n, dm.dense_width), dtype=torch.float32, device="cuda:0")
+    for v in range(m.n_nodes):
+        c = torch.arange(int(m.card[v]), device="cuda:0", dtype=torch.int32)[None, :]
+        sel = (c >= d_lo[:, v:v + 1]) & (c <= d_hi[:, v:v + 1])
+        w = 0.25 + 0.75 * torch.rand((n, int(m.card[v])), device="cuda:0", generator=gen)
+        o = int(dm.dense_offset[v])
+        dense[:, o:o + int(m.card[v])] = sel.to(torch.float32) * w
+    fan_nodes = [v for v in range(m.n_nodes) if m.fan_vector(v) is not None]
+    mask_h = np.zeros(n, dtype=np.uint32)
+    for v in fan_nodes:
+        mask_h |= (rng.random(n) < 0.4).astype(np.uint32) << np.uint32(v)
+    mask = torch.from_numpy(mask_h.view(np.int32)).cuda()
+    out = torch.empty(n, dtype=torch.float32, device="cuda:0")
+
+    def run(rows, msk, kernel=L.KERNEL_FUSED):
+        o = torch.empty(rows.shape[0], dtype=torch.float32, device="cuda:0")
+        dm.run_device(rows.data_ptr(), rows.shape[0], L.DESC_DENSE_F32, o.data_ptr(), mask_ptr=msk.data_ptr(), kernel=kernel, stream=st)
+        torch.cuda.synchronize()
+        return o
+
+    out = run(dense, mask)
+    assert bool(torch.all(out >= 0))
+    # (a) permutation: results follow their factors bit for bit (tiles are formed from different neighbours)
+    perm = torch.randperm(n, device="cuda:0", generator=gen)
+    assert torch.equal(run(dense[perm].contiguous(), mask[perm].contiguous()), out[perm])
+    # (b) additivity: the weights of one column split into two disjoint halves
+    v = max(range(1, m.n_nodes), key=lambda u: int(m.card[u]))
+    o, card = int(dm.dense_offset[v]), int(m.card[v])
+    sub = torch.arange(0, 200000, device="cuda:0")
+    a, b = dense[sub].clone(), dense[sub].clone()
+    a[:, o + card // 2:o + card] = 0
+    b[:, o:o + card // 2] = 0
+    tot = (run(a, mask[sub].contiguous()).double() + run(b, mask[sub].contiguous()).double())
+    ref = out[sub].double()
+    assert bool(torch.all((tot - ref).abs() <= 1e-5 * ref.abs() + 1e-30))
+    # (c) linearity: scaling one column's weights by 0.5 halves the result (exact in binary floating point)
+    h = dense[sub].clone()
+    h[:, o:o + card] *= 0.5
+    assert torch.equal(run(h, mask[sub].contiguous()), out[sub] * 0.5)
+    # (d) the straight-line kernel agrees within the budget; (e) fp64 oracle on a sub-sample
+    spec = run(dense[sub].contiguous(), mask[sub].contiguous(), L.KERNEL_SPEC).double()
+    assert bool(torch.all((spec - ref).abs() <= 1e-5 * ref.abs() + 1e-30))
+    idx = np.sort(rng.choice(n, 4000, replace=False))
+    Wh = dense[torch.from_numpy(idx).cuda()].cpu().numpy().astype(np.float64)
+    W = []
+    for u in range(m.n_nodes):
+        w = Wh[:, int(dm.dense_offset[u]):int(dm.dense_offset[u]) + int(m.card[u])]
+        f = m.fan_vector(u)
+        if f is not None:
+            on = ((mask_h[idx] >> np.uint32(u)) & 1).astype(bool)
+            w = np.where(on[:, None], w * f[None, :], w)
+        W.append(w)
+    assert_close(out.cpu().numpy()[idx], O.dense_tree(m, W), "imdb2 1M factors, fused kernel")
+
+
 def test_model_from_flat_file_equals_model_from_arrays(tmp_path):
     """bc_model_create_from_file (mmap of the .bcm file, no pickle) serves the same bits as bc_model_create."""
     for name in ("dmv", "imdb1"):
