@@ -52,7 +52,7 @@ namespace {
 
 constexpr int kTile = 128;    // queries per CTA tile = TMEM lanes = UMMA M
 constexpr int kBK = 16;       // child states per ring step: one 64-byte swizzle row
-constexpr int kGroups = 3;    // producer groups of 4 warps (one warp per TMEM lane quarter): ring step i is built by group i % kGroups
+constexpr int kGroups = 2;    // producer groups of 4 warps (one warp per TMEM lane quarter): ring step i is built by group i % kGroups
 constexpr int kIssuers = 2;   // issuer warp w owns accumulator w and the ring steps with step % 2 == w
 constexpr int kStages = 6;
 constexpr int kABytes = kTile * kBK * 4;   // 8 KB per half (hi or lo)

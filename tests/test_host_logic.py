@@ -10,7 +10,7 @@ import pytest
 
 import golden_util as G
 from bayescard_b200 import _lib as L
-from bayescard_b200.decode import PredicateCompiler, unpack_ranges
+from bayescard_b200.decode import PredicateCompiler, dense_to_wsparse, unpack_ranges
 from bayescard_b200.engine import DeviceModel, ShardedModel, gen_range_queries_host
 from bayescard_b200.loader import TreeModel, topological_order
 from bayescard_b200.sql_front import parse_query_single_table
@@ -281,6 +281,48 @@ def test_flat_model_file_rejects_damaged_files(tmp_path):
                 TreeModel.load_flat(bad)
     h = ctypes.c_void_p()
     assert L.lib().bc_model_create_from_file(-1, os.fsencode(str(tmp_path / "missing.bcm")), ctypes.byref(h)) != 0
+
+
+@pytest.mark.parametrize("name", ["dmv", "imdb0", "imdb3"])
+def test_wsparse_packer_round_trip(name):
+    """WSPARSE (include/bayescard_b200.h): the vectorised packer against a plain expansion of its own output, on the
+    golden expectation cases (fractional n_distinct weights, IN lists, empty predicates) and on synthetic rows with holes."""
+    m = G.model(name)
+    pc = PredicateCompiler(m)
+    cases = [r for r in G.load("infer_cases.json.gz")[name] if "error" not in r]
+    decoded = [({k: list(v) for k, v in r["bins"].items()}, {k: np.asarray(v) for k, v in r["weights"].items()}) for r in cases]
+    _, _, _, dense, _ = pc.pack(decoded, [r["fanout"] for r in cases], force_dense=True)
+    rng = np.random.default_rng(3)
+    holes = np.repeat(dense, 5, axis=0) * (rng.random((dense.shape[0] * 5, dense.shape[1])) < 0.8)
+    off, acc = [], 0
+    for v in range(m.n_nodes):
+        off.append(acc)
+        acc += -(-int(m.card[v]) // 4) * 4
+    for rows in (dense, holes.astype(np.float32), np.zeros((0, dense.shape[1]), dtype=np.float32)):
+        row_off, words = dense_to_wsparse(m, rows)
+        assert row_off.dtype == np.uint32 and words.dtype == np.uint32 and row_off.size == rows.shape[0] + 1
+        back = np.zeros_like(rows)
+        for v in range(m.n_nodes):
+            back[:, off[v]:off[v] + int(m.card[v])] = 1.0
+        for q in range(rows.shape[0]):
+            i = int(row_off[q])
+            seen = set()
+            while i < int(row_off[q + 1]):
+                h = int(words[i])
+                col, cont, first, cnt = h & 0x7FFF, (h >> 15) & 1, (h >> 16) & 0xFF, h >> 24
+                assert col < m.n_nodes and first + cnt <= int(m.card[col]) and (cont == 1) == (col in seen)
+                seen.add(col)
+                if not cont:
+                    back[q, off[col]:off[col] + int(m.card[col])] = 0.0
+                back[q, off[col] + first:off[col] + first + cnt] = words[i + 1:i + 1 + cnt].view(np.float32)
+                i += 1 + cnt
+            assert i == int(row_off[q + 1])
+        for v in range(m.n_nodes):
+            assert np.array_equal(back[:, off[v]:off[v] + int(m.card[v])], rows[:, off[v]:off[v] + int(m.card[v])])
+        if rows is dense:   # real factor lists touch a few columns: an order of magnitude fewer bytes than DENSE rows
+            assert words.nbytes + row_off.nbytes < rows.nbytes / 4
+    with pytest.raises(ValueError):
+        dense_to_wsparse(m, np.zeros((2, dense.shape[1] + 4), dtype=np.float32))
 
 
 def test_shard_split():
