@@ -9,8 +9,9 @@
 //     first correction side by side (N = 2 n8), a second one adds U_lo . T_hi onto the correction half; unit-weight
 //     leaves need ONE instruction per k-step instead of two, everything else two instead of three, and the epilogue
 //     adds main + correction of both chains in round-to-nearest registers (less truncation bias than K3);
-//   * THREE producer groups of four warps build alternate ring steps and split the epilogue's columns, so the
-//     per-step latency of a producer (LDS / LDG -> split -> STS -> fence -> arrive, ~500 clk) is overlapped 3x;
+//   * TWO producer groups of four warps build alternate ring steps and split the epilogue's columns, so the
+//     per-step latency of a producer (LDS / LDG -> split -> STS -> fence -> arrive, ~500 clk) is overlapped (three
+//     groups = 480 threads hit the 128-register cap and spill: measured slower);
 //   * one operand ring: a slot holds the U_v block (hi, lo) and the T_v^T block, ONE full barrier (four warp arrivals
 //     + the TMA transaction) and ONE empty barrier (one tcgen05.commit) per slot.
 #include <algorithm>
