@@ -46,6 +46,11 @@ def test_parse_and_factor_shapes():
     tq = plan_star_query("SELECT COUNT(*) FROM title t,cast_info ci,movie_keyword mk WHERE t.id=ci.movie_id AND t.id=mk.movie_id "
                          "AND mk.keyword_id=117", js)
     assert len(tq) == 2 and tq[1]["bn_index"] == 3 and tq[1]["expectation"] == ["title.mul_cast_info.movie_id"]
+    # first model: the pairwise-RDC vector of _greedily_select_first_cardinality_spn (kind_id x company_type_id 0.553 beats
+    # kind_id x info_type_id 0.391), not the FROM order
+    tq = plan_star_query("SELECT COUNT(*) FROM movie_info_idx mi_idx,title t,movie_companies mc WHERE t.id=mi_idx.movie_id AND "
+                         "t.id=mc.movie_id AND t.kind_id=1 AND mi_idx.info_type_id=101 AND mc.company_type_id=2", js)
+    assert tq[1]["bn_index"] == 4 and tq[2]["bn_index"] == tq[3]["bn_index"] == 0
     with pytest.raises(ValueError):
         parse_job_light("SELECT COUNT(*) FROM title t,name n WHERE t.id=n.id")
 
@@ -56,10 +61,10 @@ def test_q_errors_match_the_published_row():
     est = _oracle_estimates(plan_workload(sqls, js))
     qe = np.asarray([O.q_error(e, t) for e, t in zip(est, true)])
     got = [float(np.percentile(qe, p)) for p in (50, 90, 95, 100)]
-    # measured here: 1.281 / 2.91 / 4.649 / 19.14 -- the published row within 20 % at every percentile, the maximum to 0.1 %
+    # measured here: 1.301 / 3.535 / 4.837 / 19.14 against 1.30 / 3.534 / 4.836 / 19.13 published: the row is reproduced to
+    # the digits the paper prints (first model chosen by the shipped pairwise RDC values, as the reference does)
     for g, p in zip(got, paper):
-        assert abs(g - p) / p < 0.2, (got, paper)
-    assert abs(got[3] - paper[3]) / paper[3] < 0.01
+        assert abs(g - p) / p < 0.005, (got, paper)
 
 
 @pytest.mark.gpu
@@ -84,6 +89,6 @@ def test_job_light_on_the_gpu_equals_the_oracle():
     assert np.max(np.abs(batch - ref) / np.maximum(ref, 1e-300)) < 2e-5   # up to 7 fp32 factors multiplied per query
     assert np.max(np.abs(one - batch) / np.maximum(batch, 1e-300)) < 2e-5
     qe = np.asarray([O.q_error(e, t) for e, t in zip(batch, true)])
-    assert abs(float(np.percentile(qe, 50)) - 1.281) < 0.01 and abs(float(qe.max()) - 19.14) < 0.05
+    assert abs(float(np.percentile(qe, 50)) - 1.301) < 0.01 and abs(float(qe.max()) - 19.14) < 0.05
     for bn in bns.values():
         bn.close()
