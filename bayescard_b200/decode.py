@@ -213,8 +213,10 @@ class PredicateCompiler:
         """True when the selected bins all carry weight exactly 1 and none repeats."""
         if len(set(b)) != len(b):
             return False
+        if isinstance(w, (list, tuple)):
+            return all(x == 1 for x in w)
         w = np.asarray(w, dtype=np.float64).reshape(-1)
-        return bool(np.all(w == 1))
+        return w.size <= 8 and all(x == 1.0 for x in w.tolist()) if w.size <= 8 else bool(np.all(w == 1))
 
     def geometry(self):
         """(bit offsets int64[n], BITS row bytes, dense offsets int64[n], dense width) -- same rules as the C ABI."""
@@ -243,13 +245,21 @@ class PredicateCompiler:
         words = (n + 31) // 32
         mask = np.zeros((nq, words), dtype=np.uint32) if fanouts is not None else None
         kinds = np.zeros(nq, dtype=np.int8)  # 0 = bits, 1 = dense
-        bit_rows: List[np.ndarray] = []
+        bit_rows: List[bytes] = []     # BITS rows as little-endian byte strings built from Python integers
         dense_rows: List[np.ndarray] = []
+        card = [int(c) for c in tm.card]
+        boff = [int(b) for b in bit_off]
+        full_mask = (1 << total_bits) - 1
+        col_mask = [((1 << card[v]) - 1) << boff[v] for v in range(n)]
+        dense_default = np.zeros(width, dtype=np.float32)
+        for v in range(n):
+            dense_default[off[v]: off[v] + card[v]] = 1.0
+        index = tm._index
         for qi, (bins, wts) in enumerate(decoded):
             cols = []
             ok = not force_dense
             for attr, b in bins.items():
-                v = tm._index.get(attr)
+                v = index.get(attr)
                 if v is None:
                     continue
                 bl = list(b) if isinstance(b, (list, tuple, np.ndarray)) else [b]
@@ -258,37 +268,37 @@ class PredicateCompiler:
                     ok = False
             if fanouts is not None:
                 for attr in fanouts[qi]:
-                    v = tm._index.get(attr)
+                    v = index.get(attr)
                     if v is None or attr in bins or tm.fan_vector(v) is None:
                         continue
                     mask[qi, v >> 5] |= np.uint32(1 << (v & 31))
             if ok:
-                row = np.ones(total_bits, dtype=bool)
+                row = full_mask
                 for v, bl, _ in cols:
-                    row[bit_off[v]: bit_off[v] + int(tm.card[v])] = False
-                    if len(bl):
-                        row[bit_off[v] + np.asarray(bl, dtype=np.int64)] = True
-                bit_rows.append(row)
+                    row &= ~col_mask[v]
+                    o = boff[v]
+                    for b in bl:
+                        b = int(b)
+                        if not 0 <= b < card[v]:
+                            raise IndexError(f"bin {b} outside the domain of column {v}")
+                        row |= 1 << (o + b)
+                bit_rows.append(row.to_bytes(row_bytes, "little"))
             else:
                 kinds[qi] = 1
-                row = np.zeros(width, dtype=np.float32)
-                for v in range(n):
-                    row[off[v]: off[v] + int(tm.card[v])] = 1.0
+                row = dense_default.copy()
                 for v, bl, w in cols:
                     w = np.asarray(w, dtype=np.float64).reshape(-1)
-                    seg = np.zeros(int(tm.card[v]), dtype=np.float64)
+                    seg = np.zeros(card[v], dtype=np.float64)
                     if len(bl):
                         if w.size == 1 and len(bl) > 1:
                             w = np.full(len(bl), w[0])
                         np.add.at(seg, np.asarray(bl, dtype=np.int64), w)
-                    row[off[v]: off[v] + int(tm.card[v])] = seg
+                    row[off[v]: off[v] + card[v]] = seg
                 dense_rows.append(row)
         bits_idx = np.nonzero(kinds == 0)[0]
         dense_idx = np.nonzero(kinds == 1)[0]
-        bits_desc = np.zeros((len(bit_rows), row_bytes), dtype=np.uint8)
-        if bit_rows:
-            packed = np.packbits(np.stack(bit_rows), axis=1, bitorder="little")
-            bits_desc[:, : packed.shape[1]] = packed
+        bits_desc = (np.frombuffer(b"".join(bit_rows), dtype=np.uint8).reshape(len(bit_rows), row_bytes).copy()
+                     if bit_rows else np.zeros((0, row_bytes), dtype=np.uint8))
         dense_desc = np.stack(dense_rows) if dense_rows else np.zeros((0, width), dtype=np.float32)
         return bits_idx, bits_desc, dense_idx, dense_desc, mask
 
