@@ -172,6 +172,15 @@ extern "C" int bc_model_create(int device, int n_nodes, const int32_t* parent, c
         }                                                                                         \
     } while (0)
         CK(cudaSetDevice(device));
+        {   // stream-ordered scratch (range rows -> BITS rows inside bc_query_batch) must not go back to the driver at every
+            // synchronisation: with the default release threshold of 0 a B = 1 call paid ~0.5 ms of cudaMallocAsync
+            cudaMemPool_t pool = nullptr;
+            if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+                unsigned long long keep = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            cudaGetLastError();
+        }
         CK(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device));
         CK(cudaDeviceGetAttribute(&m->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
         CK(cudaMalloc(&m->d_arena, m->arena_floats_padded * sizeof(float)));
