@@ -16,18 +16,21 @@
 //
 //   * Lambda_v of every live internal node sits in TENSOR MEMORY (one fp32 column per state, one lane per query);
 //     the columns are assigned on the host by first fit over the nodes' lifetimes in the edge schedule;
-//   * per edge and per block of 16 child states the 128 threads (thread = query = TMEM lane) read Lambda_v with
-//     tcgen05.ld, apply the query's weights (BITS mask, dense n_distinct weights, fan-out vector), split the product
-//     into TF32 hi + lo and write both as the K-major, 64-byte-swizzled A operand straight into shared memory;
-//   * the matching block of T_v^T (hi and lo, pre-split, pre-swizzled once per model) arrives by ONE TMA bulk copy
-//     (cp.async.bulk ... mbarrier::complete_tx) into the same ring slot, prefetched one step ahead;
-//   * one thread issues tcgen05.mma.cta_group::1.kind::tf32, error compensated: A_lo.B_hi + A_hi.B_lo + A_hi.B_hi
-//     (the small products first; A_lo = 0 and is skipped for unit-weight leaves) into a TMEM accumulator;
-//     tcgen05.commit frees the ring slot and, after the edge's last block, releases the accumulator;
-//   * the epilogue multiplies the accumulator into Lambda_pa with tcgen05.ld / tcgen05.st -- no shared memory, no
-//     HBM traffic; the root is a dot product with T_root in registers.
-//   * two CTAs per SM (256 TMEM columns and ~93 KB of shared memory each) overlap one tile's operand building and
-//     epilogue with the other's MMAs.
+//   * FOUR PRODUCER WARPS (thread = query = TMEM lane): per edge and per block of 16 child states they read Lambda_v
+//     with tcgen05.ld, apply the query's weights (BITS mask, dense n_distinct weights, fan-out vector), split the
+//     product into TF32 hi + lo and write both as the K-major, 64-byte-swizzled A operand straight into a 3-slot
+//     shared-memory ring (fence.proxy.async + one mbarrier arrive per warp); the message-independent inputs of the
+//     NEXT block (weights; finished 0/1 chunks for unit-weight leaves) are fetched one step ahead;
+//   * a TMA WARP keeps a 4-slot ring of T_v^T blocks (hi and lo, pre-split and pre-swizzled once per model into an
+//     "operand image") full: ONE bulk copy (cp.async.bulk ... mbarrier::complete_tx) per step;
+//   * an ISSUER WARP (whole warp converged, elect.sync inside the asm, edge table in the kernel-parameter bank so that
+//     every tcgen05 operand lives in uniform registers) issues tcgen05.mma.cta_group::1.kind::tf32, error compensated:
+//     A_lo.B_hi + A_hi.B_lo first, then A_hi.B_hi (A_lo = 0 and is skipped for unit-weight leaves), into a TMEM
+//     accumulator; tcgen05.commit frees the A and B slots and, after the edge's last block, releases the accumulator;
+//   * the producer warps then multiply the accumulator into Lambda_pa with tcgen05.ld / tcgen05.st (32 columns per
+//     round trip) -- no shared memory, no HBM traffic; the root is a dot product with T_root in registers;
+//   * two CTAs per SM (256 TMEM columns and ~104 KB of shared memory each; one CTA with 512 columns when a model's live
+//     messages need more) overlap one tile's operand building, MMA drain and epilogue with the other's MMAs.
 //
 // Algorithmic work per query = flops_dense(model) (every CPT entry once); HBM traffic = descriptor row + 4 B.
 #include <algorithm>
