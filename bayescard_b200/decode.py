@@ -227,6 +227,24 @@ class PredicateCompiler:
         dense_off = np.concatenate([[0], np.cumsum(pad)[:-1]]).astype(np.int64)
         return bit_off, row_bytes, dense_off, int(pad.sum())
 
+    def _pack_cache(self) -> dict:
+        """Per-model constants of ``pack`` (row geometry, per-column bit masks, the unconstrained DENSE row), built once."""
+        g = getattr(self, "_pack_g", None)
+        if g is None:
+            tm = self.tm
+            n = tm.n_nodes
+            bit_off, row_bytes, off, width = self.geometry()
+            card = [int(c) for c in tm.card]
+            boff = [int(b) for b in bit_off]
+            dense_default = np.zeros(width, dtype=np.float32)
+            for v in range(n):
+                dense_default[off[v]: off[v] + card[v]] = 1.0
+            g = {"row_bytes": row_bytes, "off": off, "width": width, "card": card, "boff": boff,
+                 "full_mask": (1 << int(tm.card.sum())) - 1,
+                 "col_mask": [((1 << card[v]) - 1) << boff[v] for v in range(n)], "dense_default": dense_default}
+            self._pack_g = g
+        return g
+
     def pack(self, decoded: Sequence[Tuple[Dict[str, Sequence[int]], Dict[str, np.ndarray]]],
              fanouts: Optional[Sequence[Sequence[str]]] = None, force_dense: bool = False):
         """Pack already decoded queries.
@@ -240,20 +258,14 @@ class PredicateCompiler:
         tm = self.tm
         n = tm.n_nodes
         nq = len(decoded)
-        bit_off, row_bytes, off, width = self.geometry()
-        total_bits = int(tm.card.sum())
+        g = self._pack_cache()
+        row_bytes, off, width = g["row_bytes"], g["off"], g["width"]
+        card, boff, full_mask, col_mask, dense_default = g["card"], g["boff"], g["full_mask"], g["col_mask"], g["dense_default"]
         words = (n + 31) // 32
         mask = np.zeros((nq, words), dtype=np.uint32) if fanouts is not None else None
         kinds = np.zeros(nq, dtype=np.int8)  # 0 = bits, 1 = dense
         bit_rows: List[bytes] = []     # BITS rows as little-endian byte strings built from Python integers
         dense_rows: List[np.ndarray] = []
-        card = [int(c) for c in tm.card]
-        boff = [int(b) for b in bit_off]
-        full_mask = (1 << total_bits) - 1
-        col_mask = [((1 << card[v]) - 1) << boff[v] for v in range(n)]
-        dense_default = np.zeros(width, dtype=np.float32)
-        for v in range(n):
-            dense_default[off[v]: off[v] + card[v]] = 1.0
         index = tm._index
         for qi, (bins, wts) in enumerate(decoded):
             cols = []
