@@ -211,12 +211,16 @@ class PredicateCompiler:
     @staticmethod
     def _unit_bins(b: Sequence[int], w) -> bool:
         """True when the selected bins all carry weight exactly 1 and none repeats."""
-        if len(set(b)) != len(b):
+        if len(b) > 1 and len(set(b)) != len(b):
             return False
-        if isinstance(w, (list, tuple)):
-            return all(x == 1 for x in w)
-        w = np.asarray(w, dtype=np.float64).reshape(-1)
-        return w.size <= 8 and all(x == 1.0 for x in w.tolist()) if w.size <= 8 else bool(np.all(w == 1))
+        if type(w) is np.ndarray:
+            w = w.ravel().tolist()
+        elif not isinstance(w, (list, tuple)):
+            w = np.asarray(w, dtype=np.float64).reshape(-1).tolist()
+        for x in w:
+            if x != 1:
+                return False
+        return True
 
     def geometry(self):
         """(bit offsets int64[n], BITS row bytes, dense offsets int64[n], dense width) -- same rules as the C ABI."""
