@@ -148,7 +148,42 @@ class PredicateCompiler:
                     more_up = False
         return bins, np.asarray(cov, dtype=np.float64)
 
+    _MEMO_MAX = 1 << 16
+
     def decode(self, query: dict, coverage: Optional[dict] = None, epsilon: float = 0.5) -> Decoded:
+        """``query_decoding`` (Models/Bayescard_BN.py:279-325).  Every column decodes independently of the others, so the
+        result per (column, predicate value) is memoised: serving workloads repeat the same few hundred predicates.  The
+        cached weight arrays are read-only and shared between results; the bin lists are copied."""
+        bins_out: Dict[str, List[int]] = {}
+        wts_out: Dict[str, np.ndarray] = {}
+        memo = self.__dict__.setdefault("_memo", {})
+        for attr, val in query.items():
+            key = None
+            if coverage is None:
+                try:
+                    key = (attr, tuple(val) if type(val) == list else val, type(val) == list, epsilon)
+                    hit = memo.get(key)
+                except TypeError:   # unhashable value (an ndarray, ...): decode without the memo
+                    key, hit = None, None
+                if hit is not None:
+                    if hit is False:
+                        return None, None
+                    bins_out[attr], wts_out[attr] = list(hit[0]), hit[1]
+                    continue
+            one_b, one_w = self._decode_one({attr: val}, coverage, epsilon)
+            if key is not None and len(memo) < self._MEMO_MAX:
+                if one_b is None:
+                    memo[key] = False
+                else:
+                    w = np.asarray(one_w[attr])
+                    w.setflags(write=False)
+                    memo[key] = (tuple(one_b[attr]), w)
+            if one_b is None:
+                return None, None
+            bins_out[attr], wts_out[attr] = one_b[attr], one_w[attr]
+        return bins_out, wts_out
+
+    def _decode_one(self, query: dict, coverage: Optional[dict] = None, epsilon: float = 0.5) -> Decoded:
         bins_out: Dict[str, List[int]] = {}
         wts_out: Dict[str, np.ndarray] = {}
         for attr, val in query.items():
