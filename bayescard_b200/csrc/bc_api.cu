@@ -310,7 +310,10 @@ extern "C" int bc_query_batch(bc_model* m, const void* desc, size_t nq, int fmt,
     const bool spec_via_bits = is_range && !spec_direct && m->spec_bits;
     // AUTO: models whose straight-line code outgrows the instruction caches (IMDB: > 20k CPT entries) are faster on the
     // fused tensor-core kernel in every format (profiles/r1_k3_*.txt); it declines (BC_ELIMIT) what it cannot serve
-    if (kernel == BC_KERNEL_AUTO && m->flops_dense >= 30000 && m->n <= 32 && m->max_card <= 256) {
+    // (also for models without a specialised image from ~20k dense flops: measured faster than K1 / K2 on the synthetic
+    // 10 x 100 and 20 x 50 trees, profiles/r1_config4_small_domains_k3.jsonl)
+    const bool has_image = m->spec_bits || m->spec_dense || m->spec_range8;
+    if (kernel == BC_KERNEL_AUTO && m->flops_dense >= (has_image ? 30000 : 20000) && m->n <= 32 && m->max_card <= 256) {
         rc = bc_query_batch(m, desc, nq, fmt, fan_mask, out, BC_KERNEL_FUSED, stream);
         if (rc != BC_ELIMIT) return rc;
     }
