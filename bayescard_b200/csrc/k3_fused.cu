@@ -506,14 +506,41 @@ int k3_prepare(bc_model* m) {
     if (n < 2) return fail("single-node model");
     if (n > 32) return fail("more than 32 columns (one fan-out mask word per query)");
     if (m->arena.empty()) return fail("no host copy of the CPT arena");
-    // ---- edge schedule: reverse topological order (children before parents)
+    // ---- edge schedule: depth-first post order (children before parents, a node's edge right after its last child's),
+    //      heaviest subtree first: a Lambda then only lives while its own subtree is being folded, so the live set is
+    //      bounded by the depth of the tree instead of its width (the reverse topological order kept 5+ messages of a
+    //      20-column synthetic tree alive at once and did not fit tensor memory)
+    const int n_edges = n - 1;
+    std::vector<std::vector<int>> kids(n);
+    std::vector<long long> weight(n, 0);
+    for (int v = n - 1; v >= 1; --v) {
+        weight[v] += (long long)m->nodes[v].card * m->nodes[v].card_pa;
+        weight[m->nodes[v].parent] += weight[v];
+        kids[m->nodes[v].parent].push_back(v);
+    }
+    std::vector<int> sched;   // sched[e] = child node of edge e
+    {
+        std::vector<std::pair<int, size_t>> stack{{0, 0}};
+        for (int v = 0; v < n; ++v)
+            std::stable_sort(kids[v].begin(), kids[v].end(), [&](int a, int b) { return weight[a] > weight[b]; });
+        while (!stack.empty()) {
+            auto& [v, i] = stack.back();
+            if (i < kids[v].size()) {
+                const int c = kids[v][i++];
+                stack.push_back({c, 0});
+            } else {
+                if (v != 0) sched.push_back(v);
+                stack.pop_back();
+            }
+        }
+    }
     std::vector<int> first_child_edge(n, -1), own_edge(n, -1);
-    for (int v = n - 1, e = 0; v >= 1; --v, ++e) {
+    for (int e = 0; e < n_edges; ++e) {
+        const int v = sched[e];
         own_edge[v] = e;
         const int pa = m->nodes[v].parent;
         if (first_child_edge[pa] < 0) first_child_edge[pa] = e;
     }
-    const int n_edges = n - 1;
     int npad_max = 16;
     for (int v = 1; v < n; ++v) {
         const int np = (int)bc_round_up(m->nodes[v].card_pa, 16);
@@ -574,7 +601,8 @@ int k3_prepare(bc_model* m) {
     // ---- operand images: per edge and block of 16 child states, T_v^T hi then lo, 64-byte swizzled rows
     size_t total = 0;
     k->edges.resize(n_edges);
-    for (int v = n - 1, e = 0; v >= 1; --v, ++e) {
+    for (int e = 0; e < n_edges; ++e) {
+        const int v = sched[e];
         const BcNodeRec& nd = m->nodes[v];
         K3Edge& E = k->edges[e];
         std::memset(&E, 0, sizeof(E));
