@@ -359,21 +359,28 @@ __global__ void __launch_bounds__(kThreads, 2) k3_kernel(const __grid_constant__
                         pre[4 * j] = t.x; pre[4 * j + 1] = t.y; pre[4 * j + 2] = t.z; pre[4 * j + 3] = t.w;
                     }
                 }
-                if (E.fan_off >= 0 && ((fm >> E.v) & 1u)) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (c0 + 4 * j < E.K) {
-                            const float4 f = *reinterpret_cast<const float4*>(s_fan + E.fan_off + c0 + 4 * j);
-                            pre[4 * j] *= f.x; pre[4 * j + 1] *= f.y; pre[4 * j + 2] *= f.z; pre[4 * j + 3] *= f.w;
-                        }
-                }
+                // (the fan-out vector is applied where the block is consumed: a multiply here would wait for the loads just
+                //  issued and undo the prefetch -- ncu: 22 % of the stall samples of the expectation rows sat on it)
             };
-            float pre[16];
+            // DENSE rows: the weights come from HBM / L2 (1.5-2 KB per query, 64 B per step and thread), one step of lead is
+            // not enough to cover that latency -- two blocks are kept in flight (pre = next step, pre2 = the one after);
+            // BITS rows come from shared memory and keep one
+            constexpr bool kTwoAhead = FMT == BC_DESC_DENSE_F32;
+            auto next_step = [&](int& e_, int& kb_) __attribute__((always_inline)) {
+                if (e_ < P.n_edges && ++kb_ >= P.edge[e_].nkb) { kb_ = 0; ++e_; }
+            };
+            float pre[16], pre2[16];
             fetch(0, 0, pre);
+            int pe = 0, pkb = 0;      // cursor of the block held in pre2 (kTwoAhead)
+            if (kTwoAhead) {
+                next_step(pe, pkb);
+                if (pe < P.n_edges) fetch(pe, pkb, pre2);
+            }
             for (int e = 0; e < P.n_edges; ++e, ++ed) {
                 const K3Edge& E = P.edge[e];
                 const bool leaf = E.col_v < 0;
                 const bool a_exact = FMT == BC_DESC_BITS && leaf && !(E.fan_off >= 0 && P.fan_mask != nullptr);
+                const bool fan_on = E.fan_off >= 0 && ((fm >> E.v) & 1u);
                 const int K = E.K, nkb = E.nkb;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const uint32_t sa = it % kStagesA, pa = (it / kStagesA) & 1u;
@@ -384,8 +391,23 @@ __global__ void __launch_bounds__(kThreads, 2) k3_kernel(const __grid_constant__
 #pragma unroll
                     for (int j = 0; j < 16; ++j) u[j] = pre[j];
                     // next step's inputs
-                    if (kb + 1 < nkb) fetch(e, kb + 1, pre);
-                    else if (e + 1 < P.n_edges) fetch(e + 1, 0, pre);
+                    if (kTwoAhead) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) pre[j] = pre2[j];
+                        next_step(pe, pkb);
+                        if (pe < P.n_edges) fetch(pe, pkb, pre2);
+                    } else {
+                        if (kb + 1 < nkb) fetch(e, kb + 1, pre);
+                        else if (e + 1 < P.n_edges) fetch(e + 1, 0, pre);
+                    }
+                    if (fan_on) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (c0 + 4 * j < K) {
+                                const float4 f = *reinterpret_cast<const float4*>(s_fan + E.fan_off + c0 + 4 * j);
+                                u[4 * j] *= f.x; u[4 * j + 1] *= f.y; u[4 * j + 2] *= f.z; u[4 * j + 3] *= f.w;
+                            }
+                    }
                     if (a_exact) {
                         // unit weights on a leaf: U is a 0/1 matrix, exact in TF32 -- no lo half
                         mbar_wait(a_empty0 + 8 * sa, pa ^ 1u);   // the MMAs that read this slot are done
