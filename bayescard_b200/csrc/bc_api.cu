@@ -313,7 +313,7 @@ extern "C" int bc_query_batch(bc_model* m, const void* desc, size_t nq, int fmt,
     // (also for models without a specialised image from ~20k dense flops: measured faster than K1 / K2 on the synthetic
     // 10 x 100 and 20 x 50 trees, profiles/r1_config4_small_domains_k3.jsonl)
     const bool has_image = m->spec_bits || m->spec_dense || m->spec_range8;
-    if (kernel == BC_KERNEL_AUTO && m->flops_dense >= (has_image ? 30000 : 20000) && m->n <= 32 && m->max_card <= 256) {
+    if (kernel == BC_KERNEL_AUTO && m->flops_dense >= (has_image ? 30000 : 20000) && m->n <= 128 && m->max_card <= 256) {
         rc = bc_query_batch(m, desc, nq, fmt, fan_mask, out, BC_KERNEL_FUSED, stream);
         if (rc != BC_ELIMIT) return rc;
     }

@@ -69,6 +69,7 @@ struct BcK3Plan {
 namespace {
 
 constexpr int kTile = 128;    // queries per CTA tile = TMEM lanes = UMMA M
+constexpr int kMaxEdges = 127; // trees of up to 128 columns
 constexpr int kBK = 16;       // child states per ring step: one 64-byte swizzle row
 constexpr int kStagesA = 3;   // A ring: U_v blocks written by the producer warps
 constexpr int kStagesB = 4;   // B ring: T_v^T blocks fetched by TMA (deeper: an L2 round trip is longer than a step)
@@ -77,7 +78,7 @@ constexpr int kProducerWarps = 4;
 constexpr int kThreads = 32 * (kProducerWarps + 2);   // + MMA issuer warp + TMA warp
 
 struct K3Params {
-    K3Edge edge[31];           // in the kernel parameter bank: uniform loads, warp-uniform control flow
+    K3Edge edge[kMaxEdges];    // in the kernel parameter bank (8 KB of the 32 KB sm_100 allows): uniform loads, warp-uniform control flow
     int n_edges;
     const uint8_t* bimg;
     const uint8_t* desc;
@@ -95,6 +96,7 @@ struct K3Params {
     int b_slot_bytes;          // 2 * npad_max * 64
     int d_col, d_stride, n_dbuf;
     int tmem_cols;
+    int mask_words;            // fan-out mask words per query
     float debias_unit;         // expected relative truncation loss per accumulating MMA (1.1e-8 measured; BC_K3_DEBIAS overrides, 0 = off)
 };
 
@@ -319,7 +321,9 @@ __global__ void __launch_bounds__(kThreads, 2) k3_kernel(const __grid_constant__
         for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
             const size_t q = (size_t)tile * kTile + tid;
             const size_t qc = q < P.nq ? q : P.nq - 1;
-            const uint32_t fm = P.fan_mask ? P.fan_mask[qc] : 0u;
+            // fan-out mask: one word per 32 columns; word 0 (the root's) is kept, the others are read per fan-out edge
+            const uint32_t* fm_row = P.fan_mask ? P.fan_mask + qc * (size_t)P.mask_words : nullptr;
+            const uint32_t fm = fm_row ? fm_row[0] : 0u;
             const float* drow = reinterpret_cast<const float*>(P.desc + qc * P.dstride);
             if (FMT == BC_DESC_BITS) {
                 const uint32_t* grow = reinterpret_cast<const uint32_t*>(P.desc + qc * P.dstride);
@@ -380,7 +384,7 @@ __global__ void __launch_bounds__(kThreads, 2) k3_kernel(const __grid_constant__
                 const K3Edge& E = P.edge[e];
                 const bool leaf = E.col_v < 0;
                 const bool a_exact = FMT == BC_DESC_BITS && leaf && !(E.fan_off >= 0 && P.fan_mask != nullptr);
-                const bool fan_on = E.fan_off >= 0 && ((fm >> E.v) & 1u);
+                const bool fan_on = E.fan_off >= 0 && fm_row != nullptr && ((fm_row[E.v >> 5] >> (E.v & 31)) & 1u);
                 const int K = E.K, nkb = E.nkb;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const uint32_t sa = it % kStagesA, pa = (it / kStagesA) & 1u;
@@ -526,7 +530,7 @@ int k3_prepare(bc_model* m) {
     };
     const int n = m->n;
     if (n < 2) return fail("single-node model");
-    if (n > 32) return fail("more than 32 columns (one fan-out mask word per query)");
+    if (n - 1 > kMaxEdges) return fail("more than 128 columns (the edge table travels in the kernel parameter bank)");
     if (m->arena.empty()) return fail("no host copy of the CPT arena");
     // ---- edge schedule: depth-first post order (children before parents, a node's edge right after its last child's),
     //      heaviest subtree first: a Lambda then only lives while its own subtree is being folded, so the live set is
@@ -735,6 +739,7 @@ int bc_k3_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32
     P.d_stride = k->npad_max;
     P.n_dbuf = k->n_dbuf;
     P.tmem_cols = k->tmem_cols;
+    P.mask_words = m->mask_words;
     P.debias_unit = 1.1e-8f;
     if (const char* e = std::getenv("BC_K3_DEBIAS")) P.debias_unit = (float)std::atof(e);
     long long grid = (long long)m->sm_count * k->ctas_per_sm;

@@ -86,7 +86,8 @@ extern "C" {
                                 where the edge shape allows, FP32 SIMT GEMM otherwise; RANGE_* rows */
 #define BC_KERNEL_GEMM_SIMT 4 /* K2 with the FP32 SIMT GEMM only (the comparator for K2)      */
 #define BC_KERNEL_FUSED 5    /* K3: whole tree per 128-query tile on the tensor cores (tcgen05 3xTF32), messages in
-                                tensor memory; models of <= 32 columns with domains <= 256 states, else BC_ELIMIT */
+                                tensor memory; trees of <= 128 columns with domains <= 256 states whose live messages fit the 512
+                                TMEM columns, else BC_ELIMIT */
 
 #define BC_KERNEL_FUSED_1CTA 6 /* K3b: K3 scheduled as one CTA per SM (two accumulator chains, two issuer warps, three
                                 producer groups, [T_hi | T_lo] concatenated); domains <= 128 states */

@@ -271,12 +271,32 @@ def test_wsparse_rows_expand_to_the_dense_rows(name):
     assert np.all(np.abs(one - 1.0) < 1e-5)
 
 
-def test_fused_kernel_declines_wide_models():
-    dm = dev_model("census")  # 68 columns: one fan-out mask word per query is not enough
-    desc = dm.gen_range_queries_host(1, 0, 256, 1, 5)
+def test_fused_kernel_wide_model_and_refusals():
+    """K3 serves trees of up to 128 columns (Census: 68 columns, three fan-out-mask words would be two) and declines, with a
+    message, what does not fit tensor memory; AUTO then falls through to the other kernels."""
+    from bayescard_b200.synth import make_tree_model, pack_ranges_u16, random_range_queries
+
+    m, dm = G.model("census"), dev_model("census")
+    desc = dm.gen_range_queries_host(1, 0, 3000, 1, 14)
+    lo, hi = unpack_ranges(m, desc)
+    ref = O.dense_tree(m, O.range_weights(m, lo, hi))
+    assert_close(dm.run_host(desc, L.DESC_RANGE_U8, None, L.KERNEL_FUSED), ref, "census through the fused kernel")
+    big = make_tree_model(10, 200, seed=10, dtype=np.float32)   # two 200-state messages + a 208-column accumulator
+    db = DeviceModel(big, device=0, specialize=False)
+    lo, hi = random_range_queries(big, 512, seed=1, kmax=5)
+    rows = pack_ranges_u16(lo, hi)
     with pytest.raises(L.BayesCardError, match="K3"):
-        dm.run_host(desc, L.DESC_RANGE_U8, None, L.KERNEL_FUSED)
-    assert dm.run_host(desc, L.DESC_RANGE_U8, None, L.KERNEL_AUTO).shape == (256,)
+        db.run_host(rows, L.DESC_RANGE_U16, None, L.KERNEL_FUSED)
+    auto = db.run_host(rows, L.DESC_RANGE_U16, None, L.KERNEL_AUTO)
+    assert_close(auto, O.dense_tree(big, O.range_weights(big, lo, hi)), "declined model through AUTO")
+    db.close()
+    wide = make_tree_model(100, 10, seed=100, dtype=np.float32)  # 100 columns x 10 states: beyond one mask word, small domains
+    dw = DeviceModel(wide, device=0, specialize=False)
+    lo, hi = random_range_queries(wide, 2000, seed=2, kmax=10)
+    rows = pack_ranges_u16(lo, hi)
+    assert_close(dw.run_host(rows, L.DESC_RANGE_U16, None, L.KERNEL_FUSED), O.dense_tree(wide, O.range_weights(wide, lo, hi)),
+                 "100-column tree through the fused kernel")
+    dw.close()
 
 
 @pytest.mark.parametrize("name", ["dmv", "census", "imdb1"])

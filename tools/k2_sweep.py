@@ -69,7 +69,7 @@ def main():
         small = card <= 256 and sum(-(-int(c) // 4) * 4 for c in m.card) * 4 < 40000 and float(rec["arena_MB"]) < 0.2
         if small:
             kernels.append(("k1", L.KERNEL_GENERIC))
-        if n_cols <= 32 and card <= 256:   # the fused tensor-core tree kernel (K3): Lambda stays in tensor memory
+        if n_cols <= 128 and card <= 256:   # the fused tensor-core tree kernel (K3): Lambda stays in tensor memory
             kernels.append(("fused", L.KERNEL_FUSED))
         rec["flops_dense_per_query"] = dm.flops_dense
         for name, k in kernels:
