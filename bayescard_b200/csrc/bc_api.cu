@@ -314,6 +314,9 @@ extern "C" int bc_query_batch(bc_model* m, const void* desc, size_t nq, int fmt,
     // 10 x 100 and 20 x 50 trees, profiles/r1_config4_small_domains_k3.jsonl)
     const bool has_image = m->spec_bits || m->spec_dense || m->spec_range8;
     if (kernel == BC_KERNEL_AUTO && m->flops_dense >= (has_image ? 30000 : 20000) && m->n <= 128 && m->max_card <= 256) {
+        // a handful of queries (the scalar drop-in call is B = 1): the warp-per-query kernel answers in 33 us where the
+        // tile kernel needs 46 us and the straight-line kernel 94 us (400 KB of cold code); tools/latency_probe.py
+        if (nq <= 32) return bc_k1_launch(m, desc, nq, fmt, fan_mask, out, st);
         rc = bc_query_batch(m, desc, nq, fmt, fan_mask, out, BC_KERNEL_FUSED, stream);
         if (rc != BC_ELIMIT) return rc;
     }

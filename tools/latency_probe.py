@@ -9,10 +9,14 @@ for name in ("census","imdb1"):
     pc=PredicateCompiler(m)
     from bayescard_b200.decode import unpack_ranges
     lo,hi=unpack_ranges(m,host); bits=pc.pack_bits(lo,hi)
-    for fmt,desc in ((L.DESC_RANGE_U8,host),(L.DESC_BITS,bits)):
-        for _ in range(50): dm.run_host(desc[:1], fmt)
+    for kname,kernel in (('auto',L.KERNEL_AUTO),('spec',L.KERNEL_SPEC),('fused',L.KERNEL_FUSED),('generic',L.KERNEL_GENERIC)):
+      for fmt,desc in ((L.DESC_RANGE_U8,host),(L.DESC_BITS,bits)):
+        try:
+            for _ in range(50): dm.run_host(desc[:1], fmt, None, kernel)
+        except Exception as e:
+            print(name, kname, fmt, 'n/a'); continue
         ts=[]
         for i in range(300):
-            t=time.perf_counter(); dm.run_host(desc[i%64:i%64+1], fmt); ts.append(time.perf_counter()-t)
-        print(name, fmt, 'run_host B=1 p50 us', round(np.median(ts)*1e6,1), 'p99', round(np.percentile(ts,99)*1e6,1))
+            t=time.perf_counter(); dm.run_host(desc[i%64:i%64+1], fmt, None, kernel); ts.append(time.perf_counter()-t)
+        print(name, kname, fmt, 'run_host B=1 p50 us', round(np.median(ts)*1e6,1), 'p99', round(np.percentile(ts,99)*1e6,1))
     dm.close()
