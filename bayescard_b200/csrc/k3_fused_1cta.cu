@@ -634,6 +634,10 @@ int bc_k3b_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint3
         bc_set_error("the fused kernel reads BITS or DENSE_F32 rows (convert range rows with bc_convert_desc)");
         return BC_EINVAL;
     }
+    if (reinterpret_cast<uintptr_t>(desc) & 15u) {
+        bc_set_error("descriptor rows are read with 16-byte loads: the buffer must be 16-byte aligned");
+        return BC_EINVAL;
+    }
     {
         std::lock_guard<std::mutex> g(m->k3b_mu);
         int rc = k3b_prepare(m);
