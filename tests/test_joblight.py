@@ -55,6 +55,22 @@ def test_parse_and_factor_shapes():
         parse_job_light("SELECT COUNT(*) FROM title t,name n WHERE t.id=n.id")
 
 
+def test_operators_and_single_join():
+    js = {i: float(G.model(f"imdb{i}").nrows) for i in range(5)}
+    tq = plan_star_query("SELECT COUNT(*) FROM title t,cast_info ci WHERE t.id=ci.movie_id AND t.kind_id=1 AND ci.role_id>=2 AND "
+                         "ci.role_id<=4 AND t.production_year<=2000;", js)
+    assert len(tq) == 2 and tq[0] == js[2] and tq[1]["expectation"] == [] and not tq[1]["inverse"]
+    assert tq[1]["query"] == {"title.kind_id": 1.0, "title.production_year": (-np.inf, 2000.0), "cast_info.role_id": (2.0, 4.0),
+                              "cast_info.cast_info_nn": 1}
+    # the planner's factor lists go through the reference-format glue unchanged (CPU port of parse_query_all / cardinality)
+    est = _oracle_estimates([tq])
+    assert np.isfinite(est[0]) and est[0] >= 1.0
+    # conditions only on title: every joined table contributes its fan-out, no nominator / denominator pair survives
+    tq = plan_star_query("SELECT COUNT(*) FROM title t,movie_keyword mk,movie_info mi WHERE t.id=mk.movie_id AND t.id=mi.movie_id "
+                         "AND t.production_year>1990", js)
+    assert len(tq) == 2 and tq[1]["bn_index"] in (1, 3) and len(tq[1]["expectation"]) == 1
+
+
 def test_q_errors_match_the_published_row():
     sqls, true, paper = _workload()
     js = {i: float(G.model(f"imdb{i}").nrows) for i in range(5)}
