@@ -366,20 +366,10 @@ __global__ void __launch_bounds__(kThreads, 2) k3_kernel(const __grid_constant__
                 // (the fan-out vector is applied where the block is consumed: a multiply here would wait for the loads just
                 //  issued and undo the prefetch -- ncu: 22 % of the stall samples of the expectation rows sat on it)
             };
-            // DENSE rows: the weights come from HBM / L2 (1.5-2 KB per query, 64 B per step and thread), one step of lead is
-            // not enough to cover that latency -- two blocks are kept in flight (pre = next step, pre2 = the one after);
-            // BITS rows come from shared memory and keep one
-            constexpr bool kTwoAhead = FMT == BC_DESC_DENSE_F32;
-            auto next_step = [&](int& e_, int& kb_) __attribute__((always_inline)) {
-                if (e_ < P.n_edges && ++kb_ >= P.edge[e_].nkb) { kb_ = 0; ++e_; }
-            };
-            float pre[16], pre2[16];
+            // (two blocks in flight for DENSE rows were measured too: +3 % without fan-out columns, -4...-9 % on the fan-out
+            //  weighted expectation factors this kernel exists for -- one step of lead it is; tools/runs/_gpu_run59.sh)
+            float pre[16];
             fetch(0, 0, pre);
-            int pe = 0, pkb = 0;      // cursor of the block held in pre2 (kTwoAhead)
-            if (kTwoAhead) {
-                next_step(pe, pkb);
-                if (pe < P.n_edges) fetch(pe, pkb, pre2);
-            }
             for (int e = 0; e < P.n_edges; ++e, ++ed) {
                 const K3Edge& E = P.edge[e];
                 const bool leaf = E.col_v < 0;
@@ -395,15 +385,8 @@ __global__ void __launch_bounds__(kThreads, 2) k3_kernel(const __grid_constant__
 #pragma unroll
                     for (int j = 0; j < 16; ++j) u[j] = pre[j];
                     // next step's inputs
-                    if (kTwoAhead) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) pre[j] = pre2[j];
-                        next_step(pe, pkb);
-                        if (pe < P.n_edges) fetch(pe, pkb, pre2);
-                    } else {
-                        if (kb + 1 < nkb) fetch(e, kb + 1, pre);
-                        else if (e + 1 < P.n_edges) fetch(e + 1, 0, pre);
-                    }
+                    if (kb + 1 < nkb) fetch(e, kb + 1, pre);
+                    else if (e + 1 < P.n_edges) fetch(e + 1, 0, pre);
                     if (fan_on) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
