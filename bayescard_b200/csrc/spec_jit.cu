@@ -34,17 +34,7 @@ int bc_spec_attach(bc_model* m, const void* image, size_t bytes) {
         cudaGetLastError();
         return BC_ECOMPILE;
     }
-    // an image may hold any subset of the entry points; formats without one use the generic kernel
-    cudaKernel_t kr = nullptr, kd = nullptr, kb = nullptr;
-    if (cudaLibraryGetKernel(&kd, lib, "bc_spec_dense") != cudaSuccess) { kd = nullptr; cudaGetLastError(); }
-    if (cudaLibraryGetKernel(&kr, lib, "bc_spec_range8") != cudaSuccess) { kr = nullptr; cudaGetLastError(); }
-    if (cudaLibraryGetKernel(&kb, lib, "bc_spec_bits") != cudaSuccess) { kb = nullptr; cudaGetLastError(); }
-    if (!kd && !kr && !kb) {
-        bc_set_error("specialised image has none of bc_spec_bits / bc_spec_range8 / bc_spec_dense");
-        cudaLibraryUnload(lib);
-        return BC_ECUDA;
-    }
-    // geometry travels with the image: {threads per CTA, queries per thread and trip, version, 0}
+    // geometry travels with the image: {threads per CTA, queries per thread and trip, generator version, 0}
     uint32_t meta[4] = {128, 1, 0, 0};
     void* dptr = nullptr;
     size_t gbytes = 0;
@@ -52,6 +42,18 @@ int bc_spec_attach(bc_model* m, const void* image, size_t bytes) {
         BC_CUDA_CHECK(cudaMemcpy(meta, dptr, sizeof(meta), cudaMemcpyDeviceToHost));
     else
         cudaGetLastError();
+    // an image may hold any subset of the entry points; formats without one use the generic kernel.  Generator versions
+    // >= 5 emit no RANGE_U8 entry point (range rows are converted to BITS rows): it is only looked up in older images, so
+    // that attaching a current image makes no failing API call (keeps compute-sanitizer's API-error report empty)
+    cudaKernel_t kr = nullptr, kd = nullptr, kb = nullptr;
+    if (cudaLibraryGetKernel(&kd, lib, "bc_spec_dense") != cudaSuccess) { kd = nullptr; cudaGetLastError(); }
+    if (meta[2] < 5 && cudaLibraryGetKernel(&kr, lib, "bc_spec_range8") != cudaSuccess) { kr = nullptr; cudaGetLastError(); }
+    if (cudaLibraryGetKernel(&kb, lib, "bc_spec_bits") != cudaSuccess) { kb = nullptr; cudaGetLastError(); }
+    if (!kd && !kr && !kb) {
+        bc_set_error("specialised image has none of bc_spec_bits / bc_spec_range8 / bc_spec_dense");
+        cudaLibraryUnload(lib);
+        return BC_ECUDA;
+    }
     if (meta[0] == 0 || meta[0] > 1024 || meta[0] % 32) {
         bc_set_error("specialised image declares %u threads per CTA", meta[0]);
         cudaLibraryUnload(lib);
