@@ -658,11 +658,14 @@ int k3_prepare(bc_model* m) {
     const size_t fan_floats = (size_t)bc_round_up((int64_t)m->fan.size(), 4);
     const size_t fixed = (size_t)m->bits_words * kTile * 4 + fan_floats * 4 + 256 /* nibble table */ +                          256 /* barriers */ + 1024 /* alignment */;
     k->smem = (size_t)kStagesA * 2 * kABytes + (size_t)kStagesB * npad_max * 128 + fixed;
-    if (k->smem > (size_t)m->smem_optin) return fail("operand rings exceed shared memory");
+    const size_t smem_optin = m->device >= 0 ? (size_t)m->smem_optin : (size_t)227 * 1024;   // host-only model: the sm_100 value
+    if (k->smem > smem_optin) return fail("operand rings exceed shared memory");
     k->ctas_per_sm = (tmem_cols <= 256 && 2 * (k->smem + 1024) <= 228 * 1024) ? 2 : 1;
-    if (k->ctas_per_sm == 1) k->smem = (size_t)m->smem_optin;   // a second CTA would only spin in tcgen05.alloc
-    BC_CUDA_CHECK(cudaMalloc(&k->d_bimg, total));
-    BC_CUDA_CHECK(cudaMemcpy(k->d_bimg, img.data(), total, cudaMemcpyHostToDevice));
+    if (k->ctas_per_sm == 1) k->smem = smem_optin;   // a second CTA would only spin in tcgen05.alloc
+    if (m->device >= 0) {   // (a host-only model keeps the plan for inspection: bc_model_fused_plan)
+        BC_CUDA_CHECK(cudaMalloc(&k->d_bimg, total));
+        BC_CUDA_CHECK(cudaMemcpy(k->d_bimg, img.data(), total, cudaMemcpyHostToDevice));
+    }
     return BC_OK;
 }
 
@@ -733,6 +736,33 @@ int bc_k3_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32
     if (grid > P.n_tiles) grid = P.n_tiles;
     if (fmt == BC_DESC_BITS) return k3_launch_fmt<BC_DESC_BITS>(m, P, (int)grid, st);
     return k3_launch_fmt<BC_DESC_DENSE_F32>(m, P, (int)grid, st);
+}
+
+extern "C" int bc_model_fused_plan(bc_model* m, int32_t* info, int32_t* edges, size_t edges_capacity) {
+    if (!m || !info) { bc_set_error("model/info is NULL"); return BC_EINVAL; }
+    {
+        std::lock_guard<std::mutex> g(m->k3_mu);
+        int rc = k3_prepare(m);
+        if (rc) return rc;
+    }
+    const BcK3Plan* k = m->k3;
+    info[0] = (int32_t)k->edges.size();
+    info[1] = k->tmem_cols;
+    info[2] = k->ctas_per_sm;
+    info[3] = (int32_t)k->smem;
+    info[4] = k->d_col;
+    info[5] = k->npad_max * k->n_dbuf;   // accumulator columns [d_col, d_col + this)
+    info[6] = k->root_col;
+    info[7] = (int32_t)(k->bimg_bytes >> 10);
+    if (edges) {
+        if (edges_capacity < k->edges.size()) { bc_set_error("edges buffer too small"); return BC_EINVAL; }
+        for (size_t e = 0; e < k->edges.size(); ++e) {
+            const K3Edge& E = k->edges[e];
+            int32_t* o = edges + 8 * e;
+            o[0] = E.v; o[1] = E.K; o[2] = E.N; o[3] = E.n_pad; o[4] = E.col_v; o[5] = E.col_pa; o[6] = E.first; o[7] = E.nkb;
+        }
+    }
+    return BC_OK;
 }
 
 void bc_k3_free(bc_model* m) {

@@ -132,6 +132,14 @@ BC_API int64_t bc_model_flops_dense(const bc_model* m);
  * the generic kernel keeps working. */
 BC_API int bc_model_specialize(bc_model* m, const char* cache_dir);
 BC_API int bc_model_has_spec(const bc_model* m);
+/* Plan of the fused tensor-core kernel (K3) for this model, for inspection and tests (works on host-only models):
+ *   info[8]  = {edges, TMEM columns allocated per CTA, CTAs per SM, shared memory bytes per CTA, first accumulator
+ *               column, accumulator columns, column of the root's message, operand images in KB}
+ *   edges    = per edge in schedule order {child, card(child), card(parent), parent states padded to 16, TMEM column of
+ *               the child's message (-1: leaf), TMEM column of the parent's message, first message into the parent,
+ *               ring steps}; may be NULL.
+ * BC_ELIMIT (with the reason in bc_last_error) when K3 does not serve the model. */
+BC_API int bc_model_fused_plan(bc_model* m, int32_t* info, int32_t* edges, size_t edges_capacity);
 /* Write the generated CUDA source of the specialised kernel (host only, no GPU needed; used by the
  * ahead-of-time build and by tests).  Returns the number of bytes needed including the NUL. */
 BC_API int64_t bc_model_spec_source(const bc_model* m, char* buf, size_t buf_bytes);

@@ -325,6 +325,70 @@ def test_wsparse_packer_round_trip(name):
         dense_to_wsparse(m, np.zeros((2, dense.shape[1] + 4), dtype=np.float32))
 
 
+def _fused_plan(dm):
+    info = np.zeros(8, dtype=np.int32)
+    rc = L.lib().bc_model_fused_plan(dm._h, info.ctypes.data, None, 0)
+    if rc != 0:
+        return None, None, L.lib().bc_last_error().decode()
+    edges = np.zeros((int(info[0]), 8), dtype=np.int32)
+    L.check(L.lib().bc_model_fused_plan(dm._h, info.ctypes.data, edges.ctypes.data, edges.shape[0]))
+    return info, edges, ""
+
+
+@pytest.mark.parametrize("name", G.MODEL_NAMES)
+def test_fused_kernel_plan_invariants(name):
+    """K3's host-side plan (edge schedule + tensor-memory columns), checked without a GPU on a host-only model: every edge once,
+    children before parents, exactly one `first` message per internal node, and no two allocations that are alive at the
+    same edge (the accumulators; a message from its first child's edge to its own edge, the root's to the end) share a column."""
+    from bayescard_b200.synth import make_tree_model
+
+    m = G.model(name)
+    dm = DeviceModel(m, device=-1, specialize=False)
+    info, edges, why = _fused_plan(dm)
+    assert info is not None, why
+    n_edges, tmem_cols, ctas, smem, d_col, d_cols, root_col, _ = (int(x) for x in info)
+    assert n_edges == m.n_nodes - 1 and tmem_cols in (32, 64, 128, 256, 512) and ctas in (1, 2) and smem <= 227 * 1024
+    assert ctas == (1 if name == "imdb3" else 2)   # IMDB-3 keeps three wide messages alive: 352 columns
+    child = edges[:, 0]
+    assert sorted(child.tolist()) == list(range(1, m.n_nodes))
+    own = {int(v): e for e, v in enumerate(child)}
+    parent = {int(v): int(m.parent[v]) for v in child}
+    first_seen = {}
+    for e, (v, K, N, n_pad, col_v, col_pa, first, nkb) in enumerate(edges.tolist()):
+        pa = parent[v]
+        assert K == int(m.card[v]) and N == int(m.card[pa]) and n_pad == -(-N // 16) * 16 and nkb == -(-K // 16)
+        assert pa == 0 or own[pa] > e                      # children before parents
+        assert bool(first) == (pa not in first_seen)       # the first message overwrites, the others multiply
+        first_seen.setdefault(pa, e)
+        has_kids = v in first_seen
+        assert (col_v >= 0) == has_kids                    # a leaf has no message in tensor memory
+        if has_kids:
+            assert first_seen[v] < e                       # all of v's children are done
+    assert root_col == int(edges[own[next(v for v in own if parent[v] == 0)], 5])
+    # column ranges alive at each edge
+    spans = [("D", d_col, d_col + d_cols, 0, n_edges)]
+    col_of = {parent[int(r[0])]: int(r[5]) for r in edges}
+    for node, start in first_seen.items():
+        end = n_edges if node == 0 else own[node]
+        width = -(-int(m.card[node]) // 8) * 8
+        spans.append((node, col_of[node], col_of[node] + width, start, end))
+    for i, (a, a0, a1, as_, ae) in enumerate(spans):
+        assert 0 <= a0 < a1 <= tmem_cols, (a, a0, a1)
+        for b, b0, b1, bs, be in spans[i + 1:]:
+            if as_ <= be and bs <= ae:                     # lifetimes overlap
+                assert a1 <= b0 or b1 <= a0, (a, b)
+    dm.close()
+    # a model that does not fit is declined with a reason; a wide tree with small domains is planned
+    big = DeviceModel(make_tree_model(10, 200, seed=10, dtype=np.float32), device=-1, specialize=False)
+    info, _, why = _fused_plan(big)
+    assert info is None and "tensor memory" in why
+    big.close()
+    wide = DeviceModel(make_tree_model(100, 10, seed=100, dtype=np.float32), device=-1, specialize=False)
+    info, edges, why = _fused_plan(wide)
+    assert info is not None and int(info[0]) == 99, why
+    wide.close()
+
+
 def test_shard_split():
     assert ShardedModel.split(10, 4) == [(0, 2), (2, 4), (4, 6), (6, 10)]
     assert ShardedModel.split(3, 8)[-1] == (0, 3)
