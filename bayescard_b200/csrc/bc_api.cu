@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <new>
 
 #include "bc_internal.h"
 
@@ -83,8 +84,13 @@ extern "C" int bc_model_create(int device, int n_nodes, const int32_t* parent, c
         bc_set_error("bad model arguments (n_nodes=%d)", n_nodes);
         return BC_EINVAL;
     }
+    if (arena_floats == 0 || arena_floats > (size_t(1) << 40) || fan_floats > (size_t(1) << 40)) {
+        bc_set_error("implausible arena size (%zu CPT floats, %zu fan-out floats)", arena_floats, fan_floats);
+        return BC_EINVAL;
+    }
     bc_model* m = new (std::nothrow) bc_model();
     if (!m) { bc_set_error("out of host memory"); return BC_ENOMEM; }
+    try {   // std::vector allocations below must not throw across the C ABI
     m->device = device;
     m->n = n_nodes;
     m->nodes.resize(n_nodes);
@@ -207,6 +213,11 @@ extern "C" int bc_model_create(int device, int n_nodes, const int32_t* parent, c
         CK(cudaMemcpy(m->d_ent_node, m->ent_node.data(), m->ent_node.size() * sizeof(uint16_t),
                       cudaMemcpyHostToDevice));
 #undef CK
+    }
+    } catch (const std::bad_alloc&) {
+        bc_set_error("out of host memory while building the model");
+        bc_model_destroy(m);
+        return BC_ENOMEM;
     }
     *out = m;
     return BC_OK;
@@ -378,6 +389,9 @@ static int pipe_ensure(bc_model* m, size_t chunk_q, size_t desc_stride) {
     BcHostPipe* p = m->pipe;
     const size_t need_desc = chunk_q * desc_stride, need_mask = chunk_q * m->mask_words * 4;
     if (need_desc > p->cap_desc || need_mask > p->cap_mask || chunk_q > p->cap_q) {
+        // capacities are zeroed first and set only after every slot is allocated: a cudaMalloc that fails half way must
+        // not leave NULL slots behind capacities that a later, smaller request would pass
+        p->cap_desc = 0; p->cap_mask = 0; p->cap_q = 0;
         for (int i = 0; i < BcHostPipe::kSlots; ++i) {
             cudaFree(p->d_desc[i]); cudaFree(p->d_mask[i]); cudaFree(p->d_out[i]);
             cudaFreeHost(p->h_desc[i]); cudaFreeHost(p->h_mask[i]); cudaFreeHost(p->h_out[i]);
@@ -391,6 +405,21 @@ static int pipe_ensure(bc_model* m, size_t chunk_q, size_t desc_stride) {
     }
     return BC_OK;
 }
+
+// An error return in the middle of a pipelined host call must not leave asynchronous copies running against the caller's
+// pinned buffers (the caller may free them on error): the guard drains the three pipe streams on every exit path that
+// did not reach the final synchronisation.
+struct PipeDrain {
+    BcHostPipe* p;
+    bool armed = false;
+    explicit PipeDrain(BcHostPipe* pipe) : p(pipe) {}
+    ~PipeDrain() {
+        if (!armed || !p) return;
+        cudaStreamSynchronize(p->s_in);
+        cudaStreamSynchronize(p->s_k);
+        cudaStreamSynchronize(p->s_out);
+    }
+};
 
 static bool is_pinned(const void* ptr) {
     cudaPointerAttributes a{};
@@ -415,6 +444,7 @@ extern "C" int bc_query_batch_host(bc_model* m, const void* desc, size_t nq, int
     rc = pipe_ensure(m, chunk, stride);
     if (rc) return rc;
     BcHostPipe* p = m->pipe;
+    PipeDrain drain(p);
     const bool pin_desc = is_pinned(desc), pin_out = is_pinned(out), pin_mask = !fan_mask || is_pinned(fan_mask);
     auto ensure_host = [&](void** h, size_t bytes) -> int {
         if (!*h) BC_CUDA_CHECK(cudaHostAlloc(h, bytes, cudaHostAllocDefault));
@@ -438,6 +468,7 @@ extern "C" int bc_query_batch_host(bc_model* m, const void* desc, size_t nq, int
             std::memcpy(p->h_desc[s], src, cq * stride);
             src = static_cast<const unsigned char*>(p->h_desc[s]);
         }
+        drain.armed = true;
         BC_CUDA_CHECK(cudaMemcpyAsync(p->d_desc[s], src, cq * stride, cudaMemcpyHostToDevice, p->s_in));
         const uint32_t* dmask = nullptr;
         if (fan_mask) {
@@ -467,6 +498,7 @@ extern "C" int bc_query_batch_host(bc_model* m, const void* desc, size_t nq, int
         BC_CUDA_CHECK(cudaStreamWaitEvent(p->s_in, p->ev_out[s], 0));
     }
     BC_CUDA_CHECK(cudaStreamSynchronize(p->s_out));
+    drain.armed = false;   // s_out waited for every kernel and copy of the call
     if (!pin_out) {
         const size_t first = nchunks > (size_t)BcHostPipe::kSlots ? nchunks - BcHostPipe::kSlots : 0;
         for (size_t ci = first; ci < nchunks; ++ci) {
@@ -503,6 +535,7 @@ static int sparse_ensure(bc_model* m, size_t chunk_q, size_t chunk_entries) {
     if (rc) return rc;
     BcHostPipe* p = m->pipe;
     if (chunk_q > p->cap_sq) {
+        p->cap_sq = 0;
         for (int i = 0; i < BcHostPipe::kSlots; ++i) {
             cudaFree(p->d_rowoff[i]); cudaFree(p->d_bits[i]);
             cudaFreeHost(p->h_rowoff[i]);
@@ -513,6 +546,7 @@ static int sparse_ensure(bc_model* m, size_t chunk_q, size_t chunk_entries) {
         p->cap_sq = chunk_q;
     }
     if (chunk_entries > p->cap_entries) {
+        p->cap_entries = 0;
         for (int i = 0; i < BcHostPipe::kSlots; ++i) {
             cudaFree(p->d_entries[i]);
             cudaFreeHost(p->h_entries[i]);
@@ -523,6 +557,7 @@ static int sparse_ensure(bc_model* m, size_t chunk_q, size_t chunk_entries) {
     }
     const size_t need_mask = chunk_q * m->mask_words * 4;
     if (chunk_q > p->cap_q || need_mask > p->cap_mask) {
+        p->cap_q = 0; p->cap_mask = 0; p->cap_desc = 0;
         for (int i = 0; i < BcHostPipe::kSlots; ++i) {
             cudaFree(p->d_mask[i]); cudaFree(p->d_out[i]);
             cudaFreeHost(p->h_mask[i]); cudaFreeHost(p->h_out[i]);
@@ -569,7 +604,9 @@ static int sparse_host_impl(bc_model* m, const uint32_t* row_off, const uint32_t
     int rc = sparse_ensure(m, chunk, max_entries);
     if (rc) return rc;
     BcHostPipe* p = m->pipe;
+    PipeDrain drain(p);
     if (weighted && chunk > p->cap_wq) {
+        p->cap_wq = 0;
         for (int i = 0; i < BcHostPipe::kSlots; ++i) {
             cudaFree(p->d_wdense[i]);
             p->d_wdense[i] = nullptr;
@@ -598,6 +635,7 @@ static int sparse_host_impl(bc_model* m, const uint32_t* row_off, const uint32_t
             std::memcpy(p->h_rowoff[s], osrc, (cq + 1) * 4);
             osrc = p->h_rowoff[s];
         }
+        drain.armed = true;
         BC_CUDA_CHECK(cudaMemcpyAsync(p->d_rowoff[s], osrc, (cq + 1) * 4, cudaMemcpyHostToDevice, p->s_in));
         if (ne) {
             const uint32_t* esrc = entries + e0;
@@ -644,6 +682,7 @@ static int sparse_host_impl(bc_model* m, const uint32_t* row_off, const uint32_t
         BC_CUDA_CHECK(cudaStreamWaitEvent(p->s_in, p->ev_out[s], 0));
     }
     BC_CUDA_CHECK(cudaStreamSynchronize(p->s_out));
+    drain.armed = false;   // s_out waited for every kernel and copy of the call
     if (!pin_out) {
         const size_t first = nchunks > (size_t)BcHostPipe::kSlots ? nchunks - BcHostPipe::kSlots : 0;
         for (size_t ci = first; ci < nchunks; ++ci) {

@@ -60,17 +60,19 @@ extern "C" int bc_model_create_from_file(int device, const char* path, bc_model*
         bc_set_error("%s: %s", path, why);
         rc = BC_EINVAL;
     };
-    auto inside = [&](uint64_t off, uint64_t len, uint64_t align) {
-        return off % align == 0 && off <= bytes && len <= bytes - off;
+    // counts are checked BEFORE they are multiplied: 4 * arena_floats wraps in uint64 for a crafted count
+    auto inside = [&](uint64_t off, uint64_t count, uint64_t elem, uint64_t align) {
+        return off % align == 0 && off <= bytes && count <= (bytes - off) / elem;
     };
     const uint64_t n = h.n_nodes;
     if (std::memcmp(h.magic, "BCB200M\0", 8) != 0) bad("bad magic (not a bayescard_b200 flat model file)");
     else if (h.version != 1) bad("unsupported flat model file version");
     else if (h.file_bytes != bytes) bad("truncated or padded file (size differs from the header)");
     else if (n == 0 || n > (1u << 20)) bad("implausible node count");
-    else if (!inside(h.off_parent, 4 * n, 4) || !inside(h.off_card, 4 * n, 4) || !inside(h.off_cpt_off, 8 * n, 8) ||
-             !inside(h.off_stride, 4 * n, 4) || !inside(h.off_fan_off, 8 * n, 8) || !inside(h.off_arena, 4 * h.arena_floats, 16) ||
-             !inside(h.off_fan, 4 * h.fan_floats, 16) || !inside(h.off_cpt64, 8 * h.cpt64_doubles, 8) || !inside(h.off_meta, h.meta_bytes, 1))
+    else if (!inside(h.off_parent, n, 4, 4) || !inside(h.off_card, n, 4, 4) || !inside(h.off_cpt_off, n, 8, 8) ||
+             !inside(h.off_stride, n, 4, 4) || !inside(h.off_fan_off, n, 8, 8) || !inside(h.off_arena, h.arena_floats, 4, 16) ||
+             !inside(h.off_fan, h.fan_floats, 4, 16) || !inside(h.off_cpt64, h.cpt64_doubles, 8, 8) ||
+             !inside(h.off_meta, h.meta_bytes, 1, 1))
         bad("a section lies outside the file");
     if (rc == BC_OK)
         rc = bc_model_create(device, (int)n, reinterpret_cast<const int32_t*>(base + h.off_parent),

@@ -35,6 +35,7 @@
 // Algorithmic work per query = flops_dense(model) (every CPT entry once); HBM traffic = descriptor row + 4 B.
 #include <algorithm>
 #include <cstring>
+#include <memory>
 
 #include "bc_internal.h"
 
@@ -503,11 +504,18 @@ uint32_t host_tf32_hi(float x) {
 }
 
 int k3_prepare(bc_model* m) {
-    if (m->k3) return m->k3->failed ? BC_ELIMIT : BC_OK;
-    BcK3Plan* k = new BcK3Plan();
-    m->k3 = k;
+    if (m->k3) {
+        if (m->k3->failed) bc_set_error("fused tensor-core kernel (K3) does not serve this model");
+        return m->k3->failed ? BC_ELIMIT : BC_OK;
+    }
+    // the plan is built locally and published to m->k3 only when it is complete: a structural "does not serve" verdict is
+    // published (failed = 1, so it is not recomputed); a CUDA error while uploading the operand image publishes nothing, so
+    // that the next call retries instead of launching with a NULL image
+    std::unique_ptr<BcK3Plan> plan(new BcK3Plan());
+    BcK3Plan* k = plan.get();
     auto fail = [&](const char* why) {
         k->failed = 1;
+        m->k3 = plan.release();
         bc_set_error("fused tensor-core kernel (K3) does not serve this model: %s", why);
         return BC_ELIMIT;
     };
@@ -565,7 +573,8 @@ int k3_prepare(bc_model* m) {
     for (int v = 0; v < n; ++v)
         if (first_child_edge[v] >= 0) order.push_back(v);
     std::sort(order.begin(), order.end(), [&](int a, int b) { return first_child_edge[a] < first_child_edge[b]; });
-    auto assign = [&](int n_dbuf) -> int {   // columns used, or -1
+    auto assign = [&](int n_dbuf) -> int {   // columns used, or -1 (col[] is only written when every node found a place)
+        std::vector<int> place(n, -1);
         const int units_total = 512 / 8;
         std::vector<int> busy_until(units_total, -1);   // last edge index that uses the unit
         const int d_units = n_dbuf * npad_max / 8;
@@ -584,9 +593,10 @@ int k3_prepare(bc_model* m) {
             }
             if (at < 0) return -1;
             for (int u = at; u < at + need; ++u) busy_until[u] = end;
-            col[v] = at * 8;
+            place[v] = at * 8;
             if (at + need > units_used) units_used = at + need;
         }
+        col = place;
         return units_used * 8;
     };
     int n_dbuf = 2, used = assign(2);
@@ -664,8 +674,14 @@ int k3_prepare(bc_model* m) {
     if (k->ctas_per_sm == 1) k->smem = smem_optin;   // a second CTA would only spin in tcgen05.alloc
     if (m->device >= 0) {   // (a host-only model keeps the plan for inspection: bc_model_fused_plan)
         BC_CUDA_CHECK(cudaMalloc(&k->d_bimg, total));
-        BC_CUDA_CHECK(cudaMemcpy(k->d_bimg, img.data(), total, cudaMemcpyHostToDevice));
+        const cudaError_t ce = cudaMemcpy(k->d_bimg, img.data(), total, cudaMemcpyHostToDevice);
+        if (ce != cudaSuccess) {
+            cudaFree(k->d_bimg);
+            bc_set_error("upload of the K3 operand image failed: %s", cudaGetErrorString(ce));
+            return BC_ECUDA;
+        }
     }
+    m->k3 = plan.release();
     return BC_OK;
 }
 

@@ -422,7 +422,11 @@ def dense_to_wsparse(tm: TreeModel, dense: np.ndarray):
         l = np.where(anynz, card - 1 - nz[:, ::-1].argmax(axis=1), -1)
         first[:, v] = f
         count[:, v] = np.where(con, l - f + 1, -1)
-    run_words = np.where(count >= 0, count + 1, 0)                       # header + weights per (row, column)
+    # the run length is an 8-bit field: a run of 256 states (a 256-state column whose first and last weights are
+    # non-zero) is sent as a run of 255 plus a one-state continuation run (bit 15)
+    tail = np.where(count > 255, count - 255, 0)
+    head = count - tail
+    run_words = np.where(count >= 0, head + 1, 0) + np.where(tail > 0, tail + 1, 0)   # headers + weights per (row, column)
     row_len = run_words.sum(axis=1)
     row_off = np.zeros(nq + 1, dtype=np.int64)
     np.cumsum(row_len, out=row_off[1:])
@@ -434,12 +438,20 @@ def dense_to_wsparse(tm: TreeModel, dense: np.ndarray):
         rows = np.nonzero(count[:, v] >= 0)[0]
         if rows.size == 0:
             continue
-        c, f, st = count[rows, v], first[rows, v], col_start[rows, v]
+        c, f, st, t = head[rows, v], first[rows, v], col_start[rows, v], tail[rows, v]
         words[st] = (np.uint32(v) | (f.astype(np.uint32) << np.uint32(16)) | (c.astype(np.uint32) << np.uint32(24)))
         seg = dense[:, off[v]: off[v] + int(tm.card[v])].view(np.uint32)
         for j in range(int(c.max()) if c.size else 0):   # at most card(v) vectorised passes
             m = c > j
             words[st[m] + 1 + j] = seg[rows[m], f[m] + j]
+        if t.any():
+            m = t > 0
+            st2, f2 = st[m] + 1 + c[m], f[m] + c[m]
+            words[st2] = (np.uint32(v) | np.uint32(1 << 15) | (f2.astype(np.uint32) << np.uint32(16))
+                          | (t[m].astype(np.uint32) << np.uint32(24)))
+            for j in range(int(t.max())):
+                mm = t[m] > j
+                words[st2[mm] + 1 + j] = seg[rows[m][mm], f2[mm] + j]
     return row_off.astype(np.uint32), words
 
 

@@ -77,7 +77,17 @@ _CLASS_MAP = {
     ("networkx.classes.reportviews", "InDegreeView"): _ViewBag,
 }
 
-_ALLOWED_PREFIXES = ("numpy", "collections", "builtins", "copyreg", "_codecs")
+# Explicit (module, name) allow-list: data containers and the numpy array/scalar reconstructors only.  A prefix test
+# on the module would let builtins.eval / exec / getattr / __import__ through, i.e. arbitrary code execution.
+_ALLOWED_GLOBALS = frozenset(
+    [("builtins", n) for n in ("set", "frozenset", "dict", "list", "tuple", "slice", "complex", "bytearray",
+                               "int", "float", "bool", "str", "bytes", "range")]
+    + [(m, n) for m in ("numpy.core.multiarray", "numpy._core.multiarray") for n in ("_reconstruct", "scalar")]
+    + [("numpy", "ndarray"), ("numpy", "dtype"),
+       ("numpy.core.numeric", "_frombuffer"), ("numpy._core.numeric", "_frombuffer"),
+       ("collections", "OrderedDict"), ("collections", "defaultdict"),
+       ("copyreg", "_reconstructor"), ("_codecs", "encode")]
+)
 
 
 class _Interval:
@@ -99,7 +109,7 @@ class RestrictedUnpickler(pickle.Unpickler):
                 return Interval
             except Exception:  # pragma: no cover - pandas is in the image
                 return _Interval
-        if module.split(".")[0] in _ALLOWED_PREFIXES:
+        if key in _ALLOWED_GLOBALS:
             return super().find_class(module, name)
         raise pickle.UnpicklingError(f"class {module}.{name} is not allowed in a BayesCard model pickle")
 

@@ -76,6 +76,25 @@ def test_restricted_unpickler_rejects_foreign_classes():
     with pytest.raises(pickle.UnpicklingError):
         load_pickle(blob)
 
+    class _Evil:  # builtins.eval through __reduce__: a module-prefix allow-list would run it
+        def __init__(self, fn, args):
+            self.fn, self.args = fn, args
+
+        def __reduce__(self):
+            return self.fn, self.args
+
+    import builtins
+
+    marker = os.path.join(os.path.dirname(__file__), "_pwned_marker")
+    for fn, args in ((builtins.eval, (f"open({marker!r}, 'w').close()",)),
+                     (builtins.exec, ("import os",)),
+                     (builtins.getattr, ("abc", "upper")),
+                     (builtins.__import__, ("os",)),
+                     (os.system, ("true",))):
+        with pytest.raises(pickle.UnpicklingError):
+            load_pickle(pickle.dumps(_Evil(fn, args)))
+    assert not os.path.exists(marker)
+
 
 # ------------------------------------------------------------------------------------ sql + decode
 @pytest.mark.parametrize("name", ["dmv", "census"])
@@ -269,6 +288,11 @@ def test_flat_model_file_rejects_damaged_files(tmp_path):
     raw = open(good, "rb").read()
     cases = {"truncated": raw[:-100], "magic": b"NOTAMODL" + raw[8:], "version": raw[:8] + (7).to_bytes(4, "little") + raw[12:],
              "short": raw[:64], "section": raw[:48] + (1 << 40).to_bytes(8, "little") + raw[56:]}
+    # counts whose byte size wraps in 64 bits (4 * (2^62 + k) == 4 * k): must be rejected before they are multiplied
+    arena_floats, fan_floats = int.from_bytes(raw[16:24], "little"), int.from_bytes(raw[24:32], "little")
+    cases["wrap_arena"] = raw[:16] + ((1 << 62) + arena_floats).to_bytes(8, "little") + raw[24:]
+    cases["wrap_fan"] = raw[:24] + ((1 << 62) + fan_floats).to_bytes(8, "little") + raw[32:]
+    cases["wrap_cpt64"] = raw[:32] + ((1 << 61) + int.from_bytes(raw[32:40], "little")).to_bytes(8, "little") + raw[40:]
     for what, data in cases.items():
         bad = str(tmp_path / (what + ".bcm"))
         open(bad, "wb").write(data)
@@ -276,7 +300,7 @@ def test_flat_model_file_rejects_damaged_files(tmp_path):
         rc = L.lib().bc_model_create_from_file(-1, os.fsencode(bad), ctypes.byref(h))
         assert rc != 0 and not h.value, what
         assert L.lib().bc_last_error()
-        if what != "section":  # (the Python reader does not touch the device-only sections)
+        if what != "section" and not what.startswith("wrap_"):  # (the Python reader does not touch the device-only sections)
             with pytest.raises(ValueError):
                 TreeModel.load_flat(bad)
     h = ctypes.c_void_p()
@@ -323,6 +347,58 @@ def test_wsparse_packer_round_trip(name):
             assert words.nbytes + row_off.nbytes < rows.nbytes / 4
     with pytest.raises(ValueError):
         dense_to_wsparse(m, np.zeros((2, dense.shape[1] + 4), dtype=np.float32))
+
+
+def _wsparse_expand(m, row_off, words, nq):
+    """Plain restatement of wsparse_to_dense_kernel (csrc/bc_convert.cu) for the packer tests."""
+    off, acc = [], 0
+    for v in range(m.n_nodes):
+        off.append(acc)
+        acc += -(-int(m.card[v]) // 4) * 4
+    back = np.zeros((nq, acc), dtype=np.float32)
+    for v in range(m.n_nodes):
+        back[:, off[v]:off[v] + int(m.card[v])] = 1.0
+    for q in range(nq):
+        i = int(row_off[q])
+        while i < int(row_off[q + 1]):
+            h = int(words[i])
+            col, cont, first, cnt = h & 0x7FFF, (h >> 15) & 1, (h >> 16) & 0xFF, h >> 24
+            assert col < m.n_nodes and first + cnt <= int(m.card[col])
+            if not cont:
+                back[q, off[col]:off[col] + int(m.card[col])] = 0.0
+            back[q, off[col] + first:off[col] + first + cnt] = words[i + 1:i + 1 + cnt].view(np.float32)
+            i += 1 + cnt
+        assert i == int(row_off[q + 1])
+    return back, off
+
+
+def test_wsparse_run_of_256_states():
+    """A 256-state column with non-zero weights at states 0 and 255 is one run of 256 states: the 8-bit count field
+    would wrap to 0, so the packer sends 255 + a one-state continuation run."""
+    from bayescard_b200.synth import make_tree_model
+
+    m = make_tree_model(3, [256, 200, 256], seed=5)
+    rng = np.random.default_rng(0)
+    rows = np.ones((6, 256 + 200 + 256), dtype=np.float32)
+    rows[0, :256] = 0.0
+    rows[0, 0] = 0.25
+    rows[0, 255] = 0.5                          # the advisor's case
+    rows[1, :256] = rng.random(256).astype(np.float32) + 0.1   # all 256 states weighted
+    rows[2, 456:] = 0.0
+    rows[2, 456 + 1] = 1.0
+    rows[2, 456 + 255] = 0.125                  # run of 255: no continuation
+    rows[3, 456:] = (rng.random(256) < 0.5).astype(np.float32)
+    rows[3, 456] = 1.0
+    rows[3, 456 + 255] = 1.0
+    rows[4, 256:456] = 0.0                      # an all-zero column: run of 0 states
+    row_off, words = dense_to_wsparse(m, rows)
+    back, off = _wsparse_expand(m, row_off, words, rows.shape[0])
+    assert np.array_equal(back, rows)
+    # row 0: header(255) + 255 weights + header(cont, first 255, 1) + 1 weight
+    assert int(row_off[1] - row_off[0]) == 1 + 255 + 1 + 1
+    h0, h1 = int(words[0]), int(words[256])
+    assert (h0 >> 24, (h0 >> 16) & 0xFF, (h0 >> 15) & 1) == (255, 0, 0)
+    assert (h1 >> 24, (h1 >> 16) & 0xFF, (h1 >> 15) & 1, h1 & 0x7FFF) == (1, 255, 1, 0)
 
 
 def _fused_plan(dm):

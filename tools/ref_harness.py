@@ -23,7 +23,21 @@ import pickle
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("BAYESCARD_REFERENCE", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+
+
+def _default_root() -> str:
+    """``/root/reference`` in the build container, the staged byte-for-byte copy ``baseline/_ref`` on the GPU box
+    (``baseline/stage_reference.py``)."""
+    env = os.environ.get("BAYESCARD_REFERENCE")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/Pgmpy"):
+        return "/root/reference"
+    return _STAGED
+
+
+REFERENCE_ROOT = _default_root()
 
 
 def available() -> bool:
