@@ -271,6 +271,37 @@ def test_wsparse_rows_expand_to_the_dense_rows(name):
     assert np.all(np.abs(one - 1.0) < 1e-5)
 
 
+def test_wsparse_run_of_256_states_on_the_device():
+    """A 256-state column with weights at states 0 and 255 (one run of 256 states: sent as 255 + a continuation run)."""
+    import torch
+
+    from bayescard_b200.synth import make_tree_model
+
+    m = make_tree_model(3, [256, 200, 256], seed=5)
+    dm = DeviceModel(m, device=0, specialize=False)
+    rng = np.random.default_rng(0)
+    rows = np.ones((64, dm.dense_width), dtype=np.float32)
+    o = dm.dense_offset
+    rows[0, o[0]:o[0] + 256] = 0.0
+    rows[0, o[0]] = 0.25
+    rows[0, o[0] + 255] = 0.5
+    rows[1:, o[0]:o[0] + 256] = rng.uniform(0.1, 1.0, (63, 256))
+    rows[2::2, o[2]:o[2] + 256] = (rng.random((31, 256)) < 0.5)
+    rows[2::2, o[2]] = 1.0
+    rows[2::2, o[2] + 255] = 1.0
+    row_off, words = dense_to_wsparse(m, rows)
+    d_off = torch.from_numpy(row_off.astype(np.int64)).to(torch.int32).cuda()
+    d_words = torch.from_numpy(words.astype(np.int64)).to(torch.int32).cuda()
+    d_dense = torch.empty(rows.shape, dtype=torch.float32, device="cuda:0")
+    L.check(L.lib().bc_expand_wsparse(dm._h, d_off.data_ptr(), d_words.data_ptr(), rows.shape[0], d_dense.data_ptr(), None))
+    torch.cuda.synchronize()
+    assert np.array_equal(d_dense.cpu().numpy(), rows)
+    got = dm.run_wsparse_host(row_off, words, None, L.KERNEL_GENERIC)
+    ref = O.dense_tree(m, [rows[:, o[v]:o[v] + int(m.card[v])].astype(np.float64) for v in range(3)])
+    assert_close(got, ref, "wsparse 256")
+    dm.close()
+
+
 def test_fused_kernel_wide_model_and_refusals():
     """K3 serves trees of up to 128 columns (Census: 68 columns, three fan-out-mask words would be two) and declines, with a
     message, what does not fit tensor memory; AUTO then falls through to the other kernels."""

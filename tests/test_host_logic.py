@@ -468,3 +468,38 @@ def test_fused_kernel_plan_invariants(name):
 def test_shard_split():
     assert ShardedModel.split(10, 4) == [(0, 2), (2, 4), (4, 6), (6, 10)]
     assert ShardedModel.split(3, 8)[-1] == (0, 3)
+
+
+def test_reference_arm_query_stream_equals_the_c_generator():
+    """bench.py --impl reference regenerates the seeded query stream in pure Python (baseline/ref_runner.py) so that the
+    reference arm loads none of this repository's native code: it must be the stream the C generator produces."""
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from baseline import ref_runner as RR
+    from bayescard_b200.engine import gen_range_queries_host
+
+    for name, first, kmin, kmax in (("census", 0, 1, 14), ("census", 123456789012, 1, 14), ("dmv", 7, 1, 5), ("imdb3", 99, 0, 9)):
+        m = G.model(name)
+        lo, hi = RR.gen_ranges([int(c) for c in m.card], 0, first, 200, kmin, kmax)
+        lo2, hi2 = unpack_ranges(m, gen_range_queries_host(m, 0, first, 200, kmin, kmax))
+        assert np.array_equal(lo, lo2) and np.array_equal(hi, hi2), name
+
+
+def test_staged_reference_reproduces_the_golden_probabilities():
+    """baseline/_ref (the byte-for-byte staged reference that bench.py times) against the committed golden vectors."""
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from baseline import ref_runner as RR
+
+    if not RR.available():
+        pytest.skip("baseline/_ref not staged on this machine")
+    bn = RR.load_bn("dmv")
+    rows = [r for r in G.load("dmv_workload.json.gz")["queries"] if r.get("decoded")][:60]
+    for r in rows:
+        q = {k: list(v) for k, v in r["decoded"]["bins"].items()}
+        nd = {k: np.asarray(v) for k, v in r["decoded"]["weights"].items()}
+        p = bn.query(q, n_distinct=nd, return_prob=True)[0]
+        want = np.asarray(r["card"]["value"]).reshape(-1)[0] / bn.nrows
+        assert abs(float(np.asarray(p).reshape(-1)[0]) - want) <= 1e-12 * max(abs(want), 1e-300)
