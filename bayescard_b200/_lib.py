@@ -18,7 +18,6 @@ BC_OK = 0
 DESC_RANGE_U8, DESC_RANGE_U16, DESC_DENSE_F32, DESC_BITS = 0, 1, 2, 3
 SQLC_BITS, SQLC_DENSE, SQLC_ZERO, SQLC_PYTHON, SQLC_OVERFLOW = 0, 1, 2, 3, 4
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_SPEC, KERNEL_GEMM, KERNEL_GEMM_SIMT, KERNEL_FUSED = 0, 1, 2, 3, 4, 5
-KERNEL_FUSED_1CTA = 6
 
 _lib = None
 

@@ -230,7 +230,6 @@ extern "C" void bc_model_destroy(bc_model* m) {
         pipe_free(m->pipe);
         bc_k2_free(m);
         bc_k3_free(m);
-        bc_k3b_free(m);
         if (m->spec_lib) cudaLibraryUnload(m->spec_lib);
         cudaFree(m->d_arena);
         cudaFree(m->d_fan);
@@ -347,8 +346,8 @@ extern "C" int bc_query_batch(bc_model* m, const void* desc, size_t nq, int fmt,
             return rc;
         }
     }
-    if (kernel == BC_KERNEL_FUSED || kernel == BC_KERNEL_FUSED_1CTA) {
-        auto launch = kernel == BC_KERNEL_FUSED ? bc_k3_launch : bc_k3b_launch;
+    if (kernel == BC_KERNEL_FUSED) {
+        auto launch = bc_k3_launch;
         if (!is_range) return launch(m, desc, nq, fmt, fan_mask, out, st);
         void* scratch = nullptr;   // range rows -> BITS rows in stream-ordered scratch
         BC_CUDA_CHECK(cudaMallocAsync(&scratch, nq * (size_t)m->bits_words * 4, st));

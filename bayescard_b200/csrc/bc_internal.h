@@ -37,7 +37,6 @@ struct BcBitsRec {
 struct BcHostPipe;  // bc_api.cu
 struct BcUmmaPlan;  // k2_umma.cu
 struct BcK3Plan;    // k3_fused.cu
-struct BcK3bPlan;   // k3_fused_1cta.cu
 
 // State of the batched large-domain path (K2), built on first use.
 struct BcK2Plan {
@@ -93,8 +92,6 @@ struct bc_model {
     std::mutex k2_mu;                // guards the lazy construction of k2 (pipe_mu may already be held)
     BcK3Plan* k3 = nullptr;          // fused tensor-core tree kernel: edge schedule, TMEM columns, operand images
     std::mutex k3_mu;
-    BcK3bPlan* k3b = nullptr;        // single-CTA variant of the fused kernel
-    std::mutex k3b_mu;
     BcHostPipe* pipe = nullptr;
     std::mutex pipe_mu;
 };
@@ -133,9 +130,6 @@ void bc_k2_umma_free(bc_model* m);
 // k3_fused.cu: whole tree per 128-query tile on the tensor cores (BITS / DENSE_F32 rows); BC_ELIMIT = model not served
 int bc_k3_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32_t* fan_mask, float* out, cudaStream_t stream);
 void bc_k3_free(bc_model* m);
-// k3_fused_1cta.cu: the same kernel as one CTA per SM with two accumulator chains, two issuer warps, three producer groups
-int bc_k3b_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32_t* fan_mask, float* out, cudaStream_t stream);
-void bc_k3b_free(bc_model* m);
 // spec_codegen.cc
 std::string bc_spec_generate(const bc_model& m);
 uint64_t bc_spec_hash_of(const bc_model& m);

@@ -1,5 +1,5 @@
-// K3 -- fused whole-tree sum-product on the tensor cores: one CTA carries a tile of 128 queries through EVERY edge
-// of the tree without leaving the SM.
+// K3 -- fused whole-tree sum-product on the tensor cores: one CTA per SM carries tiles of 128 queries through EVERY
+// edge of the tree without leaving the SM.
 //
 //     out[q] = sum_x prod_v w_v[x_v] * T_v[x_v, x_pa(v)]        (VariableEliminationJIT.query / .expectation,
 //                                                                 reference Pgmpy/inference/ExactInference.py:112-287)
@@ -9,37 +9,47 @@
 //     D[128 x N]  = U_v[128 x K] . T_v[K x N]        U_v = w_v (*) Lambda_v,  K = card(v), N = card(pa)
 //     Lambda_pa  *= D
 //
-// Why it exists: the per-model straight-line kernel (K-spec) keeps the CPTs in the instruction stream and is
-// instruction-fetch bound once a model has more than ~10k CPT entries (IMDB: 45 % of the FP32 peak with unit
-// weights, 19 % with fractional weights / fan-out expectations); K2 runs one launch per edge and moves every Lambda
-// through HBM.  Here the messages never leave the SM:
+// What the schedule is built on (MEASURED, tools/microbench/umma_chain.cu, profiles/r2_microbench_umma_chain.txt):
+//   * tcgen05.mma.kind::tf32 M128 x N x K8 instructions that accumulate into the SAME tensor-memory columns pipeline
+//     at the floor rate (N / 2 clk each; 1 chain == 4 chains) -- there is no dependent-chain penalty;
+//   * with the A operand in SHARED memory an instruction costs 32 + N / 4 clk (4 KB of A + 32 N bytes of B per instruction
+//     over the 128 B/clk shared-memory port: N = 96 -> 56 clk), on top of the producers' and TMA's writes into the same
+//     port; with A in TENSOR memory it runs at the floor for every N >= 32;
+//   * tcgen05.ld moves ~190 B/clk/SM and neither slows the MMAs down nor is slowed by them.
+// Hence (round 2): the operand U_v is written by the producer warps straight into a ring of TENSOR-MEMORY columns
+// (tcgen05.st: hi and lo TF32 halves, 16 columns each per block of 16 child states) and read from there by the MMAs;
+// shared memory only carries T_v^T (TMA) and the staged query weights.
 //
-//   * Lambda_v of every live internal node sits in TENSOR MEMORY (one fp32 column per state, one lane per query);
-//     the columns are assigned on the host by first fit over the nodes' lifetimes in the edge schedule;
-//   * FOUR PRODUCER WARPS (thread = query = TMEM lane): per edge and per block of 16 child states they read Lambda_v
-//     with tcgen05.ld, apply the query's weights (BITS mask, dense n_distinct weights, fan-out vector), split the
-//     product into TF32 hi + lo and write both as the K-major, 64-byte-swizzled A operand straight into a 3-slot
-//     shared-memory ring (fence.proxy.async + one mbarrier arrive per warp); the message-independent inputs of the
-//     NEXT block (weights; finished 0/1 chunks for unit-weight leaves) are fetched one step ahead;
-//   * a TMA WARP keeps a 4-slot ring of T_v^T blocks (hi and lo, pre-split and pre-swizzled once per model into an
-//     "operand image") full: ONE bulk copy (cp.async.bulk ... mbarrier::complete_tx) per step;
-//   * an ISSUER WARP (whole warp converged, elect.sync inside the asm, edge table in the kernel-parameter bank so that
-//     every tcgen05 operand lives in uniform registers) issues tcgen05.mma.cta_group::1.kind::tf32, error compensated:
-//     A_lo.B_hi + A_hi.B_lo first, then A_hi.B_hi (A_lo = 0 and is skipped for unit-weight leaves), into a TMEM
-//     accumulator; tcgen05.commit frees the A and B slots and, after the edge's last block, releases the accumulator;
-//   * the producer warps then multiply the accumulator into Lambda_pa with tcgen05.ld / tcgen05.st (32 columns per
-//     round trip) -- no shared memory, no HBM traffic; the root is a dot product with T_root in registers;
-//   * two CTAs per SM (256 TMEM columns and ~104 KB of shared memory each; one CTA with 512 columns when a model's live
-//     messages need more) overlap one tile's operand building, MMA drain and epilogue with the other's MMAs.
+// Roles (448 threads, one CTA per SM, all 512 tensor-memory columns):
+//   * warps 0-3 / 4-7  TWO PRODUCER GROUPS (thread = query = TMEM lane) build alternate blocks: weights from the BITS tile
+//     in shared memory or, for DENSE_F32 rows, from a shared-memory ring that the TMA warp fills four blocks ahead with
+//     2-D tensor-map loads (128 queries x 16 floats, 64-byte swizzle) -- no global-memory latency in the loop; times the
+//     fan-out vector, times Lambda_v (tcgen05.ld) for an internal node; split into TF32 hi (round to nearest) and lo = x - hi;
+//     tcgen05.st into the A ring; one mbarrier arrive per warp;
+//   * warps 8-11       EPILOGUE WARPS: Lambda_pa (*)= D with tcgen05.ld / tcgen05.st while the MMAs of the next edge fill the
+//     other accumulator buffer; they publish "Lambda_v complete" (one mbarrier per internal edge) to the producers and
+//     finish a tile with the root's dot product;
+//   * warp 12          MMA ISSUER (whole warp converged, elect.sync inside the asm, edge table in the kernel-parameter bank
+//     so that every tcgen05 operand lives in uniform registers): error-compensated 3xTF32, A_lo.B_hi + A_hi.B_lo first, then
+//     A_hi.B_hi (A_lo = 0 and skipped for unit-weight leaves); tcgen05.commit frees the A and B slots and hands the accumulator
+//     to the epilogue warps;
+//   * warp 13          TMA WARP: T_v^T blocks (hi and lo, pre-split and pre-swizzled once per model into an "operand image",
+//     L2 resident) by ONE bulk copy per step, and the DENSE weight blocks; the step sequence is static, so both rings run
+//     ahead across edges and tiles.
+// Lambda_v of every live internal node sits in tensor memory (one fp32 column per state); the columns are assigned on the
+// host by first fit over the nodes' lifetimes in the edge schedule.
 //
 // Algorithmic work per query = flops_dense(model) (every CPT entry once); HBM traffic = descriptor row + 4 B.
+#include <cuda.h>
+
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
 #include <memory>
 
 #include "bc_internal.h"
 
-struct K3Edge {            // 64 bytes, copied to shared memory
+struct K3Edge {            // 64 bytes, in the kernel parameter bank
     int32_t v, K, N, n_pad;
     int32_t lam_off;       // first float of column v in a DENSE row
     int32_t bit_off;       // first bit of column v in a BITS row
@@ -50,7 +60,10 @@ struct K3Edge {            // 64 bytes, copied to shared memory
     int32_t nkb;           // blocks of 16 child states
     uint32_t idesc;        // tcgen05 instruction descriptor (M = 128, N = n_pad, TF32 x TF32 -> F32, K-major)
     uint64_t bimg_off;     // byte offset of the edge's operand images
-    int32_t pad[2];
+    int32_t publish;       // >= 0: this edge is the LAST message into Lambda_pa, pa's own edge is `publish` (its producers may
+                           // start); -2: ... and pa is the root (the tile's result follows); -3: ... and pa is the root's only
+                           // child, folded into the result by the SIMT tail; -1: more messages to come
+    int32_t fin_guard;     // this edge is the first message into the node the finisher warps read (root, or the tail node)
 };
 static_assert(sizeof(K3Edge) == 64, "K3Edge layout");
 
@@ -60,23 +73,32 @@ struct BcK3Plan {
     uint8_t* d_bimg = nullptr;
     size_t bimg_bytes = 0;
     int npad_max = 16;
-    int tmem_cols = 32;    // power of two
-    int d_col = 0, n_dbuf = 1;
+    int tmem_cols = 512;
+    int a_col = 0, a_stages = 4;   // A ring: a_stages x 32 columns (16 hi + 16 lo)
+    int d_col = 0, n_dbuf = 2;
+    int b_stages = 4;
     int root_col = 0;
+    int tail_v = -1;               // the root's only child when the edge into the root is folded into the result in registers
     int ctas_per_sm = 1;
     size_t smem = 0;
+    void* encode = nullptr;        // cuTensorMapEncodeTiled (DENSE_F32 rows are staged by 2-D TMA loads)
 };
 
 namespace {
 
-constexpr int kTile = 128;    // queries per CTA tile = TMEM lanes = UMMA M
+constexpr int kTile = 128;     // queries per CTA tile = TMEM lanes = UMMA M
 constexpr int kMaxEdges = 127; // trees of up to 128 columns
-constexpr int kBK = 16;       // child states per ring step: one 64-byte swizzle row
-constexpr int kStagesA = 3;   // A ring: U_v blocks written by the producer warps
-constexpr int kStagesB = 4;   // B ring: T_v^T blocks fetched by TMA (deeper: an L2 round trip is longer than a step)
-constexpr int kABytes = kTile * kBK * 4;   // 8 KB per half (hi or lo)
-constexpr int kProducerWarps = 4;
-constexpr int kThreads = 32 * (kProducerWarps + 2);   // + MMA issuer warp + TMA warp
+constexpr int kBK = 16;        // child states per ring step
+constexpr int kStagesW = 8;    // DENSE weight ring (8 KB per slot): deep, the loads come from HBM
+constexpr int kWBytes = kTile * kBK * 4;
+constexpr int kGroups = 2;     // producer groups of four warps, alternate blocks
+constexpr int kWarpEpi = 4 * kGroups, kWarpMma = kWarpEpi + 4, kWarpTma = kWarpMma + 1, kWarpFin = kWarpTma + 1;
+constexpr int kThreads = 32 * (kWarpFin + 4);   // + four finisher warps (one per TMEM lane quarter: warp % 4)
+constexpr int kMaxStages = 8;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 struct K3Params {
     K3Edge edge[kMaxEdges];    // in the kernel parameter bank (8 KB of the 32 KB sm_100 allows): uniform loads, warp-uniform control flow
@@ -89,17 +111,47 @@ struct K3Params {
     int fan_floats;            // multiple of 4 (shared-memory copy, zero padded)
     int fan_n;                 // floats in the fan arena
     const float* root_T;       // T_root in the arena
-    int root_card, root_col, root_bit_off, root_lam_off, root_fan_off, root_has_children;
+    int root_card, root_col, root_bit_off, root_lam_off, root_fan_off;
+    // SIMT tail: when the root has ONE child v and card(v) * card(root) is small (every shipped DMV / IMDB model: a root of 2-7
+    // states over one wide child), the edge v -> root is not worth a tensor-core pass at the end of the dependency chain
+    // (4-6 blocks that wait for the epilogue of v's last child, a drain, another epilogue): the epilogue warps fold it into
+    // the root's dot product in registers.  tail_K = 0: no tail.
+    int tail_K, tail_v, tail_col_v, tail_bit_off, tail_lam_off, tail_fan_off, tail_stride;
+    const float* tail_T;       // T_v[c * tail_stride + r]
     float* out;
     size_t nq;
     long long n_tiles;
     int bits_words;
     int b_slot_bytes;          // 2 * npad_max * 64
+    int a_col, a_stages, b_stages;
     int d_col, d_stride, n_dbuf;
-    int tmem_cols;
     int mask_words;            // fan-out mask words per query
-    float debias_unit;         // expected relative truncation loss per accumulating MMA (1.1e-8 measured; BC_K3_DEBIAS overrides, 0 = off)
+    float debias_unit;         // optional correction of the accumulator's truncation (BC_K3_DEBIAS, 0 = off = default)
+    long long* trace;          // BC_K3_TRACE: clock64 stamps of CTA 0's fifth tile, [role][edge][2] (nullptr = off)
 };
+constexpr int kTraceTile = 4;
+constexpr int kCnt = 4 * kMaxEdges * 2;   // per-step stamps behind the per-edge stamps: [step of the tile][8]
+constexpr int kTraceSteps = 64;
+#ifndef BC_K3_TRACE_BUILD
+#define BC_K3_TRACE_BUILD 0   // 1: compile the clock stamps in (they cost issue slots in every role); BC_K3_TRACE=1 then prints them
+#endif
+#if BC_K3_TRACE_BUILD
+#define K3_STAMP(role, e, k)                                                                                   \
+    do {                                                                                                       \
+        if (P.trace != nullptr && blockIdx.x == 0 && tile_iter == kTraceTile && lane == 0)                     \
+            P.trace[((role) * kMaxEdges + (e)) * 2 + (k)] = clock64();                                         \
+    } while (0)
+// per-step stamps go to SHARED memory (a global read-modify-write per stamp would perturb what it measures) and are copied out
+// at the end of the kernel: slots 0-4 producer (start, inputs ready, Lambda loaded, A slot free, stored + arrived)
+#define K3_STEP(slot)                                                                                                    \
+    do {                                                                                                                 \
+        if (P.trace != nullptr && blockIdx.x == 0 && tile_iter == kTraceTile && lane == 0 && step_in_tile < kTraceSteps)  \
+            s_trace[step_in_tile * 8 + (slot)] = clock64();                                                              \
+    } while (0)
+#else
+#define K3_STAMP(role, e, k) do { (void)tile_iter; } while (0)
+#define K3_STEP(slot) do { (void)step_in_tile; } while (0)
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, unsigned count) {
@@ -123,17 +175,22 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, unsi
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
-// K-major operands, 64-byte swizzle: rows of 64 B, 8-row groups 512 B apart (SBO), layout type 4, version 1 (sm_100).
-// descriptors as 32-bit halves: the high word (SBO, version, swizzle mode) is the same for every operand.  Called by the
-// WHOLE (converged) issuer warp; elect.sync inside picks the lane, so ptxas keeps every operand in uniform registers
-// instead of wrapping each instruction in a divergence (ELECT / R2UR / BRA.U.ANY) loop.
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint32_t a_lo32, uint32_t b_lo32, uint32_t desc_hi32, uint32_t idesc,
-                                          uint32_t accumulate) {
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
     asm volatile(
-        "{\n.reg .pred p, q;\n.reg .b64 da, db;\nelect.sync _|q, 0xffffffff;\nsetp.ne.b32 p, %5, 0;\n"
-        "mov.b64 da, {%1, %3};\nmov.b64 db, {%2, %3};\n"
-        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n}\n" ::"r"(tmem_c),
-        "r"(a_lo32), "r"(b_lo32), "r"(desc_hi32), "r"(idesc), "r"(accumulate)
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+// D[tmem] (+)= A[tmem: 128 lanes x 8 columns] . B[smem, K-major, 64-byte swizzle: rows of 64 B, 8-row groups 512 B apart (SBO),
+// layout type 4, version 1 (sm_100)].  Called by the WHOLE (converged) issuer warp; elect.sync inside picks the lane, so ptxas
+// keeps every operand in uniform registers instead of wrapping each instruction in a divergence loop.
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_c, uint32_t tmem_a, uint32_t b_lo32, uint32_t desc_hi32, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p, q;\n.reg .b64 db;\nelect.sync _|q, 0xffffffff;\nsetp.ne.b32 p, %5, 0;\n"
+        "mov.b64 db, {%2, %3};\n"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], db, %4, p;\n}\n" ::"r"(tmem_c),
+        "r"(tmem_a), "r"(b_lo32), "r"(desc_hi32), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {   // whole warp, one elected lane
@@ -155,13 +212,40 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
                  "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                  : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+    const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+        "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,"
+        "%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+          "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
+    const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,"
+        "%30,%31,%32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+        "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]),
+        "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z, float w) {
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
-}
 
 // x = hi + lo, hi = x rounded to the nearest TF32 number (ties away from zero: two integer instructions); lo = x - hi is
 // exact in fp32 and symmetric around zero, so the tensor core's truncation of its low bits is unbiased
@@ -179,10 +263,10 @@ __device__ __forceinline__ uint32_t bits16(const uint32_t* my_bits, int bits_wor
     return __funnelshift_r(w0, w1, sh) & (valid >= 16 ? 0xFFFFu : ((1u << valid) - 1u));
 }
 
-// weights of 8 consecutive states [c0, c0 + 8) of a column (root only: the edges have their own code below)
+// weights of 8 consecutive states [c0, c0 + 8) of a column for this thread's query (epilogue warps: root and SIMT tail)
 template <int FMT>
-__device__ __forceinline__ void load_weights8(const uint32_t* my_bits, int bits_words, const float* drow, const float* s_fan, uint32_t fm,
-                                              int v, int lam_off, int bit_off, int fan_off, int card, int c0, float* w) {
+__device__ __forceinline__ void weights8(const uint32_t* my_bits, int bits_words, const float* drow, int lam_off, int bit_off, int card, int c0,
+                                         float* w) {
     if (FMT == BC_DESC_BITS) {
         const uint32_t m = bits16(my_bits, bits_words, bit_off, card, c0);
 #pragma unroll
@@ -194,58 +278,75 @@ __device__ __forceinline__ void load_weights8(const uint32_t* my_bits, int bits_
         w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-            if (c0 + j >= card) w[j] = 0.f;   // padding entries of a DENSE row never contribute
-    }
-    if (fan_off >= 0 && ((fm >> v) & 1u)) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (c0 + j < card) w[j] *= s_fan[fan_off + c0 + j];
+            if (c0 + j >= card) w[j] = 0.f;   // row padding / the next column's weights never contribute
     }
 }
 
+struct Ring {   // slot / parity cursor of a ring of `n` slots advanced once per step
+    uint32_t s = 0, par = 0;
+    __device__ __forceinline__ void next(uint32_t n) {
+        if (++s == n) { s = 0; par ^= 1u; }
+    }
+};
+
 template <int FMT>
-__global__ void __launch_bounds__(kThreads, 2) k3_kernel(const __grid_constant__ K3Params P) {
+__global__ void __launch_bounds__(kThreads, 1) k3_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUtensorMap tm_w) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler (role dispatch without divergence)
-    // carve-up: A ring | B ring | BITS rows of the tile [word][query] | fan arena | nibble table | barriers
-    uint8_t* p = smem + (size_t)kStagesA * 2 * kABytes;
-    const uint32_t a_ring = smem_u32(smem), b_ring = smem_u32(p);
-    p += (size_t)kStagesB * P.b_slot_bytes;
+    // carve-up: B ring | W ring (DENSE) | BITS rows of two tiles [word][query] | fan-out mask of two tiles | fan arena | table | barriers
+    uint8_t* p = smem;
+    const uint32_t b_ring = smem_u32(p);
+    p += (size_t)P.b_stages * P.b_slot_bytes;
+    const uint32_t w_ring = smem_u32(p);
+    const uint8_t* w_ring_ptr = p;
+    p += (FMT == BC_DESC_DENSE_F32 ? (size_t)kStagesW * kWBytes : 0);
     uint32_t* s_bits = reinterpret_cast<uint32_t*>(p);
-    p += (FMT == BC_DESC_BITS ? (size_t)P.bits_words * kTile * 4 : 0);
+    const size_t bits_tile = (FMT == BC_DESC_BITS ? (size_t)P.bits_words * kTile : 0);
+    p += 2 * bits_tile * 4;
+    uint32_t* s_fm = reinterpret_cast<uint32_t*>(p);
+    const size_t fm_tile = (size_t)P.mask_words * kTile;
+    p += 2 * fm_tile * 4;
     float* s_fan = reinterpret_cast<float*>(p);
     p += (size_t)P.fan_floats * 4;
     float4* s_tab = reinterpret_cast<float4*>(p);   // nibble -> four 0/1 floats
     p += 256;
     uint64_t* bars = reinterpret_cast<uint64_t*>(p);
-    const uint32_t a_full0 = smem_u32(bars), a_empty0 = a_full0 + 8 * kStagesA, b_full0 = a_empty0 + 8 * kStagesA,
-                   b_empty0 = b_full0 + 8 * kStagesB, d_full0 = b_empty0 + 8 * kStagesB, d_empty0 = d_full0 + 16;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStagesA + 2 * kStagesB + 4);
+    const uint32_t a_full0 = smem_u32(bars), a_empty0 = a_full0 + 8 * kMaxStages, b_full0 = a_empty0 + 8 * kMaxStages,
+                   b_empty0 = b_full0 + 8 * kMaxStages, w_full0 = b_empty0 + 8 * kMaxStages, w_empty0 = w_full0 + 8 * kStagesW,
+                   d_full0 = w_empty0 + 8 * kStagesW, d_empty0 = d_full0 + 16, bits_free0 = d_empty0 + 16, fin_ready0 = bits_free0 + 16,
+                   fin_done0 = fin_ready0 + 8, lam_ready0 = fin_done0 + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * kMaxStages + 2 * kStagesW + 8 + kMaxEdges + 1);
+    long long* s_trace = reinterpret_cast<long long*>(bars + 4 * kMaxStages + 2 * kStagesW + 8 + kMaxEdges + 2);   // BC_K3_TRACE only
 
     {   // tables -> shared memory
         for (int i = tid; i < P.fan_floats; i += kThreads) s_fan[i] = i < P.fan_n ? P.fan[i] : 0.f;
         if (tid < 16) s_tab[tid] = make_float4(tid & 1 ? 1.f : 0.f, tid & 2 ? 1.f : 0.f, tid & 4 ? 1.f : 0.f, tid & 8 ? 1.f : 0.f);
     }
     if (tid == 0) {
-        for (int s = 0; s < kStagesA; ++s) {
-            mbar_init(a_full0 + 8 * s, kProducerWarps);
+        for (int s = 0; s < kMaxStages; ++s) {
+            mbar_init(a_full0 + 8 * s, 4);
             mbar_init(a_empty0 + 8 * s, 1);
-        }
-        for (int s = 0; s < kStagesB; ++s) {
             mbar_init(b_full0 + 8 * s, 1);
             mbar_init(b_empty0 + 8 * s, 1);
         }
+        for (int s = 0; s < kStagesW; ++s) {
+            mbar_init(w_full0 + 8 * s, 1);
+            mbar_init(w_empty0 + 8 * s, 4);
+        }
         for (int b = 0; b < 2; ++b) {
             mbar_init(d_full0 + 8 * b, 1);
-            mbar_init(d_empty0 + 8 * b, kProducerWarps);
+            mbar_init(d_empty0 + 8 * b, 4);
+            mbar_init(bits_free0 + 8 * b, 4);
         }
+        mbar_init(fin_ready0, 4);
+        mbar_init(fin_done0, 4);
+        for (int e = 0; e < P.n_edges; ++e) mbar_init(lam_ready0 + 8 * e, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(P.tmem_cols)
-                     : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -253,27 +354,38 @@ __global__ void __launch_bounds__(kThreads, 2) k3_kernel(const __grid_constant__
     tc_fence_after();
     const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform for the compiler: tcgen05 operands live in uniform registers
 
-    if (warp == kProducerWarps + 1) {
-        // ================= TMA warp: keeps the B ring full; the (edge, block) sequence repeats for every tile
+    if (warp == kWarpTma) {
+        // ================= TMA warp: keeps the B ring (and the DENSE weight ring) full; the step sequence is static
         if (lane == 0) {
-            uint32_t it = 0;
+            Ring rb, rw;
             for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x)
                 for (int e = 0; e < P.n_edges; ++e) {
                     const K3Edge& E = P.edge[e];
                     const unsigned bytes = (unsigned)E.n_pad * 128u;   // hi + lo, 64 B per row each
-                    for (int kb = 0; kb < E.nkb; ++kb, ++it) {
-                        const uint32_t s = it % kStagesB, par = (it / kStagesB) & 1u;
-                        mbar_wait(b_empty0 + 8 * s, par ^ 1u);
-                        mbar_expect_tx(b_full0 + 8 * s, bytes);
-                        tma_bulk_g2s(b_ring + s * P.b_slot_bytes, P.bimg + E.bimg_off + (size_t)kb * bytes, bytes, b_full0 + 8 * s);
+                    for (int kb = 0; kb < E.nkb; ++kb) {
+                        if (FMT == BC_DESC_DENSE_F32) {
+                            mbar_wait(w_empty0 + 8 * rw.s, rw.par ^ 1u);
+                            mbar_expect_tx(w_full0 + 8 * rw.s, kWBytes);
+                            tma_load_2d(w_ring + rw.s * kWBytes, &tm_w, E.lam_off + kb * kBK, (int)(tile * kTile), w_full0 + 8 * rw.s);
+                            rw.next(kStagesW);
+                        }
+                        mbar_wait(b_empty0 + 8 * rb.s, rb.par ^ 1u);
+                        mbar_expect_tx(b_full0 + 8 * rb.s, bytes);
+                        tma_bulk_g2s(b_ring + rb.s * P.b_slot_bytes, P.bimg + E.bimg_off + (size_t)kb * bytes, bytes, b_full0 + 8 * rb.s);
+                        rb.next(P.b_stages);
                     }
                 }
         }
-    } else if (warp == kProducerWarps) {
-        // ================= MMA issuer warp: the whole warp runs the (uniform) loop, one elected lane issues
-        uint32_t it = 0, ed = 0;   // ring step, edge counter (D buffer = ed % n_dbuf)
+    } else if (warp == kWarpMma) {
+        // ================= MMA issuer warp: the whole warp runs the (uniform) loop, one elected lane issues.  (The issue
+        // queue is deep and neither the commits nor the fence stall it -- tools/microbench/umma_issue.cu -- but this warp
+        // shares its scheduler with three busy warps: every instruction of this loop costs the tensor pipe time.)
+        Ring ra, rb;
+        uint32_t ed = 0, tile_iter = 0;   // edge counter (D buffer = ed % n_dbuf)
+        const uint32_t SA = (uint32_t)P.a_stages, SB = (uint32_t)P.b_stages, b_slot = (uint32_t)P.b_slot_bytes;
         const uint32_t desc_hi = (uint32_t)(512 >> 4) | (1u << 14) | (4u << 29);   // SBO, version 1, 64-byte swizzle
-        for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x)
+        const uint32_t a_base = tmem + (uint32_t)P.a_col, b_base = (((b_ring & 0x3FFFFu) >> 4) | (1u << 16));
+        for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tile_iter)
             for (int e = 0; e < P.n_edges; ++e, ++ed) {
                 const K3Edge& E = P.edge[e];
                 const bool a_exact = FMT == BC_DESC_BITS && E.col_v < 0 && !(E.fan_off >= 0 && P.fan_mask != nullptr);
@@ -282,112 +394,101 @@ __global__ void __launch_bounds__(kThreads, 2) k3_kernel(const __grid_constant__
                 const uint32_t idesc = E.idesc, b_lo_off = (uint32_t)E.n_pad * 4u;   // n_pad * 64 B in 16-byte units
                 const int K = E.K, nkb = E.nkb;
                 mbar_wait(d_empty0 + 8 * db, dpar ^ 1u);   // the epilogue of the edge that used this accumulator is done
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const uint32_t sa = it % kStagesA, pa = (it / kStagesA) & 1u;
-                    const uint32_t sb = it % kStagesB, pb = (it / kStagesB) & 1u;
-                    // low words of the four operand descriptors: start address >> 4 | LBO = 1
-                    const uint32_t a_hi = (((a_ring + sa * 2 * kABytes) & 0x3FFFFu) >> 4) | (1u << 16), a_lo = a_hi + (kABytes >> 4);
-                    const uint32_t b_hi = (((b_ring + sb * P.b_slot_bytes) & 0x3FFFFu) >> 4) | (1u << 16), b_lo = b_hi + b_lo_off;
+                K3_STAMP(0, e, 0);
+                for (int kb = 0; kb < nkb; ++kb) {
+                    const uint32_t a_hi = a_base + ra.s * 32u, a_lo = a_hi + 16u;
+                    // low word of the B descriptors: start address >> 4 | LBO = 1
+                    const uint32_t b_hi = b_base + ((rb.s * b_slot) >> 4), b_lo = b_hi + b_lo_off;
                     const bool two = K - kb * kBK > 8;
-                    mbar_wait(b_full0 + 8 * sb, pb);
-                    mbar_wait(a_full0 + 8 * sa, pa);
+                    mbar_wait(b_full0 + 8 * rb.s, rb.par);
+                    mbar_wait(a_full0 + 8 * ra.s, ra.par);
                     tc_fence_after();
-                    {
-                        // error-compensated product, the small terms first; 8 TF32 = 32 bytes per k-step: +2 in the address field
-                        if (!a_exact) {
-                            umma_tf32(d, a_lo, b_hi, desc_hi, idesc, kb != 0);
-                            umma_tf32(d, a_hi, b_lo, desc_hi, idesc, 1);
-                            if (two) {
-                                umma_tf32(d, a_lo + 2, b_hi + 2, desc_hi, idesc, 1);
-                                umma_tf32(d, a_hi + 2, b_lo + 2, desc_hi, idesc, 1);
-                            }
-                        } else {
-                            umma_tf32(d, a_hi, b_lo, desc_hi, idesc, kb != 0);
-                            if (two) umma_tf32(d, a_hi + 2, b_lo + 2, desc_hi, idesc, 1);
-                        }
-                        umma_tf32(d, a_hi, b_hi, desc_hi, idesc, 1);
-                        if (two) umma_tf32(d, a_hi + 2, b_hi + 2, desc_hi, idesc, 1);
-                        umma_commit(a_empty0 + 8 * sa);
-                        umma_commit(b_empty0 + 8 * sb);
-                        if (kb == nkb - 1) umma_commit(d_full0 + 8 * db);
-                    }
-                }
-            }
-    } else {
-        // ================= producer / epilogue warps: thread = query = TMEM lane
-        const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
-        const uint32_t sw = ((uint32_t)tid >> 1) & 3u;    // 64-byte swizzle: chunk j of row r lives at r * 64 + ((j ^ ((r >> 1) & 3)) << 4)
-        const uint32_t* my_bits = s_bits + tid;
-        uint32_t it = 0, ed = 0;
-        for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-            const size_t q = (size_t)tile * kTile + tid;
-            const size_t qc = q < P.nq ? q : P.nq - 1;
-            // fan-out mask: one word per 32 columns; word 0 (the root's) is kept, the others are read per fan-out edge
-            const uint32_t* fm_row = P.fan_mask ? P.fan_mask + qc * (size_t)P.mask_words : nullptr;
-            const uint32_t fm = fm_row ? fm_row[0] : 0u;
-            const float* drow = reinterpret_cast<const float*>(P.desc + qc * P.dstride);
-            if (FMT == BC_DESC_BITS) {
-                const uint32_t* grow = reinterpret_cast<const uint32_t*>(P.desc + qc * P.dstride);
-                for (int w4 = 0; w4 < P.bits_words; w4 += 4) {   // bits_words is a multiple of 4
-                    const uint4 x = __ldg(reinterpret_cast<const uint4*>(grow + w4));
-                    s_bits[(w4 + 0) * kTile + tid] = x.x;
-                    s_bits[(w4 + 1) * kTile + tid] = x.y;
-                    s_bits[(w4 + 2) * kTile + tid] = x.z;
-                    s_bits[(w4 + 3) * kTile + tid] = x.w;
-                }
-            }
-            // Inputs of ring step (e, kb) that do not depend on any message: for unit-weight leaves the finished hi chunks
-            // (0/1 floats from the nibble table), otherwise the weights w_v[c0 .. c0 + 16) (x fan-out).  They are fetched ONE
-            // STEP AHEAD (also across edges), so the LDS / LDG latency overlaps the previous block's stores and barriers.
-            auto fetch = [&](int e, int kb, float* pre) __attribute__((always_inline)) {
-                const K3Edge& E = P.edge[e];
-                const int c0 = kb * kBK;
-                const bool exact = FMT == BC_DESC_BITS && E.col_v < 0 && !(E.fan_off >= 0 && P.fan_mask != nullptr);
-                if (FMT == BC_DESC_BITS) {
-                    const uint32_t m = bits16(my_bits, P.bits_words, E.bit_off, E.K, c0);
-                    if (exact) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float4 t = s_tab[(m >> (4 * j)) & 15u];
-                            pre[4 * j] = t.x; pre[4 * j + 1] = t.y; pre[4 * j + 2] = t.z; pre[4 * j + 3] = t.w;
+                    // error-compensated product, the small terms first; a k-step is 8 TF32: 8 columns of A, 32 bytes (+2) of B
+                    if (!a_exact) {
+                        umma_tf32_ts(d, a_lo, b_hi, desc_hi, idesc, kb != 0);
+                        umma_tf32_ts(d, a_hi, b_lo, desc_hi, idesc, 1);
+                        if (two) {
+                            umma_tf32_ts(d, a_lo + 8, b_hi + 2, desc_hi, idesc, 1);
+                            umma_tf32_ts(d, a_hi + 8, b_lo + 2, desc_hi, idesc, 1);
                         }
                     } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) pre[j] = ((m >> j) & 1u) ? 1.f : 0.f;
+                        umma_tf32_ts(d, a_hi, b_lo, desc_hi, idesc, kb != 0);
+                        if (two) umma_tf32_ts(d, a_hi + 8, b_lo + 2, desc_hi, idesc, 1);
                     }
-                } else {
-                    const float4* src = reinterpret_cast<const float4*>(drow + E.lam_off + c0);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (c0 + 4 * j < E.K) t = __ldg(src + j);
-                        pre[4 * j] = t.x; pre[4 * j + 1] = t.y; pre[4 * j + 2] = t.z; pre[4 * j + 3] = t.w;
-                    }
+                    umma_tf32_ts(d, a_hi, b_hi, desc_hi, idesc, 1);
+                    if (two) umma_tf32_ts(d, a_hi + 8, b_hi + 2, desc_hi, idesc, 1);
+                    umma_commit(a_empty0 + 8 * ra.s);
+                    umma_commit(b_empty0 + 8 * rb.s);
+                    if (kb == nkb - 1) umma_commit(d_full0 + 8 * db);
+                    ra.next(SA);
+                    rb.next(SB);
                 }
-                // (the fan-out vector is applied where the block is consumed: a multiply here would wait for the loads just
-                //  issued and undo the prefetch -- ncu: 22 % of the stall samples of the expectation rows sat on it)
-            };
-            // (two blocks in flight for DENSE rows were measured too: +3 % without fan-out columns, -4...-9 % on the fan-out
-            //  weighted expectation factors this kernel exists for -- one step of lead it is; tools/runs/_gpu_run59.sh)
-            float pre[16];
-            fetch(0, 0, pre);
-            for (int e = 0; e < P.n_edges; ++e, ++ed) {
+                K3_STAMP(0, e, 1);
+            }
+    } else if (warp < kWarpEpi) {
+        // ================= producer warps: thread = query = TMEM lane; group g builds the blocks with (step & 1) == g
+        const int g = warp >> 2, ql = tid & (kTile - 1);
+        const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        const uint32_t sw = ((uint32_t)ql >> 1) & 3u;    // 64-byte swizzle: chunk j of row r lives at r * 64 + ((j ^ ((r >> 1) & 3)) << 4)
+        Ring ra, rw;
+        uint32_t it = 0, tile_iter = 0;
+        for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tile_iter) {
+            const size_t q = (size_t)tile * kTile + ql;
+            const size_t qc = q < P.nq ? q : P.nq - 1;
+            const uint32_t buf = tile_iter & 1u;
+            uint32_t* bits_t = s_bits + buf * bits_tile;
+            uint32_t* fm_t = s_fm + buf * fm_tile;
+            // ---- this tile's BITS rows and fan-out mask words -> shared memory (the two groups share the work)
+            if (tile_iter >= 2) mbar_wait(bits_free0 + 8 * buf, ((tile_iter >> 1) - 1u) & 1u);   // the epilogue warps are done with the tile that used this buffer
+            if (FMT == BC_DESC_BITS) {
+                const uint32_t* grow = reinterpret_cast<const uint32_t*>(P.desc + qc * P.dstride);
+                for (int w4 = 4 * g; w4 < P.bits_words; w4 += 4 * kGroups) {   // bits_words is a multiple of 4
+                    const uint4 x = __ldg(reinterpret_cast<const uint4*>(grow + w4));
+                    bits_t[(w4 + 0) * kTile + ql] = x.x;
+                    bits_t[(w4 + 1) * kTile + ql] = x.y;
+                    bits_t[(w4 + 2) * kTile + ql] = x.z;
+                    bits_t[(w4 + 3) * kTile + ql] = x.w;
+                }
+            }
+            if (P.fan_mask != nullptr && g == 0)
+                for (int w = 0; w < P.mask_words; ++w) fm_t[w * kTile + ql] = __ldg(P.fan_mask + qc * (size_t)P.mask_words + w);
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * kWarpEpi) : "memory");   // the eight producer warps
+            const uint32_t* my_bits = bits_t + ql;
+            int step_in_tile = 0;
+            for (int e = 0; e < P.n_edges; ++e) {
                 const K3Edge& E = P.edge[e];
                 const bool leaf = E.col_v < 0;
                 const bool a_exact = FMT == BC_DESC_BITS && leaf && !(E.fan_off >= 0 && P.fan_mask != nullptr);
-                const bool fan_on = E.fan_off >= 0 && fm_row != nullptr && ((fm_row[E.v >> 5] >> (E.v & 31)) & 1u);
+                const bool fan_on = E.fan_off >= 0 && P.fan_mask != nullptr && ((fm_t[(E.v >> 5) * kTile + ql] >> (E.v & 31)) & 1u);
                 const int K = E.K, nkb = E.nkb;
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const uint32_t sa = it % kStagesA, pa = (it / kStagesA) & 1u;
-                    const uint32_t row = a_ring + sa * 2 * kABytes + (uint32_t)tid * 64u;
+                if ((warp & 3) == 0) K3_STAMP(1 + g, e, 0);
+                if (!leaf) {   // every message into Lambda_v has been multiplied in
+                    mbar_wait(lam_ready0 + 8 * e, tile_iter & 1u);
+                    tc_fence_after();
+                }
+                for (int kb = 0; kb < nkb; ++kb, ++it, ++step_in_tile, ra.next(P.a_stages), rw.next(kStagesW)) {
+                    if ((it & 1u) != (uint32_t)g) continue;
                     const int c0 = kb * kBK;
-                    const int ks = (K - c0 > 8) ? 2 : 1;
+                    if ((warp & 3) == 0) K3_STEP(0);
                     float u[16];
+                    if (FMT == BC_DESC_BITS) {
+                        const uint32_t m = bits16(my_bits, P.bits_words, E.bit_off, K, c0);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) u[j] = pre[j];
-                    // next step's inputs
-                    if (kb + 1 < nkb) fetch(e, kb + 1, pre);
-                    else if (e + 1 < P.n_edges) fetch(e + 1, 0, pre);
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 t = s_tab[(m >> (4 * j)) & 15u];
+                            u[4 * j] = t.x; u[4 * j + 1] = t.y; u[4 * j + 2] = t.z; u[4 * j + 3] = t.w;
+                        }
+                    } else {
+                        mbar_wait(w_full0 + 8 * rw.s, rw.par);
+                        const uint8_t* row = w_ring_ptr + rw.s * kWBytes + ql * 64;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 t = *reinterpret_cast<const float4*>(row + (((uint32_t)j ^ sw) << 4));
+                            u[4 * j] = t.x; u[4 * j + 1] = t.y; u[4 * j + 2] = t.z; u[4 * j + 3] = t.w;
+                        }
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(w_empty0 + 8 * rw.s);   // the slot may be refilled
+                    }
                     if (fan_on) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
@@ -396,64 +497,87 @@ __global__ void __launch_bounds__(kThreads, 2) k3_kernel(const __grid_constant__
                                 u[4 * j] *= f.x; u[4 * j + 1] *= f.y; u[4 * j + 2] *= f.z; u[4 * j + 3] *= f.w;
                             }
                     }
+                    if ((warp & 3) == 0) K3_STEP(1);
+                    if (!leaf) {
+                        float lv[16];
+                        tmem_ld8(tlane + (uint32_t)(E.col_v + c0), lv);
+                        if (K - c0 > 8) tmem_ld8(tlane + (uint32_t)(E.col_v + c0 + 8), lv + 8);
+                        else {
+#pragma unroll
+                            for (int j = 8; j < 16; ++j) lv[j] = 0.f;
+                        }
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) u[j] *= lv[j];
+                    }
+                    if (c0 + kBK > K) {   // last block: states >= K must be exact zeros (stale Lambda columns, row padding, the next column's weights)
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (c0 + j >= K) u[j] = 0.f;
+                    }
+                    const uint32_t a_hi = tlane + (uint32_t)(P.a_col + (int)ra.s * 32);
+                    if ((warp & 3) == 0) K3_STEP(2);
                     if (a_exact) {
                         // unit weights on a leaf: U is a 0/1 matrix, exact in TF32 -- no lo half
-                        mbar_wait(a_empty0 + 8 * sa, pa ^ 1u);   // the MMAs that read this slot are done
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (j < 2 * ks) sts128(row + (((uint32_t)j ^ sw) << 4), u[4 * j], u[4 * j + 1], u[4 * j + 2], u[4 * j + 3]);
+                        mbar_wait(a_empty0 + 8 * ra.s, ra.par ^ 1u);   // the MMAs that read this slot are done
+                        if ((warp & 3) == 0) K3_STEP(3);
+                        tc_fence_after();
+                        tmem_st16(a_hi, u);
                     } else {
-                        if (!leaf) {
-                            float lv[16];
-                            tmem_ld8(tlane + (uint32_t)(E.col_v + c0), lv);
-                            if (ks == 2) tmem_ld8(tlane + (uint32_t)(E.col_v + c0 + 8), lv + 8);
-                            tmem_ld_wait();
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) u[j] *= lv[j];
-                        }
-                        if (c0 + kBK > K) {   // last block: states >= K must be exact zeros (stale Lambda columns, row padding)
-#pragma unroll
-                            for (int j = 0; j < 16; ++j)
-                                if (c0 + j >= K) u[j] = 0.f;
-                        }
                         float h[16], l[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) split_tf32(u[j], h[j], l[j]);
-                        mbar_wait(a_empty0 + 8 * sa, pa ^ 1u);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (j < 2 * ks) {
-                                const uint32_t a = row + (((uint32_t)j ^ sw) << 4);
-                                sts128(a, h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
-                                sts128(a + kABytes, l[4 * j], l[4 * j + 1], l[4 * j + 2], l[4 * j + 3]);
-                            }
+                        mbar_wait(a_empty0 + 8 * ra.s, ra.par ^ 1u);
+                        if ((warp & 3) == 0) K3_STEP(3);
+                        tc_fence_after();
+                        tmem_st16(a_hi, h);
+                        tmem_st16(a_hi + 16u, l);
                     }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+                    tmem_st_wait();
+                    tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(a_full0 + 8 * sa);
+                    if (lane == 0) mbar_arrive(a_full0 + 8 * ra.s);
+                    if ((warp & 3) == 0) K3_STEP(4);
                 }
-                // ---- epilogue: Lambda_pa (*)= D, all in tensor memory, 32 columns per round trip
+                if ((warp & 3) == 0) K3_STAMP(1 + g, e, 1);
+            }
+        }
+    } else if (warp < kWarpMma) {
+        // ================= epilogue warps: Lambda_pa (*)= D in tensor memory, 32 columns per round trip; the root's dot product
+        const int ql = tid & (kTile - 1);
+        const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        uint32_t ed = 0, tile_iter = 0;
+        for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tile_iter) {
+            const size_t q = (size_t)tile * kTile + ql;
+            const size_t qc = q < P.nq ? q : P.nq - 1;
+            const uint32_t buf = tile_iter & 1u;
+            for (int e = 0; e < P.n_edges; ++e, ++ed) {
+                const K3Edge& E = P.edge[e];
                 const uint32_t db = P.n_dbuf == 2 ? (ed & 1u) : 0u, dpar = (P.n_dbuf == 2 ? (ed >> 1) : ed) & 1u;
                 const uint32_t dcol = tlane + (uint32_t)(P.d_col + (int)db * P.d_stride), pcol = tlane + (uint32_t)E.col_pa;
                 const bool first = E.first;
-                // The tensor core adds into its fp32 accumulator with truncation (k2_umma.cu: UmmaCfg): every accumulating
-                // tcgen05.mma of the edge loses half an ulp of the running sum on average, and the terms are non-negative, so
-                // the loss never cancels.  The expected loss is added back here: (instructions - 1) * debias_unit relative;
-                // debias_unit = 1.1e-8 is MEASURED (profiles/r1_k3_debias.txt: the mean signed error against the fp64 oracle crosses
-                // zero there on all five IMDB models and DMV; small-product and early accumulations lose less than half an ulp).
+                // optional correction of the truncating accumulator (off by default)
+                const bool a_exact = FMT == BC_DESC_BITS && E.col_v < 0 && !(E.fan_off >= 0 && P.fan_mask != nullptr);
                 const int n_mma = ((int)E.K + 7) / 8 * (a_exact ? 2 : 3);
                 const float debias = 1.f + (float)(n_mma - 1) * P.debias_unit;
                 mbar_wait(d_full0 + 8 * db, dpar);
+                if (E.fin_guard && tile_iter > 0) mbar_wait(fin_done0, (tile_iter - 1u) & 1u);   // the previous tile's result has been read out
                 tc_fence_after();
+                if (warp == kWarpEpi) K3_STAMP(3, e, 0);
                 const int n8 = (E.N + 7) & ~7;
                 for (int j = 0; j < n8; j += 32) {
                     float dv[32], lv[32];
+                    if (j + 32 <= n8) {   // whole 32-column chunks with one instruction each
+                        tmem_ld32(dcol + (uint32_t)j, dv);
+                        if (!first) tmem_ld32(pcol + (uint32_t)j, lv);
+                    } else {
 #pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        if (j + 8 * c < n8) {
-                            tmem_ld8(dcol + (uint32_t)(j + 8 * c), dv + 8 * c);
-                            if (!first) tmem_ld8(pcol + (uint32_t)(j + 8 * c), lv + 8 * c);
-                        }
+                        for (int c = 0; c < 4; ++c)
+                            if (j + 8 * c < n8) {
+                                tmem_ld8(dcol + (uint32_t)(j + 8 * c), dv + 8 * c);
+                                if (!first) tmem_ld8(pcol + (uint32_t)(j + 8 * c), lv + 8 * c);
+                            }
+                    }
                     tmem_ld_wait();
                     if (!first) {
 #pragma unroll
@@ -462,30 +586,106 @@ __global__ void __launch_bounds__(kThreads, 2) k3_kernel(const __grid_constant__
 #pragma unroll
                         for (int i = 0; i < 32; ++i) dv[i] *= debias;
                     }
+                    if (j + 32 <= n8) {
+                        tmem_st32(pcol + (uint32_t)j, dv);
+                    } else {
 #pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        if (j + 8 * c < n8) tmem_st8(pcol + (uint32_t)(j + 8 * c), dv + 8 * c);
+                        for (int c = 0; c < 4; ++c)
+                            if (j + 8 * c < n8) tmem_st8(pcol + (uint32_t)(j + 8 * c), dv + 8 * c);
+                    }
                 }
+                tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(d_empty0 + 8 * db);   // the accumulator may be overwritten
-                tmem_st_wait();
-            }
-
-            // ---- root: sum_c w_0[c] * Lambda_0[c] * T_0[c]
-            float res = 0.f;
-            for (int c0 = 0; c0 < P.root_card; c0 += 8) {
-                float lv[8], w[8];
-                if (P.root_has_children) {
-                    tmem_ld8(tlane + (uint32_t)(P.root_col + c0), lv);
-                    tmem_ld_wait();
+                if (warp == kWarpEpi) K3_STAMP(3, e, 1);
+                if (lane == 0) {
+                    mbar_arrive(d_empty0 + 8 * db);                              // the accumulator may be overwritten
+                    if (E.publish >= 0) mbar_arrive(lam_ready0 + 8 * E.publish);   // Lambda_pa is complete: pa's own edge may be built
+                    if (E.publish <= -2) mbar_arrive(fin_ready0);                  // ... the finisher warps take the tile from here
                 }
-                load_weights8<FMT>(my_bits, P.bits_words, drow, s_fan, fm, 0, P.root_lam_off, P.root_bit_off, P.root_fan_off, P.root_card, c0, w);
+            }
+        }
+    } else if (warp >= kWarpFin) {
+        // ================= finisher warps: the root's dot product, or the SIMT tail (edge v -> root folded into it), per tile,
+        // while the other roles are already working on the next tile
+        const int ql = tid & (kTile - 1);
+        const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        uint32_t tile_iter = 0;
+        for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tile_iter) {
+            const size_t q = (size_t)tile * kTile + ql;
+            const size_t qc = q < P.nq ? q : P.nq - 1;
+            const uint32_t buf = tile_iter & 1u;
+            mbar_wait(fin_ready0, tile_iter & 1u);
+            tc_fence_after();
+            const uint32_t* my_bits = s_bits + buf * bits_tile + ql;
+            const float* drow = reinterpret_cast<const float*>(P.desc + qc * P.dstride);
+            const uint32_t* fm_q = s_fm + buf * fm_tile + ql;
+            const bool fan_root = P.root_fan_off >= 0 && P.fan_mask != nullptr && (fm_q[0] & 1u);
+            float res = 0.f;
+            if (P.tail_K == 0) {
+                // ---- root: sum_c w_0[c] * Lambda_0[c] * T_0[c]
+                for (int c0 = 0; c0 < P.root_card; c0 += 8) {
+                    float lv[8], w[8];
+                    tmem_ld8(tlane + (uint32_t)(P.root_col + c0), lv);
+                    weights8<FMT>(my_bits, P.bits_words, drow, P.root_lam_off, P.root_bit_off, P.root_card, c0, w);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (c0 + j < P.root_card) res = fmaf(P.root_has_children ? lv[j] * w[j] : w[j], __ldg(P.root_T + c0 + j), res);
+                    for (int j = 0; j < 8; ++j)
+                        if (c0 + j < P.root_card) {
+                            float x = lv[j] * w[j];
+                            if (fan_root) x *= s_fan[P.root_fan_off + c0 + j];
+                            res = fmaf(x, __ldg(P.root_T + c0 + j), res);
+                        }
+                }
+            } else {
+                // ---- SIMT tail: acc[r] = sum_c (w_v[c] * Lambda_v[c]) * T_v[c, r];  res = sum_r w_0[r] * T_0[r] * acc[r]
+                const int K = P.tail_K;
+                const bool fan_v = P.tail_fan_off >= 0 && P.fan_mask != nullptr && ((fm_q[(P.tail_v >> 5) * kTile] >> (P.tail_v & 31)) & 1u);
+                float acc[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+                for (int c0 = 0; c0 < K; c0 += 32) {   // 32 states per round trip: every load of the chunk is in flight at once
+                    float lv[32], w[32];
+#pragma unroll
+                    for (int g8 = 0; g8 < 4; ++g8)
+                        if (c0 + 8 * g8 < K) tmem_ld8(tlane + (uint32_t)(P.tail_col_v + c0 + 8 * g8), lv + 8 * g8);
+#pragma unroll
+                    for (int g8 = 0; g8 < 4; ++g8)
+                        if (c0 + 8 * g8 < K) weights8<FMT>(my_bits, P.bits_words, drow, P.tail_lam_off, P.tail_bit_off, K, c0 + 8 * g8, w + 8 * g8);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (c0 + j < K) {   // (warp-uniform)
+                            float u = lv[j] * w[j];
+                            if (fan_v) u *= s_fan[P.tail_fan_off + c0 + j];
+                            const float* T = P.tail_T + (size_t)(c0 + j) * P.tail_stride;
+                            const float4 t0 = __ldg(reinterpret_cast<const float4*>(T));
+                            acc[0] = fmaf(u, t0.x, acc[0]); acc[1] = fmaf(u, t0.y, acc[1]);
+                            acc[2] = fmaf(u, t0.z, acc[2]); acc[3] = fmaf(u, t0.w, acc[3]);
+                            if (P.root_card > 4) {
+                                const float4 t1 = __ldg(reinterpret_cast<const float4*>(T + 4));
+                                acc[4] = fmaf(u, t1.x, acc[4]); acc[5] = fmaf(u, t1.y, acc[5]);
+                                acc[6] = fmaf(u, t1.z, acc[6]); acc[7] = fmaf(u, t1.w, acc[7]);
+                            }
+                        }
+                }
+                float w0[8];
+                weights8<FMT>(my_bits, P.bits_words, drow, P.root_lam_off, P.root_bit_off, P.root_card, 0, w0);
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+                    if (r < P.root_card) {
+                        float x = acc[r] * w0[r];
+                        if (fan_root) x *= s_fan[P.root_fan_off + r];
+                        res = fmaf(x, __ldg(P.root_T + r), res);
+                    }
             }
             if (q < P.nq) P.out[q] = res;
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(fin_done0);               // the node's columns may be overwritten by the next tile
+                mbar_arrive(bits_free0 + 8 * buf);    // this tile's BITS rows / mask words are no longer read
+            }
         }
     }
 
@@ -493,8 +693,10 @@ __global__ void __launch_bounds__(kThreads, 2) k3_kernel(const __grid_constant__
     __syncthreads();
     if (warp == 0) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(P.tmem_cols) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
     }
+    if (BC_K3_TRACE_BUILD && P.trace != nullptr && blockIdx.x == 0)
+        for (int i = tid; i < kTraceSteps * 8; i += kThreads) P.trace[kCnt + i] = s_trace[i];
 }
 
 uint32_t host_tf32_hi(float x) {
@@ -527,7 +729,6 @@ int k3_prepare(bc_model* m) {
     //      heaviest subtree first: a Lambda then only lives while its own subtree is being folded, so the live set is
     //      bounded by the depth of the tree instead of its width (the reverse topological order kept 5+ messages of a
     //      20-column synthetic tree alive at once and did not fit tensor memory)
-    const int n_edges = n - 1;
     std::vector<std::vector<int>> kids(n);
     std::vector<long long> weight(n, 0);
     for (int v = n - 1; v >= 1; --v) {
@@ -538,8 +739,17 @@ int k3_prepare(bc_model* m) {
     std::vector<int> sched;   // sched[e] = child node of edge e
     {
         std::vector<std::pair<int, size_t>> stack{{0, 0}};
+        // siblings: internal subtrees first, heaviest first (their messages leave tensor memory early); then the LEAVES in
+        // ascending domain size -- the epilogue of an edge costs card(pa) columns whatever card(v) is, so small leaves at the
+        // end would queue their epilogues up right where the parent's own edge is waiting for them
+        const bool old_order = std::getenv("BC_K3_OLD_ORDER") != nullptr;   // experiments: heaviest subtree first, leaves included
         for (int v = 0; v < n; ++v)
-            std::stable_sort(kids[v].begin(), kids[v].end(), [&](int a, int b) { return weight[a] > weight[b]; });
+            std::stable_sort(kids[v].begin(), kids[v].end(), [&](int a, int b) {
+                if (old_order) return weight[a] > weight[b];
+                const bool ia = !kids[a].empty(), ib = !kids[b].empty();
+                if (ia != ib) return ia;
+                return ia ? weight[a] > weight[b] : m->nodes[a].card < m->nodes[b].card;
+            });
         while (!stack.empty()) {
             auto& [v, i] = stack.back();
             if (i < kids[v].size()) {
@@ -551,6 +761,17 @@ int k3_prepare(bc_model* m) {
             }
         }
     }
+    // ---- SIMT tail: a root with ONE internal child v and a small T_v (every shipped DMV / IMDB model) -- the edge v -> root is
+    //      the last of the schedule and is folded into the result by the epilogue warps instead of a tensor-core pass
+    int tail_v = -1;
+    if (kids[0].size() == 1 && !kids[kids[0][0]].empty() && m->nodes[0].card <= 8 &&
+        (long long)m->nodes[kids[0][0]].card * m->nodes[0].card <= 1024 && !std::getenv("BC_K3_NO_TAIL")) {
+        tail_v = kids[0][0];
+        sched.pop_back();   // post order: the root's only child is the last edge
+    }
+    k->tail_v = tail_v;
+    const int n_edges = (int)sched.size();
+    if (n_edges < 1) return fail("nothing left for the tensor cores");
     std::vector<int> first_child_edge(n, -1), own_edge(n, -1);
     for (int e = 0; e < n_edges; ++e) {
         const int v = sched[e];
@@ -559,31 +780,39 @@ int k3_prepare(bc_model* m) {
         if (first_child_edge[pa] < 0) first_child_edge[pa] = e;
     }
     int npad_max = 16;
-    for (int v = 1; v < n; ++v) {
+    for (int v : sched) {
         const int np = (int)bc_round_up(m->nodes[v].card_pa, 16);
         if (np > 256) return fail("a parent domain exceeds 256 states");
         if (np > npad_max) npad_max = np;
     }
-    // ---- TMEM columns: accumulator buffer(s) D first, then Lambda of every internal node by first fit over lifetimes
-    //      [edge of its first child, its own edge] (the root lives to the end), in units of 8 columns.  Two accumulator
-    //      buffers let the MMAs of the next edge start while the epilogue of this one runs; one buffer if that is
-    //      what keeps a tile within 256 columns (two CTAs per SM).
+    // ---- TMEM columns (one CTA per SM owns all 512): [A ring: a_stages x 32][accumulators: n_dbuf x npad_max][Lambda of
+    //      every internal node by first fit over lifetimes [edge of its first child, its own edge] (the root lives to the
+    //      end), in units of 8 columns].  Lifetimes may be reused back to back although the roles run at different places
+    //      of the step sequence: a node's columns are first WRITTEN by the epilogue of its first child's edge, which follows
+    //      that edge's MMAs, which follow every block the producers built before -- including all READS of the previous
+    //      occupant during its own edge.  Two accumulator buffers let the MMAs of the next edge run under this edge's epilogue.
     std::vector<int> col(n, -1);
     std::vector<int> order;   // internal nodes by start of lifetime
     for (int v = 0; v < n; ++v)
         if (first_child_edge[v] >= 0) order.push_back(v);
     std::sort(order.begin(), order.end(), [&](int a, int b) { return first_child_edge[a] < first_child_edge[b]; });
-    auto assign = [&](int n_dbuf) -> int {   // columns used, or -1 (col[] is only written when every node found a place)
+    // The node the FINISHER warps read (the root, or the tail node) is read after the tile's last epilogue, while the other
+    // roles are already in the next tile: with `excl` its columns are reserved for the whole tile (nobody shares them);
+    // otherwise the epilogue of the first edge of a tile that writes into an overlapping range waits for the finisher
+    // (K3Edge::fin_guard) -- correct, but that wait sits at the start of the next tile.
+    const int fin_node = tail_v >= 0 ? tail_v : 0;
+    auto assign = [&](int a_stages, int n_dbuf, bool excl = true) -> int {   // columns used, or -1 (col[] is only written when every node found a place)
         std::vector<int> place(n, -1);
         const int units_total = 512 / 8;
         std::vector<int> busy_until(units_total, -1);   // last edge index that uses the unit
-        const int d_units = n_dbuf * npad_max / 8;
-        if (d_units > units_total) return -1;
-        for (int u = 0; u < d_units; ++u) busy_until[u] = 1 << 30;
-        int units_used = d_units;
+        const int fixed_units = (a_stages * 32 + n_dbuf * npad_max) / 8;
+        if (fixed_units > units_total) return -1;
+        for (int u = 0; u < fixed_units; ++u) busy_until[u] = 1 << 30;
+        int units_used = fixed_units;
         for (int v : order) {
             const int need = (int)bc_round_up(m->nodes[v].card, 8) / 8;
-            const int start = first_child_edge[v], end = v == 0 ? (1 << 30) : own_edge[v];
+            const int start = (excl && v == fin_node) ? 0 : first_child_edge[v];
+            const int end = own_edge[v] < 0 ? (1 << 30) : own_edge[v];   // (root / tail node: to the end)
             int at = -1;
             for (int u0 = 0; u0 + need <= units_total && at < 0; ++u0) {
                 bool ok = true;
@@ -599,27 +828,34 @@ int k3_prepare(bc_model* m) {
         col = place;
         return units_used * 8;
     };
-    int n_dbuf = 2, used = assign(2);
-    if (used < 0 || used > 256) {
-        const int used1 = assign(1);
-        if (used1 < 0) return fail("live messages exceed the 512 columns of tensor memory");
-        if (used1 <= 256 || used < 0) { n_dbuf = 1; used = used1; }
-        else used = assign(2);
+    // preference: a deep A ring and two accumulators; give up ring depth first, the second accumulator last
+    static const int kTry[][3] = {{4, 2, 1}, {3, 2, 1}, {4, 2, 0}, {3, 2, 0}, {2, 2, 1}, {2, 2, 0}, {4, 1, 1}, {4, 1, 0}, {3, 1, 0}, {2, 1, 0}};
+    int a_stages = 0, n_dbuf = 0;
+    for (const auto& t : kTry)
+        if (assign(t[0], t[1], t[2] != 0) > 0) { a_stages = t[0]; n_dbuf = t[1]; break; }
+    if (const char* e = std::getenv("BC_K3_PLAN")) {   // experiments: "<a_stages>,<n_dbuf>"
+        int wa = 0, wd = 0;
+        if (std::sscanf(e, "%d,%d", &wa, &wd) == 2 && wa >= 2 && wa <= kMaxStages && (wd == 1 || wd == 2) && assign(wa, wd) > 0) {
+            a_stages = wa;
+            n_dbuf = wd;
+        } else if (a_stages) {
+            for (const auto& t : kTry)
+                if (assign(t[0], t[1], t[2] != 0) > 0) break;
+        }
     }
-    if (const char* e = std::getenv("BC_K3_DBUF")) {   // experiments
-        const int want = std::atoi(e);
-        if ((want == 1 || want == 2) && assign(want) > 0) { n_dbuf = want; used = assign(want); }
-    }
-    int tmem_cols = 32;
-    while (tmem_cols < used) tmem_cols <<= 1;
-    k->tmem_cols = tmem_cols;
+    if (!a_stages) return fail("live messages exceed the 512 columns of tensor memory");
+    k->tmem_cols = 512;
     k->npad_max = npad_max;
-    k->d_col = 0;
+    k->a_col = 0;
+    k->a_stages = a_stages;
+    k->d_col = a_stages * 32;
     k->n_dbuf = n_dbuf;
-    k->root_col = col[0];
+    k->root_col = tail_v >= 0 ? -1 : col[0];
     // ---- operand images: per edge and block of 16 child states, T_v^T hi then lo, 64-byte swizzled rows
     size_t total = 0;
     k->edges.resize(n_edges);
+    std::vector<int> last_child_edge(n, -1);
+    for (int e = 0; e < n_edges; ++e) last_child_edge[m->nodes[sched[e]].parent] = e;
     for (int e = 0; e < n_edges; ++e) {
         const int v = sched[e];
         const BcNodeRec& nd = m->nodes[v];
@@ -637,8 +873,19 @@ int k3_prepare(bc_model* m) {
         E.first = first_child_edge[nd.parent] == e;
         E.nkb = (nd.card + kBK - 1) / kBK;
         E.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(E.n_pad >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
+        E.publish = last_child_edge[nd.parent] != e ? -1 : (nd.parent == 0 ? -2 : (nd.parent == tail_v ? -3 : own_edge[nd.parent]));
         E.bimg_off = total;
         total += (size_t)E.nkb * E.n_pad * 128;
+    }
+    {   // the first edge of a tile whose epilogue writes into the columns the finisher warps read
+        const int f0 = col[fin_node], f1 = f0 + (int)bc_round_up(m->nodes[fin_node].card, 8);
+        for (K3Edge& E : k->edges) {
+            const int p0 = E.col_pa, p1 = p0 + (int)bc_round_up(E.N, 8);
+            if (E.first && p0 < f1 && f0 < p1) {
+                E.fin_guard = 1;
+                break;
+            }
+        }
     }
     std::vector<uint8_t> img(total, 0);
     for (const K3Edge& E : k->edges) {
@@ -664,15 +911,27 @@ int k3_prepare(bc_model* m) {
         }
     }
     k->bimg_bytes = total;
-    // ---- shared memory / residency
+    // ---- shared memory: B ring (as deep as fits, at most 4), DENSE weight ring, BITS rows and fan-out mask words of two tiles
     const size_t fan_floats = (size_t)bc_round_up((int64_t)m->fan.size(), 4);
-    const size_t fixed = (size_t)m->bits_words * kTile * 4 + fan_floats * 4 + 256 /* nibble table */ +                          256 /* barriers */ + 1024 /* alignment */;
-    k->smem = (size_t)kStagesA * 2 * kABytes + (size_t)kStagesB * npad_max * 128 + fixed;
+    const size_t per_fmt = std::max((size_t)kStagesW * kWBytes, (size_t)2 * m->bits_words * kTile * 4);
+    const size_t fixed = per_fmt + (size_t)2 * m->mask_words * kTile * 4 + fan_floats * 4 + 256 /* nibble table */ +
+                         8 * (4 * kMaxStages + 2 * kStagesW + 8 + kMaxEdges + 2) /* barriers, TMEM slot */ + 8 * kTraceSteps * 8 /* trace */ +
+                         1024 /* alignment */;
     const size_t smem_optin = m->device >= 0 ? (size_t)m->smem_optin : (size_t)227 * 1024;   // host-only model: the sm_100 value
-    if (k->smem > smem_optin) return fail("operand rings exceed shared memory");
-    k->ctas_per_sm = (tmem_cols <= 256 && 2 * (k->smem + 1024) <= 228 * 1024) ? 2 : 1;
-    if (k->ctas_per_sm == 1) k->smem = smem_optin;   // a second CTA would only spin in tcgen05.alloc
+    int b_stages = kMaxStages;
+    if (const char* e = std::getenv("BC_K3_BSTAGES")) b_stages = std::max(2, std::min(kMaxStages, std::atoi(e)));
+    while (b_stages > 1 && (size_t)b_stages * npad_max * 128 + fixed > smem_optin) --b_stages;
+    if ((size_t)b_stages * npad_max * 128 + fixed > smem_optin || b_stages < 2) return fail("operand rings exceed shared memory");
+    k->b_stages = b_stages;
+    k->smem = (size_t)b_stages * npad_max * 128 + fixed;
+    k->ctas_per_sm = 1;
     if (m->device >= 0) {   // (a host-only model keeps the plan for inspection: bc_model_fused_plan)
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &k->encode, cudaEnableDefault, &qr) != cudaSuccess || !k->encode ||
+            qr != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return fail("the driver does not export cuTensorMapEncodeTiled");
+        }
         BC_CUDA_CHECK(cudaMalloc(&k->d_bimg, total));
         const cudaError_t ce = cudaMemcpy(k->d_bimg, img.data(), total, cudaMemcpyHostToDevice);
         if (ce != cudaSuccess) {
@@ -686,7 +945,7 @@ int k3_prepare(bc_model* m) {
 }
 
 template <int FMT>
-int k3_launch_fmt(bc_model* m, const K3Params& P, int grid, cudaStream_t st) {
+int k3_launch_fmt(bc_model* m, const K3Params& P, const CUtensorMap& tm_w, int grid, cudaStream_t st) {
     static bool attr_set[64] = {};
     int dev = 0;
     BC_CUDA_CHECK(cudaGetDevice(&dev));
@@ -694,7 +953,7 @@ int k3_launch_fmt(bc_model* m, const K3Params& P, int grid, cudaStream_t st) {
         BC_CUDA_CHECK(cudaFuncSetAttribute(k3_kernel<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_optin));
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
-    k3_kernel<FMT><<<grid, kThreads, m->k3->smem, st>>>(P);
+    k3_kernel<FMT><<<grid, kThreads, m->k3->smem, st>>>(P, tm_w);
     BC_CUDA_CHECK(cudaGetLastError());
     bc_count_launch();
     return BC_OK;
@@ -735,23 +994,90 @@ int bc_k3_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32
     P.root_bit_off = m->bits[0].bit_off;
     P.root_lam_off = r.lam_off;
     P.root_fan_off = r.fan_off;
-    P.root_has_children = k->root_col >= 0;
+    if (k->tail_v >= 0) {
+        const BcNodeRec& t = m->nodes[k->tail_v];
+        P.tail_K = t.card;
+        P.tail_v = k->tail_v;
+        P.tail_col_v = k->edges.empty() ? 0 : -1;
+        for (const K3Edge& E : k->edges)
+            if (m->nodes[E.v].parent == k->tail_v) P.tail_col_v = E.col_pa;
+        P.tail_bit_off = m->bits[k->tail_v].bit_off;
+        P.tail_lam_off = t.lam_off;
+        P.tail_fan_off = t.fan_off;
+        P.tail_stride = t.stride;
+        P.tail_T = m->d_arena + t.cpt_off;
+    }
     P.out = out;
     P.nq = nq;
     P.n_tiles = (long long)((nq + kTile - 1) / kTile);
     P.bits_words = m->bits_words;
     P.b_slot_bytes = k->npad_max * 128;
+    P.a_col = k->a_col;
+    P.a_stages = k->a_stages;
+    P.b_stages = k->b_stages;
     P.d_col = k->d_col;
     P.d_stride = k->npad_max;
     P.n_dbuf = k->n_dbuf;
-    P.tmem_cols = k->tmem_cols;
     P.mask_words = m->mask_words;
-    P.debias_unit = 1.1e-8f;
+    P.debias_unit = 0.f;
     if (const char* e = std::getenv("BC_K3_DEBIAS")) P.debias_unit = (float)std::atof(e);
     long long grid = (long long)m->sm_count * k->ctas_per_sm;
     if (grid > P.n_tiles) grid = P.n_tiles;
-    if (fmt == BC_DESC_BITS) return k3_launch_fmt<BC_DESC_BITS>(m, P, (int)grid, st);
-    return k3_launch_fmt<BC_DESC_DENSE_F32>(m, P, (int)grid, st);
+    struct TraceDump {   // BC_K3_TRACE=1 (debugging): synchronises and prints the clock stamps of one tile
+        long long* d = nullptr;
+        const BcK3Plan* k;
+        int fmt;
+        ~TraceDump() {
+            if (!d) return;
+            std::vector<long long> h(kCnt + kTraceSteps * 8);
+            cudaDeviceSynchronize();
+            cudaMemcpy(h.data(), d, h.size() * 8, cudaMemcpyDeviceToHost);
+            cudaFree(d);
+            const long long t0 = h[(1 * kMaxEdges + 0) * 2];
+            std::fprintf(stderr, "K3 trace fmt %d (clk since the producers entered edge 0 of the tile; role: start..end)\n", fmt);
+            for (size_t e = 0; e < k->edges.size(); ++e) {
+                const K3Edge& E = k->edges[e];
+                std::fprintf(stderr, "  e%zu K%d N%d %s:", e, E.K, E.N, E.col_v < 0 ? "leaf" : "int ");
+                static const char* names[4] = {"mma", "prodA", "prodB", "epi"};
+                for (int r = 0; r < 4; ++r)
+                    std::fprintf(stderr, "  %s %lld..%lld", names[r], h[(r * kMaxEdges + e) * 2] - t0, h[(r * kMaxEdges + e) * 2 + 1] - t0);
+                std::fprintf(stderr, "\n");
+            }
+            std::fprintf(stderr, "  step: producer start, +inputs, +Lambda, +slot free, +stored | mma: B full, A full, issued (clk, same origin)\n");
+            int step = 0;
+            for (size_t e = 0; e < k->edges.size(); ++e)
+                for (int kb = 0; kb < k->edges[e].nkb && step < kTraceSteps; ++kb, ++step) {
+                    const long long* c = h.data() + kCnt + step * 8;
+                    std::fprintf(stderr, "  e%zu.%d g%d: %6lld +%4lld +%4lld +%4lld +%4lld | %6lld %6lld %6lld\n", e, kb, step & 1, c[0] - t0, c[1] - c[0],
+                                 c[2] - c[1], c[3] - c[2], c[4] - c[3], c[5] - t0, c[6] - t0, c[7] - t0);
+                }
+        }
+    } trace_dump;
+    trace_dump.k = k;
+    trace_dump.fmt = fmt;
+    if (BC_K3_TRACE_BUILD && std::getenv("BC_K3_TRACE") && P.n_tiles > (long long)(kTraceTile + 1) * grid) {
+        if (cudaMalloc(&trace_dump.d, (kCnt + kTraceSteps * 8) * 8) == cudaSuccess) cudaMemset(trace_dump.d, 0, (kCnt + kTraceSteps * 8) * 8);
+        P.trace = trace_dump.d;
+    }
+    CUtensorMap tm_w;
+    std::memset(&tm_w, 0, sizeof(tm_w));
+    if (fmt == BC_DESC_DENSE_F32) {
+        // DENSE_F32 rows as a 2-D tensor [nq rows x lam_total floats]; one box = 128 queries x 16 states, 64-byte swizzle (the
+        // producers read their own row conflict free); rows past the batch and columns past the row read as zeros
+        const cuuint64_t dims[2] = {(cuuint64_t)m->lam_total, (cuuint64_t)nq};
+        const cuuint64_t strides[1] = {(cuuint64_t)m->lam_total * 4};
+        const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)kTile};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult cr = reinterpret_cast<EncodeTiledFn>(k->encode)(&tm_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(desc), dims, strides,
+                                                                       box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                                                                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) {
+            bc_set_error("cuTensorMapEncodeTiled failed (%d) for %zu DENSE_F32 rows of %d floats", (int)cr, nq, m->lam_total);
+            return BC_ECUDA;
+        }
+        return k3_launch_fmt<BC_DESC_DENSE_F32>(m, P, tm_w, (int)grid, st);
+    }
+    return k3_launch_fmt<BC_DESC_BITS>(m, P, tm_w, (int)grid, st);
 }
 
 extern "C" int bc_model_fused_plan(bc_model* m, int32_t* info, int32_t* edges, size_t edges_capacity) {
@@ -767,7 +1093,7 @@ extern "C" int bc_model_fused_plan(bc_model* m, int32_t* info, int32_t* edges, s
     info[2] = k->ctas_per_sm;
     info[3] = (int32_t)k->smem;
     info[4] = k->d_col;
-    info[5] = k->npad_max * k->n_dbuf;   // accumulator columns [d_col, d_col + this)
+    info[5] = k->npad_max * k->n_dbuf;   // accumulator columns [d_col, d_col + this); the A ring is [0, d_col)
     info[6] = k->root_col;
     info[7] = (int32_t)(k->bimg_bytes >> 10);
     if (edges) {

@@ -89,9 +89,6 @@ extern "C" {
                                 tensor memory; trees of <= 128 columns with domains <= 256 states whose live messages fit the 512
                                 TMEM columns, else BC_ELIMIT */
 
-#define BC_KERNEL_FUSED_1CTA 6 /* K3b: K3 scheduled as one CTA per SM (two accumulator chains, two issuer warps, three
-                                producer groups, [T_hi | T_lo] concatenated); domains <= 128 states */
-
 typedef struct bc_model bc_model;
 
 /* Replaces VariableEliminationJIT.__init__ + align_cpds_in_topological (ExactInference.py:25-40,

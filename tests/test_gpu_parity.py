@@ -87,32 +87,6 @@ def test_infer_cases_fused_kernel(name):
         assert_close(got, ref, (name, "fused", force_dense))
 
 
-@pytest.mark.parametrize("name", ["dmv", "imdb0", "imdb1"])
-def test_fused_kernel_single_cta_variant(name):
-    """K3b (BC_KERNEL_FUSED_1CTA, experimental schedule of K3: one CTA per SM, two accumulator chains, two issuer warps,
-    three producer groups, [T_hi | T_lo] concatenated): golden cases and a ragged batch against the fp64 oracle."""
-    m, dm = G.model(name), dev_model(name)
-    pc = PredicateCompiler(m)
-    cases = [r for r in G.load("infer_cases.json.gz")[name] if "error" not in r]
-    decoded = [({k: list(v) for k, v in r["bins"].items()}, {k: np.asarray(v) for k, v in r["weights"].items()}) for r in cases]
-    ref = np.asarray([np.asarray(r["p"]["value"]).reshape(-1)[0] for r in cases])
-    for force_dense in (False, True):
-        r_idx, r_desc, d_idx, d_desc, mask = pc.pack(decoded, [r["fanout"] for r in cases], force_dense=force_dense)
-        got = np.zeros(len(cases))
-        if len(r_idx):
-            got[r_idx] = dm.run_host(r_desc, L.DESC_BITS, mask[r_idx], L.KERNEL_FUSED_1CTA)
-        if len(d_idx):
-            got[d_idx] = dm.run_host(d_desc, L.DESC_DENSE_F32, mask[d_idx], L.KERNEL_FUSED_1CTA)
-        assert_close(got, ref, (name, "fused 1cta", force_dense))
-    n = 148 * 128 * 3 + 51
-    host = dm.gen_range_queries_host(8, 2, n, 1, min(m.n_nodes, 14))
-    lo, hi = unpack_ranges(m, host)
-    sub = np.random.default_rng(2).choice(n, 4000, replace=False)
-    sub[:200] = np.arange(n - 200, n)
-    got = dm.run_host(host, L.DESC_RANGE_U8, None, L.KERNEL_FUSED_1CTA).astype(np.float64)
-    assert_close(got[sub], O.dense_tree(m, O.range_weights(m, lo[sub], hi[sub])), (name, "fused 1cta ranges"))
-
-
 @pytest.mark.parametrize("name", ["dmv", "imdb1", "imdb3"])
 def test_fused_kernel_batch_vs_oracle_and_formats(name):
     """A ragged batch (not a multiple of the 128-query tile, more tiles than CTAs) through K3: fp64 oracle on every

@@ -32,7 +32,7 @@ def main():
     from bayescard_b200.engine import DeviceModel
     from oracle import bayescard_oracle as O
 
-    FUSED = L.KERNEL_FUSED_1CTA if os.environ.get("K3B") else L.KERNEL_FUSED   # K3B=1: the single-CTA variant
+    FUSED = L.KERNEL_FUSED
     st = torch.cuda.current_stream().cuda_stream
     for name in args.models.split(","):
         tm = G.model(name)

@@ -139,6 +139,11 @@ int main() {
                     printf("grid %3d A %s N %3d chains %d: %7.1f clk/mma (floor %5.1f, pipe %4.1f %%)\n", grid, a_tmem ? "tmem" : "smem", N, C,
                            (double)h[0].clk_mma / n, N / 2.0, 100.0 * (N / 2.0) * n / (double)h[0].clk_mma);
                 }
+    printf("# latency: issue n MMAs (N = 96, A in tensor memory) + tcgen05.commit, spin on the mbarrier: clk from first issue to wake-up\n");
+    for (int nn : {1, 2, 4, 6, 8, 16, 32}) {
+        run(96, 1, nn, 1, 0, 1, sms);
+        printf("n %2d: %lld clk (floor %d)\n", nn, h[0].clk_mma, nn * 48);
+    }
     printf("# tcgen05.ld 32x32b.x32 by four warps (each instruction: 4 KB per warp)\n");
     run(96, 1, n, 0, 2048, 0, sms);
     printf("ld alone              : %7.1f clk per x32 load per warp -> %.1f B/clk/SM\n", (double)h[0].clk_ld / 2048, 4.0 * 4096 * 2048 / (double)h[0].clk_ld);
