@@ -1,6 +1,7 @@
 // C ABI of libbayescard_b200.so: model lifecycle, kernel dispatch, host-buffer pipeline,
 // synthetic query generator, FP32 peak probe.  See include/bayescard_b200.h for the contract.
 #include <atomic>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -46,6 +47,11 @@ struct BcHostPipe {
     // WSPARSE path: weighted runs in, DENSE_F32 rows built on the device
     float* d_wdense[kSlots]{};
     size_t cap_wq = 0;
+    // PACKED path: klen bytes, block offsets and the entry bit stream
+    uint8_t* d_klen[kSlots]{};
+    uint32_t* d_blk[kSlots]{};
+    uint32_t* d_pay[kSlots]{};
+    size_t cap_pq = 0, cap_pay = 0;
 };
 
 static void pipe_free(BcHostPipe* p) {
@@ -59,6 +65,9 @@ static void pipe_free(BcHostPipe* p) {
         cudaFreeHost(p->h_out[i]);
         cudaFree(p->d_rowoff[i]);
         cudaFree(p->d_wdense[i]);
+        cudaFree(p->d_klen[i]);
+        cudaFree(p->d_blk[i]);
+        cudaFree(p->d_pay[i]);
         cudaFree(p->d_entries[i]);
         cudaFree(p->d_bits[i]);
         cudaFreeHost(p->h_rowoff[i]);
@@ -364,6 +373,80 @@ extern "C" int bc_query_batch(bc_model* m, const void* desc, size_t nq, int fmt,
     if (kernel == BC_KERNEL_GENERIC || kernel == BC_KERNEL_AUTO) return bc_k1_launch(m, desc, nq, fmt, fan_mask, out, st);
     bc_set_error("kernel %d not available in this build", kernel);
     return BC_EINVAL;
+}
+
+extern "C" int bc_query_batch_scaled(bc_model* m, const void* desc, size_t nq, int fmt, const uint32_t* fan_mask, float* out_mant,
+                                     int32_t* out_exp, int kernel, void* stream) {
+    if (!m || m->device < 0) { bc_set_error("model has no device (host-only model)"); return BC_EINVAL; }
+    if (nq == 0) return BC_OK;
+    if (!desc || !out_mant || !out_exp) { bc_set_error("desc/out is NULL"); return BC_EINVAL; }
+    int rc = check_format(m, fmt);
+    if (rc) return rc;
+    BC_CUDA_CHECK(cudaSetDevice(m->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool is_range = fmt == BC_DESC_RANGE_U8 || fmt == BC_DESC_RANGE_U16;
+    if (kernel == BC_KERNEL_AUTO)   // large domains: the batched path (K1 re-reads every CPT once per query)
+        kernel = (is_range && !fan_mask && (m->max_card > 256 || m->lam_total > 4096)) ? BC_KERNEL_GEMM : BC_KERNEL_GENERIC;
+    if (kernel == BC_KERNEL_GEMM || kernel == BC_KERNEL_GEMM_SIMT)
+        return bc_k2_launch(m, desc, nq, fmt, fan_mask, out_mant, kernel == BC_KERNEL_GEMM, st, out_exp);
+    if (kernel == BC_KERNEL_GENERIC) return bc_k1_launch(m, desc, nq, fmt, fan_mask, out_mant, st, out_exp);
+    bc_set_error("scaled results are served by BC_KERNEL_GENERIC and BC_KERNEL_GEMM(_SIMT), not by kernel %d", kernel);
+    return BC_EINVAL;
+}
+
+extern "C" int bc_query_batch_scaled_host(bc_model* m, const void* desc, size_t nq, int fmt, const uint32_t* fan_mask, double* out,
+                                          int kernel) {
+    if (!m || m->device < 0) { bc_set_error("model has no device (host-only model)"); return BC_EINVAL; }
+    if (nq == 0) return BC_OK;
+    if (!desc || !out) { bc_set_error("desc/out is NULL"); return BC_EINVAL; }
+    int rc = check_format(m, fmt);
+    if (rc) return rc;
+    BC_CUDA_CHECK(cudaSetDevice(m->device));
+    // not a throughput path (wide-range results are the rare case): one synchronous round trip in chunks
+    const size_t stride = (size_t)bc_model_desc_stride(m, fmt);
+    size_t chunk = (64u << 20) / stride;
+    if (chunk < 4096) chunk = 4096;
+    if (chunk > nq) chunk = nq;
+    void* d_desc = nullptr;
+    uint32_t* d_mask = nullptr;
+    float* d_m = nullptr;
+    int32_t* d_e = nullptr;
+    auto cleanup = [&]() { cudaFree(d_desc); cudaFree(d_mask); cudaFree(d_m); cudaFree(d_e); };
+    std::vector<float> hm;
+    std::vector<int32_t> he;
+    try {
+        hm.resize(chunk);
+        he.resize(chunk);
+    } catch (const std::bad_alloc&) {
+        bc_set_error("out of host memory");
+        return BC_ENOMEM;
+    }
+#define CKS(expr)                                                                        \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            bc_set_error("%s failed: %s", #expr, cudaGetErrorString(_e));                \
+            cleanup();                                                                   \
+            return BC_ECUDA;                                                             \
+        }                                                                                \
+    } while (0)
+    CKS(cudaMalloc(&d_desc, chunk * stride));
+    if (fan_mask) CKS(cudaMalloc(&d_mask, chunk * m->mask_words * 4));
+    CKS(cudaMalloc(&d_m, chunk * 4));
+    CKS(cudaMalloc(&d_e, chunk * 4));
+    for (size_t q0 = 0; q0 < nq; q0 += chunk) {
+        const size_t cq = nq - q0 < chunk ? nq - q0 : chunk;
+        CKS(cudaMemcpy(d_desc, static_cast<const unsigned char*>(desc) + q0 * stride, cq * stride, cudaMemcpyHostToDevice));
+        if (fan_mask) CKS(cudaMemcpy(d_mask, fan_mask + q0 * m->mask_words, cq * m->mask_words * 4, cudaMemcpyHostToDevice));
+        rc = bc_query_batch_scaled(m, d_desc, cq, fmt, fan_mask ? d_mask : nullptr, d_m, d_e, kernel, nullptr);
+        if (rc) { cleanup(); return rc; }
+        CKS(cudaMemcpy(hm.data(), d_m, cq * 4, cudaMemcpyDeviceToHost));
+        CKS(cudaMemcpy(he.data(), d_e, cq * 4, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < cq; ++i) out[q0 + i] = std::ldexp((double)hm[i], he[i]);
+    }
+#undef CKS
+    cleanup();
+    return BC_OK;
 }
 
 static int pipe_streams(bc_model* m) {
@@ -701,6 +784,155 @@ extern "C" int bc_query_batch_sparse_host(bc_model* m, const uint32_t* row_off, 
 extern "C" int bc_query_batch_wsparse_host(bc_model* m, const uint32_t* row_off, const uint32_t* words, size_t nq,
                                            const uint32_t* fan_mask, float* out, int kernel) {
     return sparse_host_impl(m, row_off, words, nq, fan_mask, out, kernel, true);
+}
+
+// ------------------------------------------------------------------------------------ PACKED wire format
+extern "C" int bc_model_packed_geometry(const bc_model* m, int* entry_bits, int* col_bits, int* state_bits) {
+    if (!m) { bc_set_error("model is NULL"); return BC_EINVAL; }
+    int cb, sb;
+    bc_packed_geometry(m, &cb, &sb);
+    if (entry_bits) *entry_bits = cb + 2 * sb;
+    if (col_bits) *col_bits = cb;
+    if (state_bits) *state_bits = sb;
+    if (cb + 2 * sb > 31) { bc_set_error("PACKED entries hold at most 31 bits; this model needs %d", cb + 2 * sb); return BC_ELIMIT; }
+    return BC_OK;
+}
+
+extern "C" int bc_pack_sparse(const bc_model* m, const uint32_t* row_off, const uint32_t* entries, size_t nq, uint8_t* klen,
+                              uint32_t* blk_off, void* payload, size_t payload_capacity, size_t* payload_bytes) {
+    if (!m || !row_off || (!klen && nq) || !blk_off || !payload) { bc_set_error("bad arguments"); return BC_EINVAL; }
+    int w, cb, sb;
+    int rc = bc_model_packed_geometry(m, &w, &cb, &sb);
+    if (rc) return rc;
+    const size_t ne = nq ? (size_t)row_off[nq] - row_off[0] : 0;
+    const size_t need = ((ne * (size_t)w + 31) / 32 + 2) * 4;   // whole 32-bit words + 2: the expansion kernel reads two words per entry
+    if (payload_bytes) *payload_bytes = need;
+    if (need > payload_capacity) { bc_set_error("payload buffer too small: %zu B needed", need); return BC_EINVAL; }
+    if (ne && !entries) { bc_set_error("entries is NULL"); return BC_EINVAL; }
+    if (ne >= (1ull << 32)) { bc_set_error("batch too large for 32-bit entry indices: split it"); return BC_ELIMIT; }
+    std::memset(payload, 0, need);
+    uint32_t* words = static_cast<uint32_t*>(payload);
+    const uint32_t e_base = nq ? row_off[0] : 0;
+    size_t e = 0;
+    for (size_t q = 0; q < nq; ++q) {
+        if (q % BC_PACKED_BLOCK == 0) blk_off[q / BC_PACKED_BLOCK] = (uint32_t)e;
+        const uint32_t a = row_off[q], b = row_off[q + 1];
+        if (b < a || b - a > 255) { bc_set_error("query %zu: %u entries (PACKED holds at most 255 per query)", q, b - a); return BC_ELIMIT; }
+        klen[q] = (uint8_t)(b - a);
+        int prev = -1;
+        for (uint32_t i = a; i < b; ++i, ++e) {
+            const uint32_t x = entries[i];
+            const int col = (int)(x & 0x7fffu), cont = (int)((x >> 15) & 1u);
+            const uint32_t lo = (x >> 16) & 0xffu, hi = x >> 24;
+            if (cont != (col == prev)) {   // PACKED has no continuation bit: entries of a column must be adjacent, first one without `cont`
+                bc_set_error("query %zu: entries must be grouped by column (continuation entries right behind their column's first)", q);
+                return BC_EINVAL;
+            }
+            if (col >= (1 << cb) || lo >= (1u << sb) || hi >= (1u << sb)) { bc_set_error("query %zu: entry out of range for this model", q); return BC_EINVAL; }
+            prev = col;
+            const uint64_t v = (uint64_t)col | ((uint64_t)lo << cb) | ((uint64_t)hi << (cb + sb));
+            const size_t bit = e * (size_t)w;
+            const uint64_t sh = v << (bit & 31);
+            words[bit >> 5] |= (uint32_t)sh;
+            words[(bit >> 5) + 1] |= (uint32_t)(sh >> 32);
+        }
+        (void)e_base;
+    }
+    blk_off[(nq + BC_PACKED_BLOCK - 1) / BC_PACKED_BLOCK] = (uint32_t)e;
+    return BC_OK;
+}
+
+extern "C" int bc_expand_packed(bc_model* m, const uint8_t* klen, const uint32_t* blk_off, const void* payload, size_t nq, void* dst_bits,
+                                void* stream) {
+    if (!m || m->device < 0) { bc_set_error("model has no device (host-only model)"); return BC_EINVAL; }
+    if (nq && (!klen || !blk_off || !payload || !dst_bits)) { bc_set_error("klen/blk_off/payload/dst is NULL"); return BC_EINVAL; }
+    BC_CUDA_CHECK(cudaSetDevice(m->device));
+    return bc_expand_packed_launch(m, klen, blk_off, static_cast<const uint32_t*>(payload), 0ull, nq, dst_bits, static_cast<cudaStream_t>(stream));
+}
+
+// Host buffers in (pinned for full speed), fp32 probabilities out.  Batches beyond one chunk of 1 M queries (BC_PACKED_CHUNK
+// overrides; a multiple of 128) flow through three slots on three streams (H2D | expansion + inference | D2H).  Smaller
+// chunks were measured and LOSE on this platform (profiles/r2_e2e_packed_chunk_sweep.txt: every chunk costs ~100 us of
+// enqueue / event latency -- 1 M queries: one chunk 1.69e9 q/s, four chunks 1.42e9, sixteen 0.60e9), so a 1 M-query call
+// is one H2D copy of 15 MB, two kernels and one D2H copy; what it gains over SPARSE is the bytes: 15.4 B instead of 31 B per
+// Census query.
+extern "C" int bc_query_batch_packed_host(bc_model* m, const uint8_t* klen, const uint32_t* blk_off, const void* payload, size_t payload_bytes,
+                                          size_t nq, const uint32_t* fan_mask, float* out, int kernel) {
+    if (!m || m->device < 0) { bc_set_error("model has no device (host-only model)"); return BC_EINVAL; }
+    if (nq == 0) return BC_OK;
+    if (!klen || !blk_off || !payload || !out) { bc_set_error("klen/blk_off/payload/out is NULL"); return BC_EINVAL; }
+    int w, cb, sb;
+    int rc = bc_model_packed_geometry(m, &w, &cb, &sb);
+    if (rc) return rc;
+    BC_CUDA_CHECK(cudaSetDevice(m->device));
+    size_t chunk = 1024 * 1024;
+    if (const char* env = std::getenv("BC_PACKED_CHUNK")) {
+        const long long v = std::atoll(env);
+        if (v >= BC_PACKED_BLOCK) chunk = (size_t)v / BC_PACKED_BLOCK * BC_PACKED_BLOCK;
+    }
+    const size_t nblk_total = (nq + BC_PACKED_BLOCK - 1) / BC_PACKED_BLOCK;
+    if (chunk > nblk_total * BC_PACKED_BLOCK) chunk = nblk_total * BC_PACKED_BLOCK;
+    const size_t nchunks = (nq + chunk - 1) / chunk;
+    const size_t total_words = payload_bytes / 4;
+    const uint32_t* pay = static_cast<const uint32_t*>(payload);
+    // largest payload slice of a chunk (+ 2 words of read-ahead)
+    size_t max_words = 4;
+    for (size_t ci = 0; ci < nchunks; ++ci) {
+        const size_t b0 = ci * chunk / BC_PACKED_BLOCK, q1 = (ci + 1) * chunk < nq ? (ci + 1) * chunk : nq;
+        const size_t b1 = (q1 + BC_PACKED_BLOCK - 1) / BC_PACKED_BLOCK;
+        if (blk_off[b1] < blk_off[b0]) { bc_set_error("blk_off is not monotone at block %zu", b0); return BC_EINVAL; }
+        const size_t w0 = ((size_t)blk_off[b0] * w) >> 5, w1 = (((size_t)blk_off[b1] * w + 31) >> 5) + 2;
+        if (w1 > total_words) { bc_set_error("payload shorter than blk_off says (%zu words needed, %zu given)", w1, total_words); return BC_EINVAL; }
+        if (w1 - w0 > max_words) max_words = w1 - w0;
+    }
+    std::lock_guard<std::mutex> lock(m->pipe_mu);
+    rc = sparse_ensure(m, chunk, 1);
+    if (rc) return rc;
+    BcHostPipe* p = m->pipe;
+    if (chunk > p->cap_pq || max_words * 4 > p->cap_pay) {
+        p->cap_pq = 0;
+        p->cap_pay = 0;
+        for (int i = 0; i < BcHostPipe::kSlots; ++i) {
+            cudaFree(p->d_klen[i]); cudaFree(p->d_blk[i]); cudaFree(p->d_pay[i]);
+            p->d_klen[i] = nullptr; p->d_blk[i] = nullptr; p->d_pay[i] = nullptr;
+            BC_CUDA_CHECK(cudaMalloc(&p->d_klen[i], chunk));
+            BC_CUDA_CHECK(cudaMalloc(&p->d_blk[i], (chunk / BC_PACKED_BLOCK + 2) * 4));
+            BC_CUDA_CHECK(cudaMalloc(&p->d_pay[i], max_words * 4));
+        }
+        p->cap_pq = chunk;
+        p->cap_pay = max_words * 4;
+    }
+    PipeDrain drain(p);
+    for (size_t ci = 0; ci < nchunks; ++ci) {
+        const int s = (int)(ci % BcHostPipe::kSlots);
+        const size_t q0 = ci * chunk, cq = (q0 + chunk <= nq) ? chunk : nq - q0;
+        const size_t b0 = q0 / BC_PACKED_BLOCK, nb = (cq + BC_PACKED_BLOCK - 1) / BC_PACKED_BLOCK;
+        if (ci >= (size_t)BcHostPipe::kSlots) BC_CUDA_CHECK(cudaEventSynchronize(p->ev_out[s]));   // the slot's buffers are free again
+        const size_t w0 = ((size_t)blk_off[b0] * w) >> 5, w1 = (((size_t)blk_off[b0 + nb] * w + 31) >> 5) + 2;
+        drain.armed = true;
+        BC_CUDA_CHECK(cudaMemcpyAsync(p->d_klen[s], klen + q0, cq, cudaMemcpyHostToDevice, p->s_in));
+        BC_CUDA_CHECK(cudaMemcpyAsync(p->d_blk[s], blk_off + b0, (nb + 1) * 4, cudaMemcpyHostToDevice, p->s_in));
+        BC_CUDA_CHECK(cudaMemcpyAsync(p->d_pay[s], pay + w0, (w1 - w0) * 4, cudaMemcpyHostToDevice, p->s_in));
+        const uint32_t* dmask = nullptr;
+        if (fan_mask) {
+            BC_CUDA_CHECK(cudaMemcpyAsync(p->d_mask[s], fan_mask + q0 * m->mask_words, cq * m->mask_words * 4, cudaMemcpyHostToDevice, p->s_in));
+            dmask = p->d_mask[s];
+        }
+        BC_CUDA_CHECK(cudaEventRecord(p->ev_in[s], p->s_in));
+        BC_CUDA_CHECK(cudaStreamWaitEvent(p->s_k, p->ev_in[s], 0));
+        rc = bc_expand_packed_launch(m, p->d_klen[s], p->d_blk[s], p->d_pay[s], (unsigned long long)w0, cq, p->d_bits[s], p->s_k);
+        if (rc) return rc;
+        rc = bc_query_batch(m, p->d_bits[s], cq, BC_DESC_BITS, dmask, p->d_out[s], kernel, p->s_k);
+        if (rc) return rc;
+        BC_CUDA_CHECK(cudaEventRecord(p->ev_k[s], p->s_k));
+        BC_CUDA_CHECK(cudaStreamWaitEvent(p->s_out, p->ev_k[s], 0));
+        BC_CUDA_CHECK(cudaMemcpyAsync(out + q0, p->d_out[s], cq * 4, cudaMemcpyDeviceToHost, p->s_out));
+        BC_CUDA_CHECK(cudaEventRecord(p->ev_out[s], p->s_out));
+        BC_CUDA_CHECK(cudaStreamWaitEvent(p->s_in, p->ev_out[s], 0));
+    }
+    BC_CUDA_CHECK(cudaStreamSynchronize(p->s_out));
+    drain.armed = false;
+    return BC_OK;
 }
 
 extern "C" int bc_expand_wsparse(bc_model* m, const uint32_t* row_off, const uint32_t* words, size_t nq, float* dst_dense,

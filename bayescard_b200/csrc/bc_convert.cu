@@ -101,6 +101,65 @@ __global__ void __launch_bounds__(128) sparse_to_bits_kernel(const BcBitsRec* __
     }
 }
 
+// PACKED -> BITS.  PACKED is the densest wire form of what SPARSE carries (unit-weight range / IN-list queries), made for the
+// one link that bounds the end-to-end rate, PCIe:
+//     klen[q]     uint8    number of entries of query q (<= 255)
+//     blk_off[b]  uint32   index of the first entry of block b of kPackedBlock = 128 queries
+//     payload     bit stream, entry e at bits [e * w, (e + 1) * w), little endian in 32-bit words;
+//                 w = cb + 2 * sb, cb = bits(n_nodes - 1), sb = bits(max_card - 1);  entry = col | lo << cb | hi << (cb + sb)
+// Entries of a query are sorted by column; an entry whose column equals its predecessor's ORs into the column's mask (IN
+// lists), the first entry of a column replaces it.  Census: 17 bits per entry, 17 B per query against 35 B as SPARSE.
+// One CTA per block of 128 queries: a warp-shuffle scan of klen gives every thread its first entry.
+__global__ void __launch_bounds__(128) packed_to_bits_kernel(const BcBitsRec* __restrict__ bits, int n, const uint32_t* __restrict__ dflt,
+                                                            int words, const uint8_t* __restrict__ klen, const uint32_t* __restrict__ blk_off,
+                                                            const uint32_t* __restrict__ payload, unsigned long long word_base, int cb, int sb,
+                                                            uint32_t* __restrict__ dst, size_t nq) {
+    extern __shared__ uint32_t smem[];
+    uint32_t* tile = smem;
+    BcBitsRec* s_bits = reinterpret_cast<BcBitsRec*>(smem + (size_t)words * blockDim.x);
+    __shared__ uint32_t s_warp[4];
+    for (int v = threadIdx.x; v < n; v += blockDim.x) s_bits[v] = bits[v];
+    __syncthreads();
+    const int T = blockDim.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* row = tile + threadIdx.x;
+    const int w = cb + 2 * sb;
+    const uint32_t cmask = (1u << cb) - 1u, smask = (1u << sb) - 1u;
+    for (size_t blk = blockIdx.x; blk * T < nq; blk += gridDim.x) {
+        const size_t q = blk * T + threadIdx.x;
+        const uint32_t k = q < nq ? klen[q] : 0u;
+        uint32_t incl = k;   // inclusive scan over the CTA
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += x;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        uint32_t before = 0;
+        for (int i = 0; i < warp; ++i) before += s_warp[i];
+        __syncthreads();
+        if (q >= nq) continue;
+        const unsigned long long e0 = (unsigned long long)blk_off[blk] + before + incl - k;
+        for (int i = 0; i < words; ++i) row[i * T] = dflt[i];
+        int prev = -1;
+        for (uint32_t j = 0; j < k; ++j) {
+            const unsigned long long bit = (e0 + j) * (unsigned long long)w;
+            const unsigned long long wi = (bit >> 5) - word_base;
+            const uint32_t sh = (uint32_t)(bit & 31u);
+            const uint32_t a = __ldg(payload + wi), b = __ldg(payload + wi + 1);   // (the stream is padded by 8 bytes)
+            const uint32_t x = __funnelshift_r(a, b, sh);
+            const int col = (int)(x & cmask);
+            if (col < n) {   // ignored otherwise, like a column outside the root component
+                const BcBitsRec r = s_bits[col];
+                row_select(row, T, r.bit_off, r.card, (int)((x >> cb) & smask), (int)((x >> (cb + sb)) & smask), col == prev);
+            }
+            prev = col;
+        }
+        uint4* out = reinterpret_cast<uint4*>(dst + q * words);
+        for (int i = 0; i < words; i += 4) out[i >> 2] = make_uint4(row[i * T], row[(i + 1) * T], row[(i + 2) * T], row[(i + 3) * T]);
+    }
+}
+
 int grid_for(const bc_model* m, size_t nq, int threads) {
     long long grid = (long long)((nq + threads - 1) / threads);
     const long long cap = (long long)m->sm_count * 16;
@@ -190,6 +249,39 @@ int bc_expand_wsparse_launch(bc_model* m, const uint32_t* row_off, const uint32_
     if (grid > cap) grid = cap;
     wsparse_to_dense_kernel<<<(int)grid, threads, 0, stream>>>(m->d_nodes, m->n, m->d_dense_default, m->lam_total, row_off, words,
                                                                dst_dense, nq);
+    BC_CUDA_CHECK(cudaGetLastError());
+    bc_count_launch();
+    return BC_OK;
+}
+
+static int bits_for(int x) {   // bits needed for values 0 .. x
+    int b = 1;
+    while ((1 << b) <= x) ++b;
+    return b;
+}
+void bc_packed_geometry(const bc_model* m, int* col_bits, int* state_bits) {
+    *col_bits = bits_for(m->n - 1);
+    *state_bits = bits_for(m->max_card - 1);
+}
+
+int bc_expand_packed_launch(bc_model* m, const uint8_t* klen, const uint32_t* blk_off, const uint32_t* payload, unsigned long long word_base,
+                            size_t nq, void* dst_bits, cudaStream_t stream) {
+    if (nq == 0) return BC_OK;
+    int cb, sb;
+    bc_packed_geometry(m, &cb, &sb);
+    if (cb + 2 * sb > 31) {
+        bc_set_error("PACKED entries hold at most 31 bits (%d columns, domains up to %d states need %d)", m->n, m->max_card, cb + 2 * sb);
+        return BC_ELIMIT;
+    }
+    const int threads = BC_PACKED_BLOCK;
+    const size_t smem = ((size_t)m->bits_words * threads) * 4 + (size_t)m->n * sizeof(BcBitsRec);
+    if (smem > (size_t)m->smem_optin) {
+        bc_set_error("model too large for the packed expansion kernel (%zu B of shared memory)", smem);
+        return BC_ELIMIT;
+    }
+    BC_CUDA_CHECK(cudaFuncSetAttribute(packed_to_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    packed_to_bits_kernel<<<grid_for(m, nq, threads), threads, smem, stream>>>(m->d_bits, m->n, m->d_bits_default, m->bits_words, klen, blk_off,
+                                                                              payload, word_base, cb, sb, static_cast<uint32_t*>(dst_bits), nq);
     BC_CUDA_CHECK(cudaGetLastError());
     bc_count_launch();
     return BC_OK;

@@ -112,16 +112,21 @@ static inline int64_t bc_round_up(int64_t x, int64_t a) { return (x + a - 1) / a
 
 // k1_generic.cu
 int bc_k1_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32_t* fan_mask,
-                 float* out, cudaStream_t stream);
+                 float* out, cudaStream_t stream, int32_t* out_exp = nullptr);
 // bc_convert.cu
 int bc_convert_launch(bc_model* m, const void* src, int src_fmt, void* dst, int dst_fmt, size_t nq, cudaStream_t stream);
 int bc_expand_sparse_launch(bc_model* m, const uint32_t* row_off, const uint32_t* entries, size_t nq, void* dst_bits,
                             cudaStream_t stream);
 int bc_expand_wsparse_launch(bc_model* m, const uint32_t* row_off, const uint32_t* words, size_t nq, float* dst_dense,
                              cudaStream_t stream);
+#define BC_PACKED_BLOCK 128   // queries per blk_off entry of the PACKED wire format
+void bc_packed_geometry(const bc_model* m, int* col_bits, int* state_bits);
+// payload points at 32-bit word `word_base` of the bit stream (a slice of a larger batch keeps absolute entry indices)
+int bc_expand_packed_launch(bc_model* m, const uint8_t* klen, const uint32_t* blk_off, const uint32_t* payload, unsigned long long word_base,
+                            size_t nq, void* dst_bits, cudaStream_t stream);
 // k2_batched.cu / k2_umma.cu
 int bc_k2_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32_t* fan_mask, float* out, int use_umma,
-                 cudaStream_t stream);
+                 cudaStream_t stream, int32_t* out_exp = nullptr);
 void bc_k2_free(bc_model* m);
 // one internal edge on the tensor cores; BC_ELIMIT = shape not served (caller falls back to FP32 SIMT)
 int bc_k2_umma_edge(bc_model* m, const uint8_t* desc, size_t dstride, int fmt, size_t q0, int rows, int v, float* lam_v,

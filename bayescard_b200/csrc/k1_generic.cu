@@ -36,6 +36,7 @@ struct K1Params {
     const uint32_t* fan_mask;
     int mask_words;
     float* out;
+    int32_t* out_exp;  // scaled results: out[q] * 2^out_exp[q] (nullptr: plain fp32 results)
     size_t nq;
     // shared memory carve-up (bytes from the base, all multiples of 16)
     unsigned off_arena, off_nodes, off_ent, off_bits, off_warp, warp_bytes, off_lam, off_desc, off_act;
@@ -72,6 +73,22 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigne
             smem_u32(dst)),
         "l"(src), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
+}
+
+// Scaled results (fp32 range): after a message has been multiplied into lambda_pa the row is renormalised to a maximum in
+// [1, 2) -- an exact power-of-two scale -- and the exponent is carried per query.  The reference computes in fp64
+// (Pgmpy/inference/ExactInference.py:157-177); ten narrow predicates on wide domains go below 1e-38.
+__device__ __forceinline__ int k1_renormalise(float* row, int card, int lane) {
+    float mx = 0.f;
+    for (int c = lane; c < card; c += kWarp) mx = fmaxf(mx, fabsf(row[c]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (!(mx > 0.f) || !isfinite(mx)) return 0;
+    const int e = ilogbf(mx);
+    if (e == 0) return 0;
+    const float s = ldexpf(1.f, -e > 126 ? 126 : -e), s2 = -e > 126 ? ldexpf(1.f, -e - 126) : 1.f;   // (2^-e itself may not be a normal float)
+    for (int c = lane; c < card; c += kWarp) row[c] = row[c] * s * s2;
+    return e;
 }
 
 template <int FMT, bool ARENA_SMEM>
@@ -219,6 +236,7 @@ __global__ void __launch_bounds__(512) k1_kernel(const K1Params P) {
         __syncwarp();
 
         // ---- 2. edges in reverse topological order -----------------------------------------
+        int esum = 0;
         for (int v = P.n - 1; v >= 1; --v) {
             if (!act[v]) continue;  // warp uniform
             const BcNodeRec nd = s_nodes[v];
@@ -296,6 +314,10 @@ __global__ void __launch_bounds__(512) k1_kernel(const K1Params P) {
                 }
             }
             __syncwarp();
+            if (P.out_exp != nullptr) {
+                esum += k1_renormalise(lam_p, cpa, lane);
+                __syncwarp();
+            }
         }
 
         // ---- 3. root: sum_c lambda_0[c] * T_0[c] -----------------------------------------------
@@ -306,7 +328,10 @@ __global__ void __launch_bounds__(512) k1_kernel(const K1Params P) {
             for (int c = lane; c < nd.card; c += kWarp) acc = fmaf(lam[nd.lam_off + c], T[c], acc);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane == 0) P.out[q] = acc;
+            if (lane == 0) {
+                P.out[q] = acc;
+                if (P.out_exp != nullptr) P.out_exp[q] = esum;
+            }
         }
         __syncwarp();
     }
@@ -332,7 +357,7 @@ int launch_fmt(bc_model* m, K1Params& P, bool arena_smem, int threads, int grid,
 }  // namespace
 
 int bc_k1_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32_t* fan_mask, float* out,
-                 cudaStream_t stream) {
+                 cudaStream_t stream, int32_t* out_exp) {
     if (nq == 0) return BC_OK;
     K1Params P{};
     P.nodes = m->d_nodes;
@@ -347,6 +372,7 @@ int bc_k1_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32
     P.fan_mask = fan_mask;
     P.mask_words = m->mask_words;
     P.out = out;
+    P.out_exp = out_exp;
     P.nq = nq;
 
     const size_t arena_bytes = (size_t)bc_round_up((int64_t)m->arena_floats_padded * 4, 16);

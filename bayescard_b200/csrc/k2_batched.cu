@@ -55,8 +55,8 @@ __global__ void k2_prefix_kernel(const float* __restrict__ T, int card, int card
 template <int FMT>
 __global__ void __launch_bounds__(256) k2_leaf_kernel(const uint8_t* __restrict__ desc, size_t dstride, size_t q0,
                                                       int rows, int v, int card, int card_pa,
-                                                      const double* __restrict__ S, float* __restrict__ lam_pa,
-                                                      int ld_pa, int accumulate) {
+                                                      const double* __restrict__ S, const float* __restrict__ T, int ld_t,
+                                                      float* __restrict__ lam_pa, int ld_pa, int accumulate) {
     const long long total = (long long)rows * card_pa;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int b = (int)(i / card_pa), p = (int)(i - (long long)b * card_pa);
@@ -67,7 +67,16 @@ __global__ void __launch_bounds__(256) k2_leaf_kernel(const uint8_t* __restrict_
             if (!accumulate) *dst = 1.f;
             continue;
         }
-        const float val = hi >= lo ? (float)(S[(size_t)(hi + 1) * card_pa + p] - S[(size_t)lo * card_pa + p]) : 0.f;
+        float val = 0.f;
+        if (hi - lo < 16) {
+            // narrow ranges (equality predicates above all) are summed directly: a difference of two prefix sums carries their
+            // ABSOLUTE rounding error (~1e-16), which on a rare state (T ~ 1e-12) is 1e-4 relative
+            double acc = 0.0;
+            for (int c = lo; c <= hi; ++c) acc += (double)T[(size_t)c * ld_t + p];
+            val = (float)acc;
+        } else {
+            val = (float)(S[(size_t)(hi + 1) * card_pa + p] - S[(size_t)lo * card_pa + p]);
+        }
         *dst = accumulate ? *dst * val : val;
     }
 }
@@ -207,9 +216,30 @@ __global__ void __launch_bounds__(256) k2_root_kernel(const uint8_t* __restrict_
     }
 }
 
+// Scaled results (fp32 range): after an edge has been multiplied into Lambda_pa every row is renormalised to a maximum in
+// [1, 2) by an exact power of two, the exponent is accumulated per query.  One warp per row.
+__global__ void __launch_bounds__(256) k2_rownorm_kernel(float* __restrict__ lam, int ld, int rows, int card, int32_t* __restrict__ exps) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int b = warp; b < rows; b += nwarps) {
+        float* row = lam + (size_t)b * ld;
+        float mx = 0.f;
+        for (int c = lane; c < card; c += 32) mx = fmaxf(mx, fabsf(row[c]));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (!(mx > 0.f) || !isfinite(mx)) continue;
+        const int e = ilogbf(mx);
+        if (e == 0) continue;
+        const float s = ldexpf(1.f, -e > 126 ? 126 : -e), s2 = -e > 126 ? ldexpf(1.f, -e - 126) : 1.f;
+        for (int c = lane; c < card; c += 32) row[c] = row[c] * s * s2;
+        if (lane == 0) exps[b] += e;
+    }
+}
+
 template <int FMT>
 int run_tile(bc_model* m, const uint8_t* desc, size_t dstride, size_t q0, int rows, size_t tile_rows, float* out,
-             float* const* lam, const int* ld, int use_umma, cudaStream_t st) {
+             float* const* lam, const int* ld, int use_umma, cudaStream_t st, int32_t* out_exp) {
     const int n = m->n;
     std::vector<char> written(n, 0);
     for (int v = n - 1; v >= 1; --v) {
@@ -220,8 +250,8 @@ int run_tile(bc_model* m, const uint8_t* desc, size_t dstride, size_t q0, int ro
             const long long total = (long long)rows * nd.card_pa;
             long long grid = (total + 255) / 256;
             if (grid > (long long)m->sm_count * 16) grid = (long long)m->sm_count * 16;
-            k2_leaf_kernel<FMT><<<(int)grid, 256, 0, st>>>(desc, dstride, q0, rows, v, nd.card, nd.card_pa,
-                                                           m->k2->d_prefix[v], lam[pa], ld[pa], acc);
+            k2_leaf_kernel<FMT><<<(int)grid, 256, 0, st>>>(desc, dstride, q0, rows, v, nd.card, nd.card_pa, m->k2->d_prefix[v],
+                                                           m->d_arena + nd.cpt_off, nd.stride, lam[pa], ld[pa], acc);
         } else {
             const float* T = m->d_arena + nd.cpt_off;
             int rc = BC_ELIMIT;
@@ -246,6 +276,13 @@ int run_tile(bc_model* m, const uint8_t* desc, size_t dstride, size_t q0, int ro
         BC_CUDA_CHECK(cudaGetLastError());
         bc_count_launch();
         written[pa] = 1;
+        if (out_exp) {
+            long long g = ((long long)rows * 32 + 255) / 256;
+            if (g > (long long)m->sm_count * 16) g = (long long)m->sm_count * 16;
+            k2_rownorm_kernel<<<(int)g, 256, 0, st>>>(lam[pa], ld[pa], rows, nd.card_pa, out_exp + q0);
+            BC_CUDA_CHECK(cudaGetLastError());
+            bc_count_launch();
+        }
     }
     const BcNodeRec& r0 = m->nodes[0];
     long long grid = ((long long)rows * 32 + 255) / 256;
@@ -290,7 +327,7 @@ static int k2_prepare(bc_model* m) {
 }
 
 int bc_k2_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32_t* fan_mask, float* out, int use_umma,
-                 cudaStream_t stream) {
+                 cudaStream_t stream, int32_t* out_exp) {
     if (fmt != BC_DESC_RANGE_U8 && fmt != BC_DESC_RANGE_U16) {
         bc_set_error("the batched large-domain kernel takes RANGE_U8 / RANGE_U16 descriptors");
         return BC_EINVAL;
@@ -375,10 +412,12 @@ int bc_k2_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32
     const size_t dstride = (size_t)bc_model_desc_stride(m, fmt);
     const uint8_t* d = static_cast<const uint8_t*>(desc);
     int rc = BC_OK;
+    if (out_exp) BC_CUDA_CHECK(cudaMemsetAsync(out_exp, 0, nq * sizeof(int32_t), stream));
     for (size_t q0 = 0; q0 < nq && rc == BC_OK; q0 += tile) {
         const int rows = (int)(nq - q0 < tile ? nq - q0 : tile);
-        rc = fmt == BC_DESC_RANGE_U8 ? run_tile<BC_DESC_RANGE_U8>(m, d, dstride, q0, rows, tile, out, lam.data(), ld.data(), use_umma, stream)
-                                     : run_tile<BC_DESC_RANGE_U16>(m, d, dstride, q0, rows, tile, out, lam.data(), ld.data(), use_umma, stream);
+        rc = fmt == BC_DESC_RANGE_U8
+                 ? run_tile<BC_DESC_RANGE_U8>(m, d, dstride, q0, rows, tile, out, lam.data(), ld.data(), use_umma, stream, out_exp)
+                 : run_tile<BC_DESC_RANGE_U16>(m, d, dstride, q0, rows, tile, out, lam.data(), ld.data(), use_umma, stream, out_exp);
     }
     BC_CUDA_CHECK(cudaEventRecord(k2->ws_event, stream));
     return rc;

@@ -61,9 +61,8 @@ struct K3Edge {            // 64 bytes, in the kernel parameter bank
     uint32_t idesc;        // tcgen05 instruction descriptor (M = 128, N = n_pad, TF32 x TF32 -> F32, K-major)
     uint64_t bimg_off;     // byte offset of the edge's operand images
     int32_t publish;       // >= 0: this edge is the LAST message into Lambda_pa, pa's own edge is `publish` (its producers may
-                           // start); -2: ... and pa is the root (the tile's result follows); -3: ... and pa is the root's only
-                           // child, folded into the result by the SIMT tail; -1: more messages to come
-    int32_t fin_guard;     // this edge is the first message into the node the finisher warps read (root, or the tail node)
+                           // start); -2: ... and pa is the root (the tile's result follows); -1: more messages to come
+    int32_t fin_guard;     // the first edge of a tile whose epilogue writes into the columns the finisher warps read (the root's message)
 };
 static_assert(sizeof(K3Edge) == 64, "K3Edge layout");
 
@@ -78,7 +77,6 @@ struct BcK3Plan {
     int d_col = 0, n_dbuf = 2;
     int b_stages = 4;
     int root_col = 0;
-    int tail_v = -1;               // the root's only child when the edge into the root is folded into the result in registers
     int ctas_per_sm = 1;
     size_t smem = 0;
     void* encode = nullptr;        // cuTensorMapEncodeTiled (DENSE_F32 rows are staged by 2-D TMA loads)
@@ -112,12 +110,6 @@ struct K3Params {
     int fan_n;                 // floats in the fan arena
     const float* root_T;       // T_root in the arena
     int root_card, root_col, root_bit_off, root_lam_off, root_fan_off;
-    // SIMT tail: when the root has ONE child v and card(v) * card(root) is small (every shipped DMV / IMDB model: a root of 2-7
-    // states over one wide child), the edge v -> root is not worth a tensor-core pass at the end of the dependency chain
-    // (4-6 blocks that wait for the epilogue of v's last child, a drain, another epilogue): the epilogue warps fold it into
-    // the root's dot product in registers.  tail_K = 0: no tail.
-    int tail_K, tail_v, tail_col_v, tail_bit_off, tail_lam_off, tail_fan_off, tail_stride;
-    const float* tail_T;       // T_v[c * tail_stride + r]
     float* out;
     size_t nq;
     long long n_tiles;
@@ -263,7 +255,7 @@ __device__ __forceinline__ uint32_t bits16(const uint32_t* my_bits, int bits_wor
     return __funnelshift_r(w0, w1, sh) & (valid >= 16 ? 0xFFFFu : ((1u << valid) - 1u));
 }
 
-// weights of 8 consecutive states [c0, c0 + 8) of a column for this thread's query (epilogue warps: root and SIMT tail)
+// weights of 8 consecutive states [c0, c0 + 8) of a column for this thread's query (the root's dot product)
 template <int FMT>
 __device__ __forceinline__ void weights8(const uint32_t* my_bits, int bits_words, const float* drow, int lam_off, int bit_off, int card, int c0,
                                          float* w) {
@@ -601,13 +593,14 @@ __global__ void __launch_bounds__(kThreads, 1) k3_kernel(const __grid_constant__
                 if (lane == 0) {
                     mbar_arrive(d_empty0 + 8 * db);                              // the accumulator may be overwritten
                     if (E.publish >= 0) mbar_arrive(lam_ready0 + 8 * E.publish);   // Lambda_pa is complete: pa's own edge may be built
-                    if (E.publish <= -2) mbar_arrive(fin_ready0);                  // ... the finisher warps take the tile from here
+                    if (E.publish == -2) mbar_arrive(fin_ready0);                  // ... the finisher warps take the tile from here
                 }
             }
         }
     } else if (warp >= kWarpFin) {
-        // ================= finisher warps: the root's dot product, or the SIMT tail (edge v -> root folded into it), per tile,
-        // while the other roles are already working on the next tile
+        // ================= finisher warps: the root's dot product per tile, while the other roles are already in the next tile
+        // (measured and dropped in round 2, profiles/r2_k3_tail_ab.txt: folding the root's only child into this step in
+        //  registers -- the reader of the hub's message then sits on the next tile's critical path)
         const int ql = tid & (kTile - 1);
         const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         uint32_t tile_iter = 0;
@@ -619,64 +612,20 @@ __global__ void __launch_bounds__(kThreads, 1) k3_kernel(const __grid_constant__
             tc_fence_after();
             const uint32_t* my_bits = s_bits + buf * bits_tile + ql;
             const float* drow = reinterpret_cast<const float*>(P.desc + qc * P.dstride);
-            const uint32_t* fm_q = s_fm + buf * fm_tile + ql;
-            const bool fan_root = P.root_fan_off >= 0 && P.fan_mask != nullptr && (fm_q[0] & 1u);
+            const bool fan_root = P.root_fan_off >= 0 && P.fan_mask != nullptr && (s_fm[buf * fm_tile + ql] & 1u);
             float res = 0.f;
-            if (P.tail_K == 0) {
-                // ---- root: sum_c w_0[c] * Lambda_0[c] * T_0[c]
-                for (int c0 = 0; c0 < P.root_card; c0 += 8) {
-                    float lv[8], w[8];
-                    tmem_ld8(tlane + (uint32_t)(P.root_col + c0), lv);
-                    weights8<FMT>(my_bits, P.bits_words, drow, P.root_lam_off, P.root_bit_off, P.root_card, c0, w);
-                    tmem_ld_wait();
+            // ---- root: sum_c w_0[c] * Lambda_0[c] * T_0[c]
+            for (int c0 = 0; c0 < P.root_card; c0 += 8) {
+                float lv[8], w[8];
+                tmem_ld8(tlane + (uint32_t)(P.root_col + c0), lv);
+                weights8<FMT>(my_bits, P.bits_words, drow, P.root_lam_off, P.root_bit_off, P.root_card, c0, w);
+                tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (c0 + j < P.root_card) {
-                            float x = lv[j] * w[j];
-                            if (fan_root) x *= s_fan[P.root_fan_off + c0 + j];
-                            res = fmaf(x, __ldg(P.root_T + c0 + j), res);
-                        }
-                }
-            } else {
-                // ---- SIMT tail: acc[r] = sum_c (w_v[c] * Lambda_v[c]) * T_v[c, r];  res = sum_r w_0[r] * T_0[r] * acc[r]
-                const int K = P.tail_K;
-                const bool fan_v = P.tail_fan_off >= 0 && P.fan_mask != nullptr && ((fm_q[(P.tail_v >> 5) * kTile] >> (P.tail_v & 31)) & 1u);
-                float acc[8];
-#pragma unroll
-                for (int r = 0; r < 8; ++r) acc[r] = 0.f;
-                for (int c0 = 0; c0 < K; c0 += 32) {   // 32 states per round trip: every load of the chunk is in flight at once
-                    float lv[32], w[32];
-#pragma unroll
-                    for (int g8 = 0; g8 < 4; ++g8)
-                        if (c0 + 8 * g8 < K) tmem_ld8(tlane + (uint32_t)(P.tail_col_v + c0 + 8 * g8), lv + 8 * g8);
-#pragma unroll
-                    for (int g8 = 0; g8 < 4; ++g8)
-                        if (c0 + 8 * g8 < K) weights8<FMT>(my_bits, P.bits_words, drow, P.tail_lam_off, P.tail_bit_off, K, c0 + 8 * g8, w + 8 * g8);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (c0 + j < K) {   // (warp-uniform)
-                            float u = lv[j] * w[j];
-                            if (fan_v) u *= s_fan[P.tail_fan_off + c0 + j];
-                            const float* T = P.tail_T + (size_t)(c0 + j) * P.tail_stride;
-                            const float4 t0 = __ldg(reinterpret_cast<const float4*>(T));
-                            acc[0] = fmaf(u, t0.x, acc[0]); acc[1] = fmaf(u, t0.y, acc[1]);
-                            acc[2] = fmaf(u, t0.z, acc[2]); acc[3] = fmaf(u, t0.w, acc[3]);
-                            if (P.root_card > 4) {
-                                const float4 t1 = __ldg(reinterpret_cast<const float4*>(T + 4));
-                                acc[4] = fmaf(u, t1.x, acc[4]); acc[5] = fmaf(u, t1.y, acc[5]);
-                                acc[6] = fmaf(u, t1.z, acc[6]); acc[7] = fmaf(u, t1.w, acc[7]);
-                            }
-                        }
-                }
-                float w0[8];
-                weights8<FMT>(my_bits, P.bits_words, drow, P.root_lam_off, P.root_bit_off, P.root_card, 0, w0);
-#pragma unroll
-                for (int r = 0; r < 8; ++r)
-                    if (r < P.root_card) {
-                        float x = acc[r] * w0[r];
-                        if (fan_root) x *= s_fan[P.root_fan_off + r];
-                        res = fmaf(x, __ldg(P.root_T + r), res);
+                for (int j = 0; j < 8; ++j)
+                    if (c0 + j < P.root_card) {
+                        float x = lv[j] * w[j];
+                        if (fan_root) x *= s_fan[P.root_fan_off + c0 + j];
+                        res = fmaf(x, __ldg(P.root_T + c0 + j), res);
                     }
             }
             if (q < P.nq) P.out[q] = res;
@@ -742,10 +691,8 @@ int k3_prepare(bc_model* m) {
         // siblings: internal subtrees first, heaviest first (their messages leave tensor memory early); then the LEAVES in
         // ascending domain size -- the epilogue of an edge costs card(pa) columns whatever card(v) is, so small leaves at the
         // end would queue their epilogues up right where the parent's own edge is waiting for them
-        const bool old_order = std::getenv("BC_K3_OLD_ORDER") != nullptr;   // experiments: heaviest subtree first, leaves included
         for (int v = 0; v < n; ++v)
             std::stable_sort(kids[v].begin(), kids[v].end(), [&](int a, int b) {
-                if (old_order) return weight[a] > weight[b];
                 const bool ia = !kids[a].empty(), ib = !kids[b].empty();
                 if (ia != ib) return ia;
                 return ia ? weight[a] > weight[b] : m->nodes[a].card < m->nodes[b].card;
@@ -761,17 +708,7 @@ int k3_prepare(bc_model* m) {
             }
         }
     }
-    // ---- SIMT tail: a root with ONE internal child v and a small T_v (every shipped DMV / IMDB model) -- the edge v -> root is
-    //      the last of the schedule and is folded into the result by the epilogue warps instead of a tensor-core pass
-    int tail_v = -1;
-    if (kids[0].size() == 1 && !kids[kids[0][0]].empty() && m->nodes[0].card <= 8 &&
-        (long long)m->nodes[kids[0][0]].card * m->nodes[0].card <= 1024 && !std::getenv("BC_K3_NO_TAIL")) {
-        tail_v = kids[0][0];
-        sched.pop_back();   // post order: the root's only child is the last edge
-    }
-    k->tail_v = tail_v;
     const int n_edges = (int)sched.size();
-    if (n_edges < 1) return fail("nothing left for the tensor cores");
     std::vector<int> first_child_edge(n, -1), own_edge(n, -1);
     for (int e = 0; e < n_edges; ++e) {
         const int v = sched[e];
@@ -796,11 +733,11 @@ int k3_prepare(bc_model* m) {
     for (int v = 0; v < n; ++v)
         if (first_child_edge[v] >= 0) order.push_back(v);
     std::sort(order.begin(), order.end(), [&](int a, int b) { return first_child_edge[a] < first_child_edge[b]; });
-    // The node the FINISHER warps read (the root, or the tail node) is read after the tile's last epilogue, while the other
+    // The ROOT's message is read by the finisher warps after the tile's last epilogue, while the other
     // roles are already in the next tile: with `excl` its columns are reserved for the whole tile (nobody shares them);
     // otherwise the epilogue of the first edge of a tile that writes into an overlapping range waits for the finisher
     // (K3Edge::fin_guard) -- correct, but that wait sits at the start of the next tile.
-    const int fin_node = tail_v >= 0 ? tail_v : 0;
+    const int fin_node = 0;
     auto assign = [&](int a_stages, int n_dbuf, bool excl = true) -> int {   // columns used, or -1 (col[] is only written when every node found a place)
         std::vector<int> place(n, -1);
         const int units_total = 512 / 8;
@@ -812,7 +749,7 @@ int k3_prepare(bc_model* m) {
         for (int v : order) {
             const int need = (int)bc_round_up(m->nodes[v].card, 8) / 8;
             const int start = (excl && v == fin_node) ? 0 : first_child_edge[v];
-            const int end = own_edge[v] < 0 ? (1 << 30) : own_edge[v];   // (root / tail node: to the end)
+            const int end = own_edge[v] < 0 ? (1 << 30) : own_edge[v];   // (the root: to the end)
             int at = -1;
             for (int u0 = 0; u0 + need <= units_total && at < 0; ++u0) {
                 bool ok = true;
@@ -850,7 +787,7 @@ int k3_prepare(bc_model* m) {
     k->a_stages = a_stages;
     k->d_col = a_stages * 32;
     k->n_dbuf = n_dbuf;
-    k->root_col = tail_v >= 0 ? -1 : col[0];
+    k->root_col = col[0];
     // ---- operand images: per edge and block of 16 child states, T_v^T hi then lo, 64-byte swizzled rows
     size_t total = 0;
     k->edges.resize(n_edges);
@@ -873,7 +810,7 @@ int k3_prepare(bc_model* m) {
         E.first = first_child_edge[nd.parent] == e;
         E.nkb = (nd.card + kBK - 1) / kBK;
         E.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(E.n_pad >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
-        E.publish = last_child_edge[nd.parent] != e ? -1 : (nd.parent == 0 ? -2 : (nd.parent == tail_v ? -3 : own_edge[nd.parent]));
+        E.publish = last_child_edge[nd.parent] != e ? -1 : (nd.parent == 0 ? -2 : own_edge[nd.parent]);
         E.bimg_off = total;
         total += (size_t)E.nkb * E.n_pad * 128;
     }
@@ -994,19 +931,6 @@ int bc_k3_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32
     P.root_bit_off = m->bits[0].bit_off;
     P.root_lam_off = r.lam_off;
     P.root_fan_off = r.fan_off;
-    if (k->tail_v >= 0) {
-        const BcNodeRec& t = m->nodes[k->tail_v];
-        P.tail_K = t.card;
-        P.tail_v = k->tail_v;
-        P.tail_col_v = k->edges.empty() ? 0 : -1;
-        for (const K3Edge& E : k->edges)
-            if (m->nodes[E.v].parent == k->tail_v) P.tail_col_v = E.col_pa;
-        P.tail_bit_off = m->bits[k->tail_v].bit_off;
-        P.tail_lam_off = t.lam_off;
-        P.tail_fan_off = t.fan_off;
-        P.tail_stride = t.stride;
-        P.tail_T = m->d_arena + t.cpt_off;
-    }
     P.out = out;
     P.nq = nq;
     P.n_tiles = (long long)((nq + kTile - 1) / kTile);

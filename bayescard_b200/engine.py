@@ -137,6 +137,25 @@ class DeviceModel:
                                             mask.ctypes.data if mask is not None else None, out.ctypes.data, kernel))
         return out
 
+    def run_host_scaled(self, desc: np.ndarray, fmt: int, mask: Optional[np.ndarray] = None,
+                        kernel: int = L.KERNEL_AUTO) -> np.ndarray:
+        """Host buffers in, **fp64** probabilities out, for results beyond the fp32 range (below ~1e-38): the kernels carry
+        one power-of-two exponent per query (``bc_query_batch_scaled_host``); the reference computes in fp64
+        (``Pgmpy/inference/ExactInference.py:157-177``)."""
+        stride = self.desc_stride(fmt)
+        desc = np.ascontiguousarray(desc)
+        n = desc.nbytes // stride
+        if desc.nbytes != n * stride:
+            raise ValueError(f"descriptor buffer of {desc.nbytes} B is not a multiple of the row stride {stride}")
+        if mask is not None:
+            mask = np.ascontiguousarray(mask, dtype=np.uint32)
+            if mask.size != n * self.mask_words:
+                raise ValueError("fan-out mask has the wrong size")
+        out = np.empty(n, dtype=np.float64)
+        L.check(L.lib().bc_query_batch_scaled_host(self._h, desc.ctypes.data, n, fmt,
+                                                   mask.ctypes.data if mask is not None else None, out.ctypes.data, kernel))
+        return out
+
     def bits_default(self) -> np.ndarray:
         row = np.zeros(self.desc_stride(L.DESC_BITS) // 4, dtype=np.uint32)
         L.check(L.lib().bc_model_bits_default(self._h, row.ctypes.data, row.nbytes))
@@ -185,6 +204,47 @@ class DeviceModel:
         L.check(L.lib().bc_query_batch_sparse_host(self._h, row_off.ctypes.data, entries.ctypes.data if entries.size else None,
                                                    n, mask.ctypes.data if mask is not None else None, out.ctypes.data,
                                                    kernel))
+        return out
+
+    # ------------------------------------------------------------------ PACKED wire format (17 B per Census query over PCIe)
+    def packed_geometry(self):
+        """``(entry_bits, col_bits, state_bits)`` of the PACKED wire format for this model."""
+        w, cb, sb = C.c_int(), C.c_int(), C.c_int()
+        L.check(L.lib().bc_model_packed_geometry(self._h, C.byref(w), C.byref(cb), C.byref(sb)))
+        return w.value, cb.value, sb.value
+
+    def pack_sparse(self, row_off: np.ndarray, entries: np.ndarray):
+        """SPARSE (CSR) -> PACKED on the host: ``(klen uint8[n], blk_off uint32[ceil(n/128)+1], payload uint8[...])``."""
+        row_off = np.ascontiguousarray(row_off, dtype=np.uint32)
+        entries = np.ascontiguousarray(entries, dtype=np.uint32)
+        n = row_off.size - 1
+        klen = np.zeros(max(n, 1), dtype=np.uint8)[:n]
+        blk = np.zeros((n + 127) // 128 + 1, dtype=np.uint32)
+        w, _, _ = self.packed_geometry()
+        ne = int(row_off[-1]) - int(row_off[0]) if n else 0
+        payload = np.zeros(((ne * w + 31) // 32 + 2) * 4, dtype=np.uint8)
+        used = C.c_size_t()
+        L.check(L.lib().bc_pack_sparse(self._h, row_off.ctypes.data, entries.ctypes.data if entries.size else None, n,
+                                       klen.ctypes.data if n else None, blk.ctypes.data, payload.ctypes.data, payload.nbytes, C.byref(used)))
+        return klen, blk, payload[: used.value]
+
+    def run_packed_host(self, klen: np.ndarray, blk_off: np.ndarray, payload: np.ndarray, mask: Optional[np.ndarray] = None,
+                        kernel: int = L.KERNEL_AUTO, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """PACKED queries from host buffers: H2D, expand to BITS, infer, D2H -- sub-chunked and pipelined in the library."""
+        klen = np.ascontiguousarray(klen, dtype=np.uint8)
+        blk_off = np.ascontiguousarray(blk_off, dtype=np.uint32)
+        payload = np.ascontiguousarray(payload, dtype=np.uint8)
+        n = klen.size
+        if blk_off.size != (n + 127) // 128 + 1:
+            raise ValueError("blk_off does not match klen")
+        if mask is not None:
+            mask = np.ascontiguousarray(mask, dtype=np.uint32)
+            if mask.size != n * self.mask_words:
+                raise ValueError("fan-out mask has the wrong size")
+        if out is None:
+            out = np.empty(n, dtype=np.float32)
+        L.check(L.lib().bc_query_batch_packed_host(self._h, klen.ctypes.data if n else None, blk_off.ctypes.data, payload.ctypes.data,
+                                                   payload.nbytes, n, mask.ctypes.data if mask is not None else None, out.ctypes.data, kernel))
         return out
 
     def gen_sparse_queries_host(self, seed: int, first: int, n: int, kmin: int, kmax: int):

@@ -183,6 +183,45 @@ BC_API int bc_expand_wsparse(bc_model* m, const uint32_t* row_off_dev, const uin
 BC_API int bc_query_batch_wsparse_host(bc_model* m, const uint32_t* row_off, const uint32_t* words, size_t n_queries,
                                 const uint32_t* fan_mask, float* out_prob, int kernel);
 
+/* ---- PACKED: the densest wire form of unit-weight range / IN-list queries (what SPARSE carries), for PCIe ------------
+ * The reference's query is a sparse dict {column: bins} (Evaluation/cardinality_estimation.py:60-111); over PCIe every
+ * byte of it counts (the end-to-end rate of bc_query_batch_*_host is the copy rate divided by bytes per query):
+ *     klen[n]                        uint8   entries of each query (<= 255)
+ *     blk_off[ceil(n / 128) + 1]     uint32  index of the first entry of every block of 128 queries
+ *     payload                        bit stream, entry e at bits [e*w, (e+1)*w), little endian in 32-bit words, rounded
+ *                                    up to whole words + 2 words of padding; w = cb + 2*sb, cb = bits(n_nodes - 1), sb = bits(max_card - 1)
+ *                                    (bc_model_packed_geometry); entry = col | lo << cb | hi << (cb + sb)
+ * Entries of a query are grouped by column; an entry with its predecessor's column ORs into that column's mask (IN lists).
+ * Census: 17 bits per entry, ~17 B per query (SPARSE: ~35 B).  Expanded to BITS rows on the device. */
+BC_API int bc_model_packed_geometry(const bc_model* m, int* entry_bits, int* col_bits, int* state_bits);
+/* HOST: SPARSE (CSR) -> PACKED.  klen[n], blk_off[ceil(n/128)+1], payload[payload_capacity]; *payload_bytes = bytes used
+ * (also set when the capacity is too small: call once with capacity 0 to size the buffer). */
+BC_API int bc_pack_sparse(const bc_model* m, const uint32_t* row_off, const uint32_t* entries, size_t n_queries, uint8_t* klen,
+                          uint32_t* blk_off, void* payload, size_t payload_capacity, size_t* payload_bytes);
+/* DEVICE buffers, stream ordered: PACKED -> BITS rows. */
+BC_API int bc_expand_packed(bc_model* m, const uint8_t* klen_dev, const uint32_t* blk_off_dev, const void* payload_dev, size_t n_queries,
+                            void* dst_bits_dev, void* stream);
+/* HOST buffers (pinned for full speed) in, fp32 probabilities out: chunks of 1 M queries flow through three slots on
+ * three streams (H2D | expansion + inference | D2H overlap across chunks of a larger batch). */
+BC_API int bc_query_batch_packed_host(bc_model* m, const uint8_t* klen, const uint32_t* blk_off, const void* payload, size_t payload_bytes,
+                                      size_t n_queries, const uint32_t* fanout_mask, float* out_prob, int kernel);
+
+/* ---- results beyond the fp32 range --------------------------------------------------------------------------------
+ * The reference computes every product in fp64 (Pgmpy/inference/ExactInference.py:157-177, np.dot / np.prod on fp64
+ * factors): ten narrow predicates on 1 000 - 10 000-bin domains give probabilities below 1e-38, which an fp32 result
+ * flushes to zero.  The *_scaled entry points carry one power-of-two exponent per query: the kernels renormalise a
+ * message row (exactly, by a power of two) every time an edge has been multiplied in, and return
+ *     probability[q] = out_mantissa[q] * 2^out_exponent[q]          (combine in fp64: ldexp(mantissa, exponent)).
+ * Served by the generic kernel (K1: every descriptor format, fan-out masks) and the batched large-domain path
+ * (K2: RANGE_* rows); BC_KERNEL_AUTO picks between them the way bc_query_batch does for a model without an image.
+ * DEVICE pointers, stream ordered. */
+BC_API int bc_query_batch_scaled(bc_model* m, const void* desc, size_t n_queries, int desc_format,
+                                 const uint32_t* fanout_mask, float* out_mantissa, int32_t* out_exponent, int kernel,
+                                 void* stream);
+/* HOST buffers in, fp64 probabilities out (the library combines mantissa and exponent). */
+BC_API int bc_query_batch_scaled_host(bc_model* m, const void* desc, size_t n_queries, int desc_format,
+                                      const uint32_t* fanout_mask, double* out_prob, int kernel);
+
 /* Synthetic workload generator (BASELINE.json configs 2 and 5): writes
  * RANGE_U8 descriptors for query indices [first, first+n) from a counter-based RNG keyed by
  * (seed, query index), so any query can be regenerated on the host for oracle spot checks

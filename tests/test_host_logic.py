@@ -423,10 +423,7 @@ def test_fused_kernel_plan_invariants(name):
     info, edges, why = _fused_plan(dm)
     assert info is not None, why
     n_edges, tmem_cols, ctas, smem, d_col, d_cols, root_col, _ = (int(x) for x in info)
-    # a root with one internal child and a small T_v: that last edge is folded into the result in registers (SIMT tail)
-    root_kids = [v for v in range(1, m.n_nodes) if int(m.parent[v]) == 0]
-    tail = root_kids[0] if len(root_kids) == 1 and any(int(m.parent[v]) == root_kids[0] for v in range(m.n_nodes)) and int(m.card[0]) <= 8 else None
-    assert (root_col < 0) == (tail is not None)
+    tail = None
     assert n_edges == m.n_nodes - 1 - (tail is not None) and tmem_cols == 512 and ctas == 1 and smem <= 227 * 1024
     assert d_col in (64, 96, 128) and d_col % 32 == 0    # the A ring (2-4 stages of 16 hi + 16 lo columns) sits below the accumulators
     child = edges[:, 0]
@@ -508,3 +505,52 @@ def test_staged_reference_reproduces_the_golden_probabilities():
         p = bn.query(q, n_distinct=nd, return_prob=True)[0]
         want = np.asarray(r["card"]["value"]).reshape(-1)[0] / bn.nrows
         assert abs(float(np.asarray(p).reshape(-1)[0]) - want) <= 1e-12 * max(abs(want), 1e-300)
+
+
+@pytest.mark.parametrize("name", ["census", "dmv", "imdb3"])
+def test_packed_wire_format_round_trip(name):
+    """PACKED (include/bayescard_b200.h): the host packer against a plain bit-stream decoder -- same columns, bounds and
+    IN-list continuation as the SPARSE entries it was made from; geometry; refusals."""
+    m = G.model(name)
+    dm = DeviceModel(m, device=-1, specialize=False)
+    w, cb, sb = dm.packed_geometry()
+    assert w == cb + 2 * sb and (1 << cb) >= m.n_nodes and (1 << sb) >= int(m.card.max()) and (1 << (cb - 1)) < max(m.n_nodes, 2)
+    n = 1000
+    row_off, entries = dm.gen_sparse_queries_host(5, 17, n, 0, min(14, m.n_nodes))
+    # IN lists: duplicate some entries as continuation entries (same column, cont bit) right behind their first
+    rng = np.random.default_rng(1)
+    ro2, en2 = [0], []
+    for q in range(n):
+        for e in entries[row_off[q]:row_off[q + 1]]:
+            en2.append(int(e))
+            if rng.random() < 0.2:
+                col, lo, hi = int(e) & 0x7FFF, (int(e) >> 16) & 0xFF, int(e) >> 24
+                en2.append(col | (1 << 15) | (min(hi, lo + 1) << 16) | (hi << 24))
+        ro2.append(len(en2))
+    row_off, entries = np.asarray(ro2, dtype=np.uint32), np.asarray(en2, dtype=np.uint32)
+    klen, blk, payload = dm.pack_sparse(row_off, entries)
+    assert klen.dtype == np.uint8 and klen.size == n and blk.size == (n + 127) // 128 + 1
+    assert np.array_equal(klen, np.diff(row_off.astype(np.int64))) and int(blk[-1]) == entries.size
+    assert payload.nbytes == ((entries.size * w + 31) // 32 + 2) * 4
+    words = np.frombuffer(payload.tobytes(), dtype=np.uint32)
+    e = 0
+    for q in range(n):
+        if q % 128 == 0:
+            assert int(blk[q // 128]) == e
+        prev = -1
+        for x in entries[row_off[q]:row_off[q + 1]]:
+            bit = e * w
+            v = ((int(words[bit >> 5]) | (int(words[(bit >> 5) + 1]) << 32)) >> (bit & 31)) & ((1 << w) - 1)
+            col, lo, hi = v & ((1 << cb) - 1), (v >> cb) & ((1 << sb) - 1), v >> (cb + sb)
+            assert (col, lo, hi) == (int(x) & 0x7FFF, (int(x) >> 16) & 0xFF, int(x) >> 24)
+            assert ((int(x) >> 15) & 1) == (col == prev)
+            prev = col
+            e += 1
+    # an ungrouped continuation entry is not representable
+    bad = np.asarray([3 | (1 << 15) | (1 << 24)], dtype=np.uint32)
+    with pytest.raises(L.BayesCardError):
+        dm.pack_sparse(np.asarray([0, 1], dtype=np.uint32), bad)
+    # empty batch
+    k0, b0, p0 = dm.pack_sparse(np.zeros(1, dtype=np.uint32), np.zeros(0, dtype=np.uint32))
+    assert k0.size == 0 and b0.tolist() == [0] and p0.nbytes == 8
+    dm.close()
