@@ -290,39 +290,38 @@ def launch_count() -> int:
 
 
 class ShardedModel:
-    """The model replicated on several GPUs of one process; batches are split contiguously."""
+    """The model replicated on several GPUs of ONE process; a batch is split into contiguous ranges, one host thread +
+    stream set per device, the results land in one host array (BASELINE.json north_star item 4).
+    No collective: the path has no exchange step.  Every ``run_*_host`` of :class:`DeviceModel` has a sharded twin here;
+    the C calls release the GIL (ctypes), so the devices really run concurrently."""
 
     def __init__(self, tm: TreeModel, devices: Sequence[int], specialize: bool = True):
         self.tm = tm
         self.replicas: List[DeviceModel] = [DeviceModel(tm, d, specialize=specialize) for d in devices]
+        self.mask_words = self.replicas[0].mask_words
 
     @staticmethod
-    def split(n: int, parts: int):
-        """Equal contiguous ranges, remainder to the last."""
-        base = n // parts
+    def split(n: int, parts: int, align: int = 1):
+        """Equal contiguous ranges, remainder to the last; boundaries on multiples of ``align``."""
+        base = n // parts // align * align
         bounds = [i * base for i in range(parts)] + [n]
         return [(bounds[i], bounds[i + 1]) for i in range(parts)]
 
-    def run_host(self, desc: np.ndarray, fmt: int, mask: Optional[np.ndarray] = None,
-                 kernel: int = L.KERNEL_AUTO) -> np.ndarray:
-        r0 = self.replicas[0]
-        stride = r0.desc_stride(fmt)
-        desc = np.ascontiguousarray(desc).reshape(-1)
-        n = desc.nbytes // stride
-        rows = desc.view(np.uint8).reshape(n, stride)
-        out = np.empty(n, dtype=np.float32)
+    def _fan_out(self, n: int, work, align: int = 1, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Run ``work(replica, a, b, out[a:b])`` for every replica's slice on its own thread."""
+        if out is None:
+            out = np.empty(n, dtype=np.float32)
         errs: List[BaseException] = []
 
-        def work(rep: DeviceModel, a: int, b: int):
+        def body(rep: DeviceModel, a: int, b: int):
             try:
                 if b > a:
-                    rep.run_host(rows[a:b], fmt, None if mask is None else mask.reshape(n, -1)[a:b], kernel,
-                                 out=out[a:b])
+                    work(rep, a, b, out[a:b])
             except BaseException as e:  # noqa: BLE001
                 errs.append(e)
 
-        threads = [threading.Thread(target=work, args=(rep, a, b))
-                   for rep, (a, b) in zip(self.replicas, self.split(n, len(self.replicas)))]
+        threads = [threading.Thread(target=body, args=(rep, a, b))
+                   for rep, (a, b) in zip(self.replicas, self.split(n, len(self.replicas), align))]
         for t in threads:
             t.start()
         for t in threads:
@@ -330,6 +329,55 @@ class ShardedModel:
         if errs:
             raise errs[0]
         return out
+
+    def _mask(self, mask, n):
+        if mask is None:
+            return None
+        mask = np.ascontiguousarray(mask, dtype=np.uint32).reshape(n, self.mask_words)
+        return mask
+
+    def run_host(self, desc: np.ndarray, fmt: int, mask: Optional[np.ndarray] = None,
+                 kernel: int = L.KERNEL_AUTO) -> np.ndarray:
+        stride = self.replicas[0].desc_stride(fmt)
+        desc = np.ascontiguousarray(desc).reshape(-1)
+        n = desc.nbytes // stride
+        rows = desc.view(np.uint8).reshape(n, stride)
+        mask = self._mask(mask, n)
+        return self._fan_out(n, lambda rep, a, b, o: rep.run_host(rows[a:b], fmt, None if mask is None else mask[a:b], kernel, out=o))
+
+    def run_sparse_host(self, row_off: np.ndarray, entries: np.ndarray, mask: Optional[np.ndarray] = None,
+                        kernel: int = L.KERNEL_AUTO) -> np.ndarray:
+        """SPARSE (CSR) batch: each replica gets a contiguous CSR slice (the library takes absolute entry indices: the
+        slice is ``row_off[a:b+1]`` as it stands plus the whole ``entries`` array, nothing is copied on the host)."""
+        row_off = np.ascontiguousarray(row_off, dtype=np.uint32)
+        entries = np.ascontiguousarray(entries, dtype=np.uint32)
+        n = row_off.size - 1
+        mask = self._mask(mask, n)
+        return self._fan_out(n, lambda rep, a, b, o: rep.run_sparse_host(row_off[a:b + 1], entries, None if mask is None else mask[a:b],
+                                                                      kernel, out=o))
+
+    def run_wsparse_host(self, row_off: np.ndarray, words: np.ndarray, mask: Optional[np.ndarray] = None,
+                         kernel: int = L.KERNEL_AUTO) -> np.ndarray:
+        row_off = np.ascontiguousarray(row_off, dtype=np.uint32)
+        words = np.ascontiguousarray(words, dtype=np.uint32)
+        n = row_off.size - 1
+        mask = self._mask(mask, n)
+        return self._fan_out(n, lambda rep, a, b, o: rep.run_wsparse_host(row_off[a:b + 1], words, None if mask is None else mask[a:b],
+                                                                       kernel, out=o))
+
+    def run_packed_host(self, klen: np.ndarray, blk_off: np.ndarray, payload: np.ndarray, mask: Optional[np.ndarray] = None,
+                        kernel: int = L.KERNEL_AUTO, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """PACKED batch: slices on multiples of the 128-query block, ``blk_off`` keeps absolute entry indices."""
+        klen = np.ascontiguousarray(klen, dtype=np.uint8)
+        blk_off = np.ascontiguousarray(blk_off, dtype=np.uint32)
+        payload = np.ascontiguousarray(payload, dtype=np.uint8)
+        n = klen.size
+        mask = self._mask(mask, n)
+
+        def work(rep, a, b, o):
+            rep.run_packed_host(klen[a:b], blk_off[a // 128:(b + 127) // 128 + 1], payload, None if mask is None else mask[a:b], kernel, out=o)
+
+        return self._fan_out(n, work, align=128, out=out)
 
     def close(self):
         for r in self.replicas:

@@ -47,11 +47,8 @@ class VariableEliminationB200:
         if len(d_idx):
             # fractional weights cross PCIe as weighted runs (WSPARSE, ~20x smaller) and become DENSE rows on the device
             dmask = None if mask is None else mask[d_idx]
-            if isinstance(self.dev, DeviceModel):
-                row_off, words = dense_to_wsparse(self.tm, d_desc)
-                out[d_idx] = self.dev.run_wsparse_host(row_off, words, dmask, self.kernel)
-            else:  # sharded over several GPUs: contiguous slices of DENSE rows
-                out[d_idx] = self.dev.run_host(d_desc, L.DESC_DENSE_F32, dmask, self.kernel)
+            row_off, words = dense_to_wsparse(self.tm, d_desc)   # (one device or several: ShardedModel slices the CSR)
+            out[d_idx] = self.dev.run_wsparse_host(row_off, words, dmask, self.kernel)
         return out
 
     def query_batch(self, queries: Sequence[Dict[str, Sequence[int]]],

@@ -487,6 +487,36 @@ def h2d_peak_leg(nbytes, device, barrier, max_over_ranks, reps=5):
     return nbytes * reps / dt / 1e9
 
 
+def inproc_leg(ngpu, B, kernel, reps=5):
+    """north_star item 4 as written: ONE process, one host thread + stream set per device (engine.ShardedModel), the PACKED
+    batch of ngpu x B queries in one pinned host array, results gathered in one pinned host array.  Same metric and workload
+    as `e2e`, beside the one-process-per-GPU (torchrun) number."""
+    import torch
+
+    from bayescard_b200.engine import ShardedModel
+
+    tm = load_tree("census")
+    sm = ShardedModel(tm, list(range(ngpu)), specialize=True)
+    n = ngpu * B
+    row_off, entries = sm.replicas[0].gen_sparse_queries_host(SEED, 0, n, KMIN, KMAX)
+    klen, blk, pay = sm.replicas[0].pack_sparse(row_off, entries)
+    pin = lambda a: torch.from_numpy(a).pin_memory()
+    hk, hb, hp = pin(klen), pin(blk.view(np.int32)), pin(pay)
+    ho = torch.empty(n, dtype=torch.float32).pin_memory()
+    k_np, b_np, p_np, o_np = hk.numpy(), hb.numpy().view(np.uint32), hp.numpy(), ho.numpy()
+    for _ in range(2):
+        sm.run_packed_host(k_np, b_np, p_np, None, kernel, out=o_np)
+    t = time.perf_counter()
+    for _ in range(reps):
+        sm.run_packed_host(k_np, b_np, p_np, None, kernel, out=o_np)
+    dt = time.perf_counter() - t
+    first = o_np[:B].copy()
+    sm.close()
+    return {"value": n * reps / dt, "unit": UNIT, "n_gpus": ngpu, "queries_per_call": n,
+            "api": "engine.ShardedModel.run_packed_host: one process, one host thread + stream set per device, no collective",
+            "h2d_bytes_per_call": int(k_np.nbytes + b_np.nbytes + p_np.nbytes)}, first
+
+
 def run_ours(args):
     import torch
 
@@ -636,9 +666,18 @@ def run_ours(args):
 
     if rank != 0:
         if dist is not None:
+            dist.barrier()   # (rank 0 runs the in-process multi-GPU leg on all N devices meanwhile)
             dist.barrier()
             dist.destroy_process_group()
         return
+    inproc = None
+    n_inproc = world if world > 1 else (torch.cuda.device_count() if args.inproc else 0)
+    if n_inproc > 1:
+        inproc, inproc_first = inproc_leg(n_inproc, B, kernel)
+        if not np.array_equal(inproc_first, e2e_first) and world == 1:
+            raise SystemExit("in-process multi-GPU results differ from the single-GPU results")
+    if dist is not None:
+        dist.barrier()
 
     # ---- parity of this very batch against the fp64 oracle (sub-sample) ------------------------
     rng = np.random.default_rng(0)
@@ -722,6 +761,8 @@ def run_ours(args):
             "cpu_baseline": cpu, "cpu_baseline_port": cpu_port,
             "rel_err_max_vs_fp64_oracle": rel_err, "p50_latency_us_scalar_query": p50_us,
             "fp32_peak_tflops_measured": fp32_peak}
+    if inproc is not None:
+        line["e2e_inproc"] = inproc
     if sustained is not None:
         line["sustained"] = sustained
     if dmv_leg is not None:

@@ -596,6 +596,60 @@ def test_results_below_the_fp32_range(shape):
     dm.close()
 
 
+def test_in_process_multi_gpu_sharding():
+    """north_star item 4: one host thread + stream set per device inside ONE process, results gathered in one host array.
+    Needs two GPUs (skipped on a one-GPU box, where `test_sharded_model_same_device` still exercises the threading with
+    two replicas on device 0): every wire format through ShardedModel equals the single-device result bit for bit, and the
+    drop-in API routes through it."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    devs = list(range(min(torch.cuda.device_count(), 8)))
+    for name in ("census", "imdb1"):
+        m, dm = G.model(name), dev_model(name)
+        sm = ShardedModel(m, devs, specialize=True)
+        n = 128 * 53 + 77
+        row_off, entries = dm.gen_sparse_queries_host(4, 11, n, 0, min(14, m.n_nodes))
+        want = dm.run_sparse_host(row_off, entries)
+        assert np.array_equal(sm.run_sparse_host(row_off, entries), want)
+        klen, blk, payload = dm.pack_sparse(row_off, entries)
+        assert np.array_equal(sm.run_packed_host(klen, blk, payload), want)
+        desc = dm.gen_range_queries_host(4, 11, n, 0, min(14, m.n_nodes))
+        assert np.array_equal(sm.run_host(desc, L.DESC_RANGE_U8), dm.run_host(desc, L.DESC_RANGE_U8))
+        if name == "imdb1":
+            pc = PredicateCompiler(m)
+            cases = [r for r in G.load("infer_cases.json.gz")[name] if "error" not in r]
+            decoded = [({k: list(v) for k, v in r["bins"].items()}, {k: np.asarray(v) for k, v in r["weights"].items()}) for r in cases]
+            _, _, _, dense, mask = pc.pack(decoded, [r["fanout"] for r in cases], force_dense=True)
+            ro, words = dense_to_wsparse(m, dense)
+            assert np.array_equal(sm.run_wsparse_host(ro, words, mask), dm.run_wsparse_host(ro, words, mask))
+        sm.close()
+    bn = Bayescard_BN(G.model("dmv"), device=devs, infer_algo="exact-jit")
+    bn.init_inference_method()
+    one = Bayescard_BN(G.model("dmv"), device=0, infer_algo="exact-jit")
+    one.init_inference_method()
+    rows = G.load("dmv_workload.json.gz")["queries"][:400]
+    qs = [parse_query_single_table(r["sql"], bn) for r in rows]
+    assert np.array_equal(bn.query_batch(copy.deepcopy(qs)), one.query_batch(copy.deepcopy(qs)))
+    bn.close()
+    one.close()
+
+
+def test_sharded_model_same_device():
+    """ShardedModel's slicing of every wire format with two replicas on device 0 (runs on a one-GPU box)."""
+    m, dm = G.model("census"), dev_model("census")
+    sm = ShardedModel(m, [0, 0], specialize=True)
+    n = 128 * 9 + 5
+    row_off, entries = dm.gen_sparse_queries_host(6, 0, n, 0, 14)
+    want = dm.run_sparse_host(row_off, entries)
+    assert np.array_equal(sm.run_sparse_host(row_off, entries), want)
+    klen, blk, payload = dm.pack_sparse(row_off, entries)
+    assert np.array_equal(sm.run_packed_host(klen, blk, payload), want)
+    assert sm.run_sparse_host(np.zeros(1, dtype=np.uint32), np.zeros(0, dtype=np.uint32)).size == 0
+    sm.close()
+
+
 def test_sharded_ranks_on_gpu():
     """The per-rank slice evaluator of bayescard_b200.sharding on the real device (single rank = whole batch;
     the two-rank split itself is covered on CPU by tests/test_sharding_gloo.py)."""
