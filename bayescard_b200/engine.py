@@ -299,6 +299,10 @@ class ShardedModel:
         self.tm = tm
         self.replicas: List[DeviceModel] = [DeviceModel(tm, d, specialize=specialize) for d in devices]
         self.mask_words = self.replicas[0].mask_words
+        # one long-lived host thread per device (creating threads per call costs ~0.1 ms, a fifth of a 1 M-query call)
+        from concurrent.futures import ThreadPoolExecutor
+
+        self._pool = ThreadPoolExecutor(max_workers=len(self.replicas), thread_name_prefix="bc-shard")
 
     @staticmethod
     def split(n: int, parts: int, align: int = 1):
@@ -311,23 +315,12 @@ class ShardedModel:
         """Run ``work(replica, a, b, out[a:b])`` for every replica's slice on its own thread."""
         if out is None:
             out = np.empty(n, dtype=np.float32)
-        errs: List[BaseException] = []
-
-        def body(rep: DeviceModel, a: int, b: int):
-            try:
-                if b > a:
-                    work(rep, a, b, out[a:b])
-            except BaseException as e:  # noqa: BLE001
-                errs.append(e)
-
-        threads = [threading.Thread(target=body, args=(rep, a, b))
-                   for rep, (a, b) in zip(self.replicas, self.split(n, len(self.replicas), align))]
-        for t in threads:
-            t.start()
-        for t in threads:
-            t.join()
-        if errs:
-            raise errs[0]
+        futs = [self._pool.submit(work, rep, a, b, out[a:b])
+                for rep, (a, b) in zip(self.replicas, self.split(n, len(self.replicas), align)) if b > a]
+        errs = [f.exception() for f in futs]   # waits for every slice (no replica may still write into `out` on return)
+        for e in errs:
+            if e is not None:
+                raise e
         return out
 
     def _mask(self, mask, n):
@@ -380,5 +373,6 @@ class ShardedModel:
         return self._fan_out(n, work, align=128, out=out)
 
     def close(self):
+        self._pool.shutdown(wait=True)
         for r in self.replicas:
             r.close()

@@ -538,6 +538,8 @@ def run_ours(args):
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # a CPU-side group for the one wait that must not occupy the GPUs (the in-process multi-GPU leg of rank 0)
+        gloo_group = dist.new_group(backend="gloo")
     dev = f"cuda:{local}"
     kernel = {"auto": L.KERNEL_AUTO, "generic": L.KERNEL_GENERIC, "spec": L.KERNEL_SPEC}[args.kernel]
 
@@ -666,7 +668,7 @@ def run_ours(args):
 
     if rank != 0:
         if dist is not None:
-            dist.barrier()   # (rank 0 runs the in-process multi-GPU leg on all N devices meanwhile)
+            dist.barrier(group=gloo_group)   # rank 0 runs the in-process multi-GPU leg on all N devices meanwhile: wait on the CPU
             dist.barrier()
             dist.destroy_process_group()
         return
@@ -677,7 +679,7 @@ def run_ours(args):
         if not np.array_equal(inproc_first, e2e_first) and world == 1:
             raise SystemExit("in-process multi-GPU results differ from the single-GPU results")
     if dist is not None:
-        dist.barrier()
+        dist.barrier(group=gloo_group)
 
     # ---- parity of this very batch against the fp64 oracle (sub-sample) ------------------------
     rng = np.random.default_rng(0)
