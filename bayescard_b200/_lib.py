@@ -16,6 +16,7 @@ SPEC_CACHE_DIR = os.path.join(_HERE, "_spec_cache")
 
 BC_OK = 0
 DESC_RANGE_U8, DESC_RANGE_U16, DESC_DENSE_F32, DESC_BITS = 0, 1, 2, 3
+ELIMIT = -5
 SQLC_BITS, SQLC_DENSE, SQLC_ZERO, SQLC_PYTHON, SQLC_OVERFLOW = 0, 1, 2, 3, 4
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_SPEC, KERNEL_GEMM, KERNEL_GEMM_SIMT, KERNEL_FUSED = 0, 1, 2, 3, 4, 5
 
@@ -87,6 +88,17 @@ _SIGS = {
                                             C.c_int, C.c_void_p]),
     "bc_sqlc_create": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
     "bc_sqlc_destroy": (None, [C.c_void_p]),
+    "bc_sqlc_set_null": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
+    "bc_sqlc_column_index": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "bc_sqlc_compile_factors": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t)]),
+    "bc_joblight_create": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_double, C.POINTER(C.c_void_p)]),
+    "bc_joblight_destroy": (None, [C.c_void_p]),
+    "bc_joblight_plan": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "bc_joblight_combine": (C.c_int, [C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bc_sqlc_bits_stride": (C.c_int64, [C.c_void_p]),
     "bc_sqlc_dense_width": (C.c_int64, [C.c_void_p]),
     "bc_sqlc_add_categorical": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,

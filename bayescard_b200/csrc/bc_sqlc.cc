@@ -62,6 +62,10 @@ struct Column {
     std::unordered_map<std::string_view, int> enc_str;  // string original value -> entry
     std::vector<Val> domain;                         // BN.domain[attr] in its stored order
     bool domain_numeric = false;                     // every domain value is a number (inequalities are defined)
+    std::vector<double> enc_key;                     // the encoding's keys in dict order (meaningful when enc_all_num)
+    bool enc_all_num = true;                         // every key of the encoding is a number: (lo, hi) tuples are defined
+    bool has_null = false;                           // BN.null_values[attr]: skipped by (lo, hi) tuples (Bayescard_BN.py:304-318)
+    double null_num = 0;
     // continuous
     double dom_lo = 0, dom_hi = 0;
     std::vector<double> edge_lo, edge_hi;
@@ -478,6 +482,83 @@ int compile_one(const bc_sqlc& c, sv sql, Scratch& sc) {
     return KIND_BITS;
 }
 
+// One FACTOR of a join query (Models/BN_ensemble_model.py:192-225 hands them to query_decoding as dicts
+// {column: scalar | (lo, hi)}): predicates pred[p0 .. p1) = (column index of this compiler, kind 0 scalar / 1 tuple, a, b),
+// numeric values only, one predicate per column.  Restates Bayescard_BN.query_decoding (Models/Bayescard_BN.py:279-325) for
+// these two value shapes; fills sc.dec like compile_one.  `has_fan`: the factor carries fan-out columns (an expectation),
+// which keeps it alive when no predicated column is reachable.
+int compile_factor(const bc_sqlc& c, const int32_t* pcol, const uint8_t* pkind, const double* pa, const double* pb, uint32_t p0, uint32_t p1,
+                   bool has_fan, Scratch& sc) {
+    sc.n_dec = 0;
+    int in_tree = 0;
+    Decoded tmp;
+    for (uint32_t p = p0; p < p1; ++p) {
+        if (pcol[p] < 0 || pcol[p] >= (int32_t)c.cols.size()) return KIND_PYTHON;   // KeyError in the reference
+        const Column& col = c.cols[pcol[p]];
+        Decoded* dp = &tmp;
+        if (col.node >= 0) {
+            if (sc.n_dec == sc.dec.size()) sc.dec.emplace_back();
+            dp = &sc.dec[sc.n_dec];
+        }
+        Decoded& d = *dp;
+        d.node = col.node;
+        d.bins.clear();
+        d.wts.clear();
+        const double a = pa[p], b = pb[p];
+        if (col.continuous) {
+            double lo, hi, mult = 1.0;
+            bool has_mult = false;
+            if (pkind[p] == 1) {
+                lo = std::max(col.dom_lo, a);
+                hi = std::min(col.dom_hi, b);
+            } else {
+                lo = a - 0.5;
+                hi = a + 0.5;
+                auto f = col.nd_map.find(num_key(a));
+                if (f != col.nd_map.end()) { mult = f->second; has_mult = true; }
+            }
+            if (lo > hi) return KIND_ZERO;
+            if (col.edge_lo.empty()) return KIND_PYTHON;
+            continuous_bins(col, lo, hi, d.bins, d.wts);
+            if (has_mult)
+                for (double& w : d.wts) w *= mult;
+        } else if (pkind[p] == 1) {
+            // categorical (lo, hi): the ORIGINAL values of the encoding inside the range, in dict order, the null marker excluded
+            if (!col.enc_all_num) return KIND_PYTHON;
+            for (size_t e = 0; e < col.enc_key.size(); ++e) {
+                const double k = col.enc_key[e];
+                if (!(k >= a && k <= b)) continue;
+                if (col.has_null && k == col.null_num) continue;
+                const int32_t bin = col.enc_bin[e];
+                const double w = col.enc_w[e];
+                size_t j = 0;
+                for (; j < d.bins.size(); ++j)
+                    if (d.bins[j] == bin) break;
+                if (j == d.bins.size()) { d.bins.push_back(bin); d.wts.push_back(w); }
+                else d.wts[j] = std::min(d.wts[j] + w, 1.0);
+            }
+            if (d.bins.empty()) return KIND_ZERO;
+        } else {
+            if (!col.has_encoding) return KIND_ZERO;
+            auto f = col.enc_num.find(num_key(a));
+            if (f == col.enc_num.end()) return KIND_ZERO;
+            d.bins.push_back(col.enc_bin[f->second]);
+            d.wts.push_back(col.enc_w[f->second]);
+        }
+        if (col.node >= 0) {
+            ++in_tree;
+            for (int32_t bin : d.bins)
+                if (bin < 0 || bin >= col.card) return KIND_PYTHON;
+            ++sc.n_dec;
+        }
+    }
+    if (in_tree == 0 && !has_fan) return KIND_ZERO;  // no queried column is reachable: ExactInference.py:197
+    for (size_t i = 0; i < sc.n_dec; ++i)
+        for (double w : sc.dec[i].wts)
+            if (w != 1.0) return KIND_DENSE;
+    return KIND_BITS;
+}
+
 // clear bits [o, o + len) of a little-endian bit row
 inline void clear_bits(uint8_t* row, int64_t o, int len) {
     int64_t b = o, e = o + len;
@@ -543,6 +624,8 @@ int bc_sqlc_add_categorical(bc_sqlc* c, const char* name, int node, int has_enco
     for (int i = 0; i < n_enc; ++i) {
         col.enc_bin.push_back(enc_bin[i]);
         col.enc_w.push_back(enc_weight[i]);
+        col.enc_key.push_back(enc_is_str[i] ? 0.0 : enc_num[i]);
+        if (enc_is_str[i]) col.enc_all_num = false;
         if (enc_is_str[i]) {
             col.text.emplace_back(enc_str[i]);
             col.enc_str.emplace(std::string_view(col.text.back()), i);
@@ -591,14 +674,15 @@ int bc_sqlc_add_continuous(bc_sqlc* c, const char* name, int node, double dom_lo
     return BC_OK;
 }
 
-int bc_sqlc_compile(const bc_sqlc* c, size_t n_queries, const char* const* sql, uint8_t* kind, void* bits_rows,
-                    float* dense_rows, size_t dense_capacity, uint32_t* dense_index, size_t* n_dense) {
-    if (!c || (n_queries && (!sql || !kind || !bits_rows)) || !n_dense) {
-        bc_set_error("bc_sqlc_compile: bad arguments");
-        return BC_EINVAL;
-    }
-    // Queries are independent: slices of the batch are compiled on host threads.  BITS rows land at their query
-    // index; DENSE rows are collected per thread and appended in query order afterwards.
+}  // extern "C"
+
+namespace {
+// Batch driver shared by the SQL and the factor entry points: `one(q, scratch)` decodes query q into scratch.dec and returns
+// its kind.  Queries are independent: slices of the batch are compiled on host threads.  BITS rows land at their query
+// index; DENSE rows are collected per thread and appended in query order afterwards.
+template <class One>
+int run_batch(const bc_sqlc* c, size_t n_queries, One one, uint8_t* kind, void* bits_rows, float* dense_rows, size_t dense_capacity,
+              uint32_t* dense_index, size_t* n_dense) {
     uint8_t* bits = static_cast<uint8_t*>(bits_rows);
     unsigned n_thr = std::thread::hardware_concurrency();
     if (const char* e = std::getenv("BC_SQLC_THREADS")) n_thr = (unsigned)std::atoi(e);
@@ -617,7 +701,7 @@ int bc_sqlc_compile(const bc_sqlc* c, size_t n_queries, const char* const* sql, 
         Part& pt = part[t];
         const size_t q0 = n_queries * t / n_thr, q1 = n_queries * (t + 1) / n_thr;
         for (size_t q = q0; q < q1; ++q) {
-            const int k = sql[q] ? compile_one(*c, sv(sql[q]), sc) : KIND_PYTHON;
+            const int k = one(q, sc);
             if (k == KIND_BITS) {
                 uint8_t* row = bits + q * (size_t)c->bits_row_bytes;
                 std::memcpy(row, c->bits_default.data(), (size_t)c->bits_row_bytes);
@@ -663,6 +747,50 @@ int bc_sqlc_compile(const bc_sqlc* c, size_t n_queries, const char* const* sql, 
         }
     *n_dense = nd;
     return BC_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int bc_sqlc_compile(const bc_sqlc* c, size_t n_queries, const char* const* sql, uint8_t* kind, void* bits_rows,
+                    float* dense_rows, size_t dense_capacity, uint32_t* dense_index, size_t* n_dense) {
+    if (!c || (n_queries && (!sql || !kind || !bits_rows)) || !n_dense) {
+        bc_set_error("bc_sqlc_compile: bad arguments");
+        return BC_EINVAL;
+    }
+    return run_batch(c, n_queries, [&](size_t q, Scratch& sc) { return sql[q] ? compile_one(*c, sv(sql[q]), sc) : (int)KIND_PYTHON; }, kind,
+                     bits_rows, dense_rows, dense_capacity, dense_index, n_dense);
+}
+
+int bc_sqlc_set_null(bc_sqlc* c, const char* name, double null_value) {
+    if (!c || !name) { bc_set_error("bc_sqlc_set_null: bad arguments"); return BC_EINVAL; }
+    auto it = c->by_name.find(std::string_view(name));
+    if (it == c->by_name.end()) { bc_set_error("bc_sqlc_set_null: unknown column %s", name); return BC_EINVAL; }
+    c->cols[it->second].has_null = true;
+    c->cols[it->second].null_num = null_value;
+    return BC_OK;
+}
+
+int bc_sqlc_column_index(const bc_sqlc* c, const char* name) {
+    if (!c || !name) return -1;
+    auto it = c->by_name.find(std::string_view(name));
+    return it == c->by_name.end() ? -1 : it->second;
+}
+
+int bc_sqlc_compile_factors(const bc_sqlc* c, size_t n_factors, const uint32_t* ids, const uint32_t* pred_off, const int32_t* pred_col,
+                            const uint8_t* pred_kind, const double* pred_a, const double* pred_b, const uint32_t* fan_mask, uint8_t* kind,
+                            void* bits_rows, float* dense_rows, size_t dense_capacity, uint32_t* dense_index, size_t* n_dense) {
+    if (!c || (n_factors && (!pred_off || !kind || !bits_rows)) || !n_dense) {
+        bc_set_error("bc_sqlc_compile_factors: bad arguments");
+        return BC_EINVAL;
+    }
+    return run_batch(c, n_factors,
+                     [&](size_t q, Scratch& sc) {
+                         const size_t f = ids ? ids[q] : q;
+                         return compile_factor(*c, pred_col, pred_kind, pred_a, pred_b, pred_off[f], pred_off[f + 1],
+                                               fan_mask != nullptr && fan_mask[f] != 0, sc);
+                     },
+                     kind, bits_rows, dense_rows, dense_capacity, dense_index, n_dense);
 }
 
 }  // extern "C"

@@ -166,3 +166,141 @@ def plan_star_query(sql: str, join_sizes: Dict[int, float]) -> list:
 
 def plan_workload(sqls: Sequence[str], join_sizes: Dict[int, float]) -> List[list]:
     return [plan_star_query(s, join_sizes) for s in sqls]
+
+
+class NativeJobLight:
+    """The whole job-light path off the Python hot loop: ``cardinality_sql_batch(sqls)`` plans a batch of SQL texts
+    (``bc_joblight_plan``, C++), decodes and packs every factor (``bc_sqlc_compile_factors``, C++, the column tables of each
+    BN), runs one device batch per BN and descriptor kind, and combines (``bc_joblight_combine``).  Queries the native planner
+    declines (not a job-light star) and factors the native decoder declines go through :func:`plan_star_query` and the Python
+    mirror, so the results equal ``BN_ensemble.cardinality(parse_query_all(plan_workload(sqls)))`` either way."""
+
+    def __init__(self, ensemble):
+        import ctypes as C
+
+        import numpy as np
+
+        from . import _lib as L
+        from .sqlc import SqlBatchCompiler
+
+        self.ens = ensemble
+        self.n_bn = len(BN_INDEX)
+        tables = [t for t, _ in sorted(BN_INDEX.items(), key=lambda kv: kv[1])]
+        self.tables = tables
+        self.machines = [ensemble.bns[i]._machine() for i in range(self.n_bn)]
+        self.sqlc = [SqlBatchCompiler(ensemble.bns[i].tree, self.machines[i].compiler) for i in range(self.n_bn)]
+        fan = np.full((self.n_bn, self.n_bn), -1, dtype=np.int32)
+        for a in range(self.n_bn):
+            tm = ensemble.bns[a].tree
+            for b in range(self.n_bn):
+                name = f"title.mul_{tables[b]}.movie_id"
+                if name in tm._index and tm.fan_vector(tm._index[name]) is not None:
+                    fan[a, b] = tm._index[name]
+        joins = np.asarray([float(ensemble.bns[i].nrows) for i in range(self.n_bn)], dtype=np.float64)
+        pairs = list(PAIRWISE_RDC.items())
+        enc = lambda xs: (C.c_char_p * max(1, len(xs)))(*[x.encode() for x in xs])
+        ra, rb = enc([k[0] for k, _ in pairs]), enc([k[1] for k, _ in pairs])
+        rv = np.asarray([v for _, v in pairs], dtype=np.float64)
+        hs = (C.c_void_p * self.n_bn)(*[c._h for c in self.sqlc])
+        tb = enc(tables)
+        h = C.c_void_p()
+        L.check(L.lib().bc_joblight_create(self.n_bn, C.cast(hs, C.c_void_p), C.cast(tb, C.c_void_p), joins.ctypes.data, fan.ctypes.data,
+                                           len(pairs), C.cast(ra, C.c_void_p), C.cast(rb, C.c_void_p), rv.ctypes.data, EPSILON, C.byref(h)))
+        self._h = h
+        self.join_sizes = {i: joins[i] for i in range(self.n_bn)}
+
+    def close(self):
+        from . import _lib as L
+
+        if getattr(self, "_h", None):
+            L.lib().bc_joblight_destroy(self._h)
+            self._h = None
+        for c in getattr(self, "sqlc", []):
+            c.close()
+
+    def plan(self, sqls: Sequence[str]):
+        """The factor table of a batch: dict of numpy arrays (``status, join_size, first_factor, factor_bn, factor_inverse,
+        factor_fan_mask, pred_off, pred_col, pred_kind, pred_a, pred_b``)."""
+        import ctypes as C
+
+        import numpy as np
+
+        from . import _lib as L
+
+        n = len(sqls)
+        raw = [s.encode("utf-8") for s in sqls]
+        arr = (C.c_char_p * max(1, n))(*raw)
+        status = np.zeros(n, dtype=np.uint8)
+        join = np.zeros(n, dtype=np.float64)
+        first = np.zeros(n + 1, dtype=np.uint32)
+        cap_f, cap_p = max(16, 4 * n), max(64, 16 * n)
+        while True:
+            f_bn = np.zeros(cap_f, dtype=np.int32)
+            f_inv = np.zeros(cap_f, dtype=np.uint8)
+            f_fan = np.zeros(cap_f, dtype=np.uint32)
+            p_off = np.zeros(cap_f + 1, dtype=np.uint32)
+            p_col = np.zeros(cap_p, dtype=np.int32)
+            p_kind = np.zeros(cap_p, dtype=np.uint8)
+            p_a = np.zeros(cap_p, dtype=np.float64)
+            p_b = np.zeros(cap_p, dtype=np.float64)
+            nf, npred = C.c_size_t(), C.c_size_t()
+            rc = L.lib().bc_joblight_plan(self._h, n, C.cast(arr, C.c_void_p), status.ctypes.data, join.ctypes.data, first.ctypes.data,
+                                          cap_f, f_bn.ctypes.data, f_inv.ctypes.data, f_fan.ctypes.data, p_off.ctypes.data, cap_p,
+                                          p_col.ctypes.data, p_kind.ctypes.data, p_a.ctypes.data, p_b.ctypes.data, C.byref(nf), C.byref(npred))
+            if rc == L.ELIMIT and (nf.value > cap_f or npred.value > cap_p):
+                cap_f, cap_p = max(cap_f, nf.value), max(cap_p, npred.value)
+                continue
+            L.check(rc)
+            break
+        nf, npred = nf.value, npred.value
+        return {"status": status, "join_size": join, "first_factor": first, "factor_bn": f_bn[:nf], "factor_inverse": f_inv[:nf],
+                "factor_fan_mask": f_fan[:nf], "pred_off": p_off[:nf + 1], "pred_col": p_col[:npred], "pred_kind": p_kind[:npred],
+                "pred_a": p_a[:npred], "pred_b": p_b[:npred]}
+
+    def factor_rows(self, plan):
+        """Per BN: ``(factor ids, kind, BITS rows, DENSE rows, dense index)`` of the planned factors."""
+        import numpy as np
+
+        out = {}
+        for b in range(self.n_bn):
+            ids = np.nonzero(plan["factor_bn"] == b)[0].astype(np.uint32)
+            if ids.size == 0:
+                continue
+            out[b] = (ids,) + self.sqlc[b].compile_factors(ids, plan["pred_off"], plan["pred_col"], plan["pred_kind"], plan["pred_a"],
+                                                           plan["pred_b"], plan["factor_fan_mask"])
+        return out
+
+    def cardinality_sql_batch(self, sqls: Sequence[str]):
+        import numpy as np
+
+        from . import _lib as L
+
+        plan = self.plan(sqls)
+        nf = plan["factor_bn"].size
+        prob = np.zeros(nf, dtype=np.float64)
+        python_factors = []
+        for b, (ids, kind, bits, dense, didx) in self.factor_rows(plan).items():
+            m = self.machines[b]
+            mask = plan["factor_fan_mask"][ids].reshape(-1, 1)
+            sel = np.nonzero(kind == L.SQLC_BITS)[0]
+            if sel.size:
+                prob[ids[sel]] = m.dev.run_host(bits[sel], L.DESC_BITS, np.ascontiguousarray(mask[sel]), m.kernel)
+            if didx.size:
+                from .decode import dense_to_wsparse
+
+                ro, words = dense_to_wsparse(m.tm, dense)
+                prob[ids[didx]] = m.dev.run_wsparse_host(ro, words, np.ascontiguousarray(mask[didx]), m.kernel)
+            python_factors.extend(int(i) for i in ids[np.nonzero(kind == L.SQLC_PYTHON)[0]])
+            # SQLC_ZERO: probability 0 (already)
+        out = np.zeros(len(sqls), dtype=np.float64)
+        redo = set(np.nonzero(plan["status"])[0].tolist())
+        if python_factors:   # a factor the native decoder declined: its whole query goes through the mirror
+            owner = np.searchsorted(plan["first_factor"], np.asarray(python_factors), side="right") - 1
+            redo.update(int(q) for q in owner)
+        L.check(L.lib().bc_joblight_combine(len(sqls), plan["status"].ctypes.data, plan["join_size"].ctypes.data,
+                                            plan["first_factor"].ctypes.data, plan["factor_inverse"].ctypes.data, prob.ctypes.data,
+                                            out.ctypes.data))
+        for q in sorted(redo):
+            tq = self.ens.parse_query_all([plan_star_query(sqls[q], self.join_sizes)])[0]
+            out[q] = float(np.asarray(self.ens.cardinality(tq)).reshape(-1)[0])
+        return out

@@ -79,6 +79,8 @@ class SqlBatchCompiler:
             self._h, name.encode("utf-8"), node, 1 if col.enc is not None else 0, len(keys),
             e_str.ctypes.data, e_num.ctypes.data, C.cast(e_arr, C.c_void_p), e_bin.ctypes.data, e_w.ctypes.data,
             len(dom), d_str.ctypes.data, d_num.ctypes.data, C.cast(d_arr, C.c_void_p)))
+        if col.has_null and _is_num(col.null):   # BN.null_values[name]: skipped by (lo, hi) tuples (Bayescard_BN.py:304-318)
+            L.check(L.lib().bc_sqlc_set_null(self._h, name.encode("utf-8"), float(col.null)))
         self.native_columns.append(name)
 
     def _add_python_only(self, name: str, node: int) -> None:
@@ -130,6 +132,25 @@ class SqlBatchCompiler:
         nd = C.c_size_t()
         L.check(L.lib().bc_sqlc_compile(self._h, n, C.cast(arr, C.c_void_p), kind.ctypes.data, bits.ctypes.data,
                                         dense.ctypes.data, cap, didx.ctypes.data, C.byref(nd)))
+        return kind, bits, dense[: nd.value], didx[: nd.value]
+
+    def column_index(self, name: str) -> int:
+        return int(L.lib().bc_sqlc_column_index(self._h, name.encode("utf-8")))
+
+    def compile_factors(self, ids: np.ndarray, pred_off: np.ndarray, pred_col: np.ndarray, pred_kind: np.ndarray, pred_a: np.ndarray,
+                        pred_b: np.ndarray, fan_mask: Optional[np.ndarray]):
+        """Factors ``ids`` of a factor table (``bc_joblight_plan``) -> ``(kind uint8[n], bits uint8[n, stride], dense, dense_index)``:
+        ``query_decoding`` + row packing of dicts ``{column: scalar | (lo, hi)}`` in one native call."""
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        n = ids.size
+        kind = np.zeros(n, dtype=np.uint8)
+        bits = np.empty((n, self.bits_stride), dtype=np.uint8)
+        dense = np.empty((n, self.dense_width), dtype=np.float32)
+        didx = np.zeros(max(n, 1), dtype=np.uint32)
+        nd = C.c_size_t()
+        L.check(L.lib().bc_sqlc_compile_factors(self._h, n, ids.ctypes.data, pred_off.ctypes.data, pred_col.ctypes.data, pred_kind.ctypes.data,
+                                                pred_a.ctypes.data, pred_b.ctypes.data, fan_mask.ctypes.data if fan_mask is not None else None,
+                                                kind.ctypes.data, bits.ctypes.data, dense.ctypes.data, n, didx.ctypes.data, C.byref(nd)))
         return kind, bits, dense[: nd.value], didx[: nd.value]
 
     def compile(self, sqls: Sequence[str]) -> Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray, np.ndarray]:

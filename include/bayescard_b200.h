@@ -304,6 +304,38 @@ BC_API uint64_t bc_launch_count(void);
 BC_API const char* bc_last_error(void);
 BC_API const char* bc_version(void);
 
+/* ---- factor lists of join queries, natively (HOST only; BASELINE.json config 3) -----------------------------------------
+ * The IMDB ensemble answers a join query as join_size * prod(p_f | 1 / p_f) over FACTORS, each a query()/expectation() of one
+ * BN with a dict {column: scalar | (lo, hi)} (Models/BN_ensemble_model.py:192-252, Evaluation/parse_query_imdb.py:54-325).
+ * bc_sqlc_compile_factors restates Bayescard_BN.query_decoding (Models/Bayescard_BN.py:279-325) for those two value shapes
+ * (numeric values) and writes the BITS / DENSE rows; factor f owns predicates pred_off[f] .. pred_off[f+1]: the column index
+ * inside this compiler (bc_sqlc_column_index), kind 0 = scalar a / 1 = tuple (a, b).  ids (nullable) selects factors of a
+ * larger table (the factors of one BN); fan_mask (nullable, one word per factor) marks factors that carry fan-out columns.
+ * kind[] as for bc_sqlc_compile. */
+BC_API int bc_sqlc_set_null(bc_sqlc* c, const char* name, double null_value);   /* BN.null_values[name] */
+BC_API int bc_sqlc_column_index(const bc_sqlc* c, const char* name);            /* -1: not a column of this BN */
+BC_API int bc_sqlc_compile_factors(const bc_sqlc* c, size_t n_factors, const uint32_t* ids, const uint32_t* pred_off,
+                                   const int32_t* pred_col, const uint8_t* pred_kind, const double* pred_a, const double* pred_b,
+                                   const uint32_t* fan_mask, uint8_t* kind, void* bits_rows, float* dense_rows, size_t dense_capacity,
+                                   uint32_t* dense_index, size_t* n_dense);
+/* The job-light star planner: a batch of SQL texts -> factor table (what Evaluation/parse_query_imdb.py:54-325 produces for a
+ * star on title.id over the two-table models title x X; first model by the pairwise-RDC vector).  sqlc[b] / tables[b] /
+ * join_sizes[b]: the model of title x tables[b]; fan_node[a * n_bn + b]: node of title.mul_<tables[b]>.movie_id in model a.
+ * status[q] = 0 planned, 1 not a job-light star query (plan it with the Python mirror).  Factors of query q:
+ * first_factor[q] .. first_factor[q+1].  BC_ELIMIT with *n_factors / *n_preds set when the buffers are too small. */
+typedef struct bc_joblight bc_joblight;
+BC_API int bc_joblight_create(int n_bn, const bc_sqlc* const* sqlc, const char* const* tables, const double* join_sizes,
+                              const int32_t* fan_node, int n_rdc, const char* const* rdc_a, const char* const* rdc_b,
+                              const double* rdc_val, double epsilon, bc_joblight** out);
+BC_API void bc_joblight_destroy(bc_joblight* h);
+BC_API int bc_joblight_plan(const bc_joblight* h, size_t n, const char* const* sqls, uint8_t* status, double* join_size,
+                            uint32_t* first_factor, size_t factor_capacity, int32_t* factor_bn, uint8_t* factor_inverse,
+                            uint32_t* factor_fan_mask, uint32_t* pred_off, size_t pred_capacity, int32_t* pred_col, uint8_t* pred_kind,
+                            double* pred_a, double* pred_b, size_t* n_factors, size_t* n_preds);
+/* BN_ensemble.cardinality (Models/BN_ensemble_model.py:228-252): join_size * prod(p | 1/p), a zero factor gives 1, clamp >= 1. */
+BC_API int bc_joblight_combine(size_t n, const uint8_t* status, const double* join_size, const uint32_t* first_factor,
+                               const uint8_t* factor_inverse, const double* factor_prob, double* out);
+
 #ifdef __cplusplus
 }
 #endif

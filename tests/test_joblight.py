@@ -106,5 +106,123 @@ def test_job_light_on_the_gpu_equals_the_oracle():
     assert np.max(np.abs(one - batch) / np.maximum(batch, 1e-300)) < 2e-5
     qe = np.asarray([O.q_error(e, t) for e, t in zip(batch, true)])
     assert abs(float(np.percentile(qe, 50)) - 1.301) < 0.01 and abs(float(qe.max()) - 19.14) < 0.05
+    # the native path (C++ planner + factor compiler + combine): SQL texts in, cardinalities out; the 70 q-errors are unchanged
+    from bayescard_b200.joblight import NativeJobLight
+
+    nat = NativeJobLight(ens)
+    native = nat.cardinality_sql_batch(sqls)
+    assert np.max(np.abs(native - batch) / np.maximum(batch, 1e-300)) < 1e-6
+    qe_n = np.asarray([O.q_error(e, t) for e, t in zip(native, true)])
+    assert np.allclose(np.percentile(qe_n, [50, 90, 95, 100]), np.percentile(qe, [50, 90, 95, 100]), rtol=1e-6)
+    fuzz = _fuzz_star_queries(3000, 11) + ["SELECT COUNT(*) FROM title t,cast_info ci WHERE t.id=ci.movie_id AND t.kind_id=1;"]
+    tq_f = ens.parse_query_all(plan_workload(fuzz, nat.join_sizes))
+    assert np.max(np.abs(nat.cardinality_sql_batch(fuzz) - ens.cardinality_batch(tq_f)) / np.maximum(ens.cardinality_batch(tq_f), 1e-300)) < 1e-6
+    nat.close()
     for bn in bns.values():
         bn.close()
+
+
+# ------------------------------------------------------------------------------------ native planner + factor compiler
+def _fuzz_star_queries(n, seed):
+    """Synthetic job-light-shaped queries: random subsets of the five tables, random conditions on the columns job-light uses."""
+    rng = np.random.default_rng(seed)
+    cols = {"title": [("kind_id", 1, 7), ("production_year", 1880, 2019)], "movie_companies": [("company_id", 1, 230000), ("company_type_id", 1, 2)],
+            "movie_info": [("info_type_id", 1, 110)], "movie_info_idx": [("info_type_id", 99, 113)], "movie_keyword": [("keyword_id", 1, 134000)],
+            "cast_info": [("role_id", 1, 11)]}
+    alias = {"title": "t", "movie_companies": "mc", "movie_info": "mi", "movie_info_idx": "mi_idx", "movie_keyword": "mk", "cast_info": "ci"}
+    out = []
+    for _ in range(n):
+        tabs = list(rng.choice(list(BN_INDEX), size=int(rng.integers(1, 5)), replace=False))
+        frm = ["title t"] + [f"{t} {alias[t]}" for t in tabs]
+        rng.shuffle(frm)
+        conds = [f"t.id={alias[t]}.movie_id" for t in tabs]
+        for t in ["title"] + tabs:
+            for c, lo, hi in cols[t]:
+                for _ in range(int(rng.integers(0, 3))):
+                    op = str(rng.choice(["=", "<", ">", "<=", ">="]))
+                    conds.append(f"{alias[t]}.{c}{op}{int(rng.integers(lo, hi + 1))}")
+        out.append("SELECT COUNT(*) FROM " + ",".join(frm) + " WHERE " + " AND ".join(conds))
+    return out
+
+
+def _host_ensemble():
+    """The five IMDB BNs as host-only models (no GPU): enough for the planner and the factor compiler."""
+    from bayescard_b200.ensemble import BN_ensemble
+    from bayescard_b200.joblight import NativeJobLight
+    from bayescard_b200.model import Bayescard_BN
+
+    ens = BN_ensemble()
+    for i in range(5):
+        bn = Bayescard_BN(G.model(f"imdb{i}"), device=-1, infer_algo="exact-jit")
+        bn.init_inference_method()
+        ens.bns[i] = bn
+    return ens, NativeJobLight(ens)
+
+
+def test_native_planner_and_factor_rows_equal_the_python_mirror():
+    """bc_joblight_plan + bc_sqlc_compile_factors (C++) against plan_star_query + query_decoding + PredicateCompiler.pack (the
+    Python mirror): same factors (BN, inverse, fan-out columns, predicates in the same order with the same values) and the same
+    descriptor rows, on the 70 shipped job-light queries and 1 500 fuzzed star queries."""
+    from bayescard_b200 import _lib as L
+
+    sqls, _, _ = _workload()
+    sqls = sqls + _fuzz_star_queries(1500, 7)
+    ens, nat = _host_ensemble()
+    js = nat.join_sizes
+    plan = nat.plan(sqls)
+    assert not plan["status"].any()
+    rows = nat.factor_rows(plan)
+    where = {}
+    for b, (ids, kind, bits, dense, didx) in rows.items():
+        dpos = {int(i): k for k, i in enumerate(didx)}
+        for j, f in enumerate(ids):
+            where[int(f)] = (b, int(kind[j]), bits[j], dense[dpos[j]] if j in dpos else None)
+    n_dense = n_zero = 0
+    for q, sql in enumerate(sqls):
+        tq = plan_star_query(sql, js)
+        f0, f1 = int(plan["first_factor"][q]), int(plan["first_factor"][q + 1])
+        assert plan["join_size"][q] == tq[0] and f1 - f0 == len(tq) - 1, sql
+        for f, fac in zip(range(f0, f1), tq[1:]):
+            b = int(plan["factor_bn"][f])
+            assert b == fac["bn_index"] and bool(plan["factor_inverse"][f]) == fac["inverse"], sql
+            tm = ens.bns[b].tree
+            want_mask = 0
+            for name in fac["expectation"]:
+                want_mask |= 1 << tm._index[name]
+            assert int(plan["factor_fan_mask"][f]) == want_mask, sql
+            p0, p1 = int(plan["pred_off"][f]), int(plan["pred_off"][f + 1])
+            got = []
+            for p in range(p0, p1):
+                name = nat.sqlc[b].py.cols and [n for n in tm.attr_type if nat.sqlc[b].column_index(n) == int(plan["pred_col"][p])][0]
+                val = float(plan["pred_a"][p]) if plan["pred_kind"][p] == 0 else (float(plan["pred_a"][p]), float(plan["pred_b"][p]))
+                got.append((name, val))
+            want = [(k, float(v) if not isinstance(v, tuple) else (float(v[0]), float(v[1]))) for k, v in fac["query"].items()]
+            assert got == want, (sql, got, want)
+            # rows: the Python mirror decodes and packs the same dict
+            bn_, kind, bits_row, dense_row = where[f]
+            m = ens.bns[b]._machine()
+            dq, dw = m.compiler.decode(dict(fac["query"]))
+            if dq is None:
+                assert kind == L.SQLC_ZERO, sql
+                n_zero += 1
+                continue
+            bi, bd, di, dd, mask = m.compiler.pack([(dq, dw)], [list(fac["expectation"])])
+            if len(bi):
+                assert kind == L.SQLC_BITS and np.array_equal(bits_row, np.asarray(bd[0]).view(np.uint8).reshape(-1)), sql
+            else:
+                assert kind == L.SQLC_DENSE and np.array_equal(dense_row, dd[0]), sql
+                n_dense += 1
+    assert n_dense > 20 and n_zero > 0   # fractional weights (continuous columns) and undecodable predicates both occur
+    # what the native planner declines goes to the mirror
+    bad = nat.plan(["SELECT COUNT(*) FROM title t,name n WHERE t.id=n.id", "SELECT 1", sqls[0]])
+    assert bad["status"].tolist() == [1, 1, 0]
+    # combine: BN_ensemble.cardinality's rules
+    import ctypes as C
+    first = np.asarray([0, 2, 4, 5], dtype=np.uint32)
+    inv = np.asarray([0, 1, 0, 0, 0], dtype=np.uint8)
+    prob = np.asarray([0.5, 0.25, 0.0, 0.5, 1e-9], dtype=np.float64)
+    out = np.zeros(3)
+    L.check(L.lib().bc_joblight_combine(3, None, np.asarray([100.0, 100.0, 100.0]).ctypes.data, first.ctypes.data, inv.ctypes.data,
+                                        prob.ctypes.data, out.ctypes.data))
+    assert out.tolist() == [200.0, 1.0, 1.0]
+    nat.close()
