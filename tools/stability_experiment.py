@@ -184,7 +184,7 @@ def main():
     ap.add_argument("--rows", type=int, default=1_000_000)
     ap.add_argument("--queries", type=int, default=200)
     ap.add_argument("--out", default="")
-    ap.add_argument("--max-columns", type=int, default=100)
+    ap.add_argument("--max-columns", type=int, default=10, help="n = 50 / 100: drawing queries with a non-zero true cardinality is rejection-bound on the host")
     args = ap.parse_args()
     res = []
     print("vary domain size (s = 1.0, c = 0.4, n = 10)")
