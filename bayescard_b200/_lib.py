@@ -91,7 +91,8 @@ _SIGS = {
     "bc_sqlc_set_null": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
     "bc_sqlc_column_index": (C.c_int, [C.c_void_p, C.c_char_p]),
     "bc_sqlc_compile_factors": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t)]),
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t),
+                                          C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "bc_joblight_create": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_double, C.POINTER(C.c_void_p)]),
     "bc_joblight_destroy": (None, [C.c_void_p]),

@@ -18,6 +18,7 @@
 // BC_SQLC_PYTHON and the host library (bayescard_b200/sqlc.py) runs it through its Python mirror of the same two
 // functions, so results are identical by construction.  tests/test_sqlc.py compares every row this file emits with
 // that mirror on the shipped workloads and on fuzzed SQL.
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -680,9 +681,16 @@ namespace {
 // Batch driver shared by the SQL and the factor entry points: `one(q, scratch)` decodes query q into scratch.dec and returns
 // its kind.  Queries are independent: slices of the batch are compiled on host threads.  BITS rows land at their query
 // index; DENSE rows are collected per thread and appended in query order afterwards.
+struct WsOut {   // DENSE-kind queries as WSPARSE rows (weighted runs, include/bayescard_b200.h) instead of DENSE_F32 rows
+    uint32_t* row_off;   // [dense_capacity + 1]
+    uint32_t* words;
+    size_t capacity;     // words
+    size_t* n_words;
+};
+
 template <class One>
 int run_batch(const bc_sqlc* c, size_t n_queries, One one, uint8_t* kind, void* bits_rows, float* dense_rows, size_t dense_capacity,
-              uint32_t* dense_index, size_t* n_dense) {
+              uint32_t* dense_index, size_t* n_dense, const WsOut* ws = nullptr) {
     uint8_t* bits = static_cast<uint8_t*>(bits_rows);
     unsigned n_thr = std::thread::hardware_concurrency();
     if (const char* e = std::getenv("BC_SQLC_THREADS")) n_thr = (unsigned)std::atoi(e);
@@ -693,6 +701,7 @@ int run_batch(const bc_sqlc* c, size_t n_queries, One one, uint8_t* kind, void* 
     struct Part {
         std::vector<float> dense;       // DENSE rows of this slice, in query order
         std::vector<uint32_t> index;
+        std::vector<uint32_t> ws, ws_len;   // ... or their WSPARSE rows and row lengths
     };
     std::vector<Part> part(n_thr);
     const size_t width = (size_t)c->dense_width;
@@ -711,6 +720,39 @@ int run_batch(const bc_sqlc* c, size_t n_queries, One one, uint8_t* kind, void* 
                     clear_bits(row, o, c->card[d.node]);
                     for (int32_t b : d.bins) row[(o + b) >> 3] |= (uint8_t)(1u << ((o + b) & 7));
                 }
+            } else if (k == KIND_DENSE && ws) {
+                // one run per constrained column: the states from the first to the last non-zero weight (zeros inside are sent);
+                // the device expansion reproduces the DENSE row bit for bit (decode.dense_to_wsparse is the Python twin)
+                const size_t at = pt.ws.size();
+                std::sort(sc.dec.begin(), sc.dec.begin() + (long)sc.n_dec, [](const Decoded& x, const Decoded& y) { return x.node < y.node; });
+                for (size_t i = 0; i < sc.n_dec; ++i) {   // runs in column order, like the Python packer
+                    const Decoded& d = sc.dec[i];
+                    const int card = c->card[d.node];
+                    sc.seg.assign((size_t)card, 0.0);
+                    for (size_t j = 0; j < d.bins.size(); ++j) sc.seg[d.bins[j]] += d.wts[j];
+                    int first = 0, last = -1;
+                    for (int s2 = 0; s2 < card; ++s2)
+                        if ((float)sc.seg[s2] != 0.f) { if (last < 0) first = s2; last = s2; }
+                    bool all_one = true;
+                    for (int s2 = 0; s2 < card && all_one; ++s2) all_one = (float)sc.seg[s2] == 1.f;
+                    if (all_one) continue;   // the column's segment equals the default: unconstrained, no run
+                    int count = last - first + 1;
+                    if (last < 0) { first = 0; count = 0; }
+                    int done = 0;
+                    do {   // the run length is an 8-bit field: 255 states, then continuation runs
+                        const int n = std::min(count - done, 255);
+                        pt.ws.push_back((uint32_t)d.node | (done ? (1u << 15) : 0u) | ((uint32_t)(first + done) << 16) | ((uint32_t)n << 24));
+                        for (int j = 0; j < n; ++j) {
+                            const float w = (float)sc.seg[first + done + j];
+                            uint32_t bits32;
+                            std::memcpy(&bits32, &w, 4);
+                            pt.ws.push_back(bits32);
+                        }
+                        done += n;
+                    } while (done < count);
+                }
+                pt.ws_len.push_back((uint32_t)(pt.ws.size() - at));
+                pt.index.push_back((uint32_t)q);
             } else if (k == KIND_DENSE) {
                 const size_t at = pt.dense.size();
                 pt.dense.resize(at + width);
@@ -734,6 +776,28 @@ int run_batch(const bc_sqlc* c, size_t n_queries, One one, uint8_t* kind, void* 
         std::vector<std::thread> pool;
         for (unsigned t = 0; t < n_thr; ++t) pool.emplace_back(work, t);
         for (std::thread& th : pool) th.join();
+    }
+    if (ws) {
+        size_t nd = 0, nw = 0;
+        for (const Part& pt : part) {
+            size_t at = 0;
+            for (size_t i = 0; i < pt.index.size(); ++i) {
+                const size_t len = pt.ws_len[i];
+                if (nd >= dense_capacity || nw + len > ws->capacity || !dense_index) {
+                    kind[pt.index[i]] = (uint8_t)KIND_OVERFLOW;
+                } else {
+                    ws->row_off[nd] = (uint32_t)nw;
+                    std::memcpy(ws->words + nw, pt.ws.data() + at, len * 4);
+                    nw += len;
+                    dense_index[nd++] = pt.index[i];
+                }
+                at += len;
+            }
+        }
+        ws->row_off[nd] = (uint32_t)nw;
+        *ws->n_words = nw;
+        *n_dense = nd;
+        return BC_OK;
     }
     size_t nd = 0;
     for (const Part& pt : part)
@@ -779,18 +843,20 @@ int bc_sqlc_column_index(const bc_sqlc* c, const char* name) {
 
 int bc_sqlc_compile_factors(const bc_sqlc* c, size_t n_factors, const uint32_t* ids, const uint32_t* pred_off, const int32_t* pred_col,
                             const uint8_t* pred_kind, const double* pred_a, const double* pred_b, const uint32_t* fan_mask, uint8_t* kind,
-                            void* bits_rows, float* dense_rows, size_t dense_capacity, uint32_t* dense_index, size_t* n_dense) {
-    if (!c || (n_factors && (!pred_off || !kind || !bits_rows)) || !n_dense) {
+                            void* bits_rows, float* dense_rows, size_t dense_capacity, uint32_t* dense_index, size_t* n_dense,
+                            uint32_t* ws_row_off, uint32_t* ws_words, size_t ws_capacity, size_t* n_ws_words) {
+    if (!c || (n_factors && (!pred_off || !kind || !bits_rows)) || !n_dense || (ws_words && (!ws_row_off || !n_ws_words))) {
         bc_set_error("bc_sqlc_compile_factors: bad arguments");
         return BC_EINVAL;
     }
+    WsOut ws{ws_row_off, ws_words, ws_capacity, n_ws_words};
     return run_batch(c, n_factors,
                      [&](size_t q, Scratch& sc) {
                          const size_t f = ids ? ids[q] : q;
                          return compile_factor(*c, pred_col, pred_kind, pred_a, pred_b, pred_off[f], pred_off[f + 1],
                                                fan_mask != nullptr && fan_mask[f] != 0, sc);
                      },
-                     kind, bits_rows, dense_rows, dense_capacity, dense_index, n_dense);
+                     kind, bits_rows, dense_rows, dense_capacity, dense_index, n_dense, ws_words ? &ws : nullptr);
 }
 
 }  // extern "C"

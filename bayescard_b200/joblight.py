@@ -257,8 +257,8 @@ class NativeJobLight:
                 "factor_fan_mask": f_fan[:nf], "pred_off": p_off[:nf + 1], "pred_col": p_col[:npred], "pred_kind": p_kind[:npred],
                 "pred_a": p_a[:npred], "pred_b": p_b[:npred]}
 
-    def factor_rows(self, plan):
-        """Per BN: ``(factor ids, kind, BITS rows, DENSE rows, dense index)`` of the planned factors."""
+    def factor_rows(self, plan, wsparse: bool = False):
+        """Per BN: ``(factor ids, kind, BITS rows, DENSE rows | WSPARSE (row_off, words), dense index)`` of the planned factors."""
         import numpy as np
 
         out = {}
@@ -267,7 +267,7 @@ class NativeJobLight:
             if ids.size == 0:
                 continue
             out[b] = (ids,) + self.sqlc[b].compile_factors(ids, plan["pred_off"], plan["pred_col"], plan["pred_kind"], plan["pred_a"],
-                                                           plan["pred_b"], plan["factor_fan_mask"])
+                                                           plan["pred_b"], plan["factor_fan_mask"], wsparse)
         return out
 
     def cardinality_sql_batch(self, sqls: Sequence[str]):
@@ -279,19 +279,18 @@ class NativeJobLight:
         nf = plan["factor_bn"].size
         prob = np.zeros(nf, dtype=np.float64)
         python_factors = []
-        for b, (ids, kind, bits, dense, didx) in self.factor_rows(plan).items():
+        for b, (ids, kind, bits, ws, didx) in self.factor_rows(plan, wsparse=True).items():
             m = self.machines[b]
             mask = plan["factor_fan_mask"][ids].reshape(-1, 1)
             sel = np.nonzero(kind == L.SQLC_BITS)[0]
             if sel.size:
                 prob[ids[sel]] = m.dev.run_host(bits[sel], L.DESC_BITS, np.ascontiguousarray(mask[sel]), m.kernel)
-            if didx.size:
-                from .decode import dense_to_wsparse
-
-                ro, words = dense_to_wsparse(m.tm, dense)
-                prob[ids[didx]] = m.dev.run_wsparse_host(ro, words, np.ascontiguousarray(mask[didx]), m.kernel)
+            if didx.size:   # fractional weights: weighted runs over PCIe (~100 B per factor), DENSE rows built on the device
+                prob[ids[didx]] = m.dev.run_wsparse_host(ws[0], ws[1], np.ascontiguousarray(mask[didx]), m.kernel)
             python_factors.extend(int(i) for i in ids[np.nonzero(kind == L.SQLC_PYTHON)[0]])
-            # SQLC_ZERO: probability 0 (already)
+            # SQLC_ZERO: probability 0 (already) -- except on an EXPECTATION factor: Bayescard_BN.expectation has no guard for an
+            # undecodable predicate and the reference fails there (Models/Bayescard_BN.py:581-583); the mirror raises the same
+            python_factors.extend(int(i) for i in ids[np.nonzero((kind == L.SQLC_ZERO) & (mask[:, 0] != 0))[0]])
         out = np.zeros(len(sqls), dtype=np.float64)
         redo = set(np.nonzero(plan["status"])[0].tolist())
         if python_factors:   # a factor the native decoder declined: its whole query goes through the mirror

@@ -138,20 +138,33 @@ class SqlBatchCompiler:
         return int(L.lib().bc_sqlc_column_index(self._h, name.encode("utf-8")))
 
     def compile_factors(self, ids: np.ndarray, pred_off: np.ndarray, pred_col: np.ndarray, pred_kind: np.ndarray, pred_a: np.ndarray,
-                        pred_b: np.ndarray, fan_mask: Optional[np.ndarray]):
+                        pred_b: np.ndarray, fan_mask: Optional[np.ndarray], wsparse: bool = False):
         """Factors ``ids`` of a factor table (``bc_joblight_plan``) -> ``(kind uint8[n], bits uint8[n, stride], dense, dense_index)``:
-        ``query_decoding`` + row packing of dicts ``{column: scalar | (lo, hi)}`` in one native call."""
+        ``query_decoding`` + row packing of dicts ``{column: scalar | (lo, hi)}`` in one native call.  ``wsparse=True``: the
+        factors with fractional weights come back as WSPARSE rows ``(row_off, words)`` in place of the DENSE_F32 rows."""
         ids = np.ascontiguousarray(ids, dtype=np.uint32)
         n = ids.size
         kind = np.zeros(n, dtype=np.uint8)
         bits = np.empty((n, self.bits_stride), dtype=np.uint8)
-        dense = np.empty((n, self.dense_width), dtype=np.float32)
         didx = np.zeros(max(n, 1), dtype=np.uint32)
         nd = C.c_size_t()
-        L.check(L.lib().bc_sqlc_compile_factors(self._h, n, ids.ctypes.data, pred_off.ctypes.data, pred_col.ctypes.data, pred_kind.ctypes.data,
-                                                pred_a.ctypes.data, pred_b.ctypes.data, fan_mask.ctypes.data if fan_mask is not None else None,
-                                                kind.ctypes.data, bits.ctypes.data, dense.ctypes.data, n, didx.ctypes.data, C.byref(nd)))
-        return kind, bits, dense[: nd.value], didx[: nd.value]
+        args = (self._h, n, ids.ctypes.data, pred_off.ctypes.data, pred_col.ctypes.data, pred_kind.ctypes.data, pred_a.ctypes.data,
+                pred_b.ctypes.data, fan_mask.ctypes.data if fan_mask is not None else None, kind.ctypes.data, bits.ctypes.data)
+        if not wsparse:
+            dense = np.empty((n, self.dense_width), dtype=np.float32)
+            L.check(L.lib().bc_sqlc_compile_factors(*args, dense.ctypes.data, n, didx.ctypes.data, C.byref(nd), None, None, 0, None))
+            return kind, bits, dense[: nd.value], didx[: nd.value]
+        cap = max(64, 48 * n)   # words; grown on overflow
+        while True:
+            ro = np.zeros(n + 1, dtype=np.uint32)
+            words = np.empty(cap, dtype=np.uint32)
+            nw = C.c_size_t()
+            L.check(L.lib().bc_sqlc_compile_factors(*args, None, n, didx.ctypes.data, C.byref(nd), ro.ctypes.data, words.ctypes.data, cap,
+                                                    C.byref(nw)))
+            if (kind == L.SQLC_OVERFLOW).any():
+                cap *= 4
+                continue
+            return kind, bits, (ro[: nd.value + 1], words[: nw.value]), didx[: nd.value]
 
     def compile(self, sqls: Sequence[str]) -> Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray, np.ndarray]:
         """Descriptors of a batch: ``(bits_idx, bits_rows, dense_idx, dense_rows, zero_idx)``.

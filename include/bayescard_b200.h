@@ -311,13 +311,15 @@ BC_API const char* bc_version(void);
  * (numeric values) and writes the BITS / DENSE rows; factor f owns predicates pred_off[f] .. pred_off[f+1]: the column index
  * inside this compiler (bc_sqlc_column_index), kind 0 = scalar a / 1 = tuple (a, b).  ids (nullable) selects factors of a
  * larger table (the factors of one BN); fan_mask (nullable, one word per factor) marks factors that carry fan-out columns.
- * kind[] as for bc_sqlc_compile. */
+ * kind[] as for bc_sqlc_compile.  With ws_words != NULL the factors with fractional weights are written as WSPARSE rows
+ * (ws_row_off[k] .. ws_row_off[k+1] for dense_index[k]; ~100 B instead of a 1.5 KB DENSE row) and dense_rows is not used. */
 BC_API int bc_sqlc_set_null(bc_sqlc* c, const char* name, double null_value);   /* BN.null_values[name] */
 BC_API int bc_sqlc_column_index(const bc_sqlc* c, const char* name);            /* -1: not a column of this BN */
 BC_API int bc_sqlc_compile_factors(const bc_sqlc* c, size_t n_factors, const uint32_t* ids, const uint32_t* pred_off,
                                    const int32_t* pred_col, const uint8_t* pred_kind, const double* pred_a, const double* pred_b,
                                    const uint32_t* fan_mask, uint8_t* kind, void* bits_rows, float* dense_rows, size_t dense_capacity,
-                                   uint32_t* dense_index, size_t* n_dense);
+                                   uint32_t* dense_index, size_t* n_dense, uint32_t* ws_row_off, uint32_t* ws_words, size_t ws_capacity,
+                                   size_t* n_ws_words);
 /* The job-light star planner: a batch of SQL texts -> factor table (what Evaluation/parse_query_imdb.py:54-325 produces for a
  * star on title.id over the two-table models title x X; first model by the pairwise-RDC vector).  sqlc[b] / tables[b] /
  * join_sizes[b]: the model of title x tables[b]; fan_node[a * n_bn + b]: node of title.mul_<tables[b]>.movie_id in model a.
