@@ -20,15 +20,16 @@
 // (tcgen05.st: hi and lo TF32 halves, 16 columns each per block of 16 child states) and read from there by the MMAs;
 // shared memory only carries T_v^T (TMA) and the staged query weights.
 //
-// Roles (448 threads, one CTA per SM, all 512 tensor-memory columns):
+// Roles (576 threads, one CTA per SM, all 512 tensor-memory columns):
 //   * warps 0-3 / 4-7  TWO PRODUCER GROUPS (thread = query = TMEM lane) build alternate blocks: weights from the BITS tile
-//     in shared memory or, for DENSE_F32 rows, from a shared-memory ring that the TMA warp fills four blocks ahead with
-//     2-D tensor-map loads (128 queries x 16 floats, 64-byte swizzle) -- no global-memory latency in the loop; times the
-//     fan-out vector, times Lambda_v (tcgen05.ld) for an internal node; split into TF32 hi (round to nearest) and lo = x - hi;
-//     tcgen05.st into the A ring; one mbarrier arrive per warp;
-//   * warps 8-11       EPILOGUE WARPS: Lambda_pa (*)= D with tcgen05.ld / tcgen05.st while the MMAs of the next edge fill the
-//     other accumulator buffer; they publish "Lambda_v complete" (one mbarrier per internal edge) to the producers and
-//     finish a tile with the root's dot product;
+//     in shared memory or, for DENSE_F32 rows, from a shared-memory ring that the TMA warp fills with 2-D tensor-map loads
+//     (128 queries x 16 floats, 64-byte swizzle) -- no global-memory latency in the loop; times the fan-out vector, times
+//     Lambda_v (tcgen05.ld) for an internal node; split into TF32 hi (round to nearest) and lo = x - hi; tcgen05.st into the
+//     A ring; one mbarrier arrive per warp;
+//   * warps 8-11 / 14-17  TWO EPILOGUE GROUPS, each owning one half of the parent's columns: over a run of consecutive edges
+//     into the same parent, Lambda_pa stays in REGISTERS (only D is read from tensor memory per edge -- TMEM reads are the
+//     slow direction); at the end of a run it is written to tensor memory and published ("Lambda_v complete", one mbarrier
+//     per internal edge) to the producers, or, for the root, folded into the tile's result on the spot;
 //   * warp 12          MMA ISSUER (whole warp converged, elect.sync inside the asm, edge table in the kernel-parameter bank
 //     so that every tcgen05 operand lives in uniform registers): error-compensated 3xTF32, A_lo.B_hi + A_hi.B_lo first, then
 //     A_hi.B_hi (A_lo = 0 and skipped for unit-weight leaves); tcgen05.commit frees the A and B slots and hands the accumulator
@@ -62,8 +63,10 @@ struct K3Edge {            // 64 bytes, in the kernel parameter bank
     uint64_t bimg_off;     // byte offset of the edge's operand images
     int32_t publish;       // >= 0: this edge is the LAST message into Lambda_pa, pa's own edge is `publish` (its producers may
                            // start); -2: ... and pa is the root (the tile's result follows); -1: more messages to come
-    int32_t fin_guard;     // the first edge of a tile whose epilogue writes into the columns the finisher warps read (the root's message)
+    int32_t flags;         // kRunFirst / kRunLast: first / last edge of a RUN of consecutive edges into the same parent (the epilogue warps keep
+                           // the parent's message in registers over a run); kRegs: the parent's domain fits the register accumulators
 };
+enum { kRunFirst = 1, kRunLast = 2, kRegs = 4 };
 static_assert(sizeof(K3Edge) == 64, "K3Edge layout");
 
 struct BcK3Plan {
@@ -90,8 +93,9 @@ constexpr int kBK = 16;        // child states per ring step
 constexpr int kStagesW = 8;    // DENSE weight ring (8 KB per slot): deep, the loads come from HBM
 constexpr int kWBytes = kTile * kBK * 4;
 constexpr int kGroups = 2;     // producer groups of four warps, alternate blocks
-constexpr int kWarpEpi = 4 * kGroups, kWarpMma = kWarpEpi + 4, kWarpTma = kWarpMma + 1, kWarpFin = kWarpTma + 1;
-constexpr int kThreads = 32 * (kWarpFin + 4);   // + four finisher warps (one per TMEM lane quarter: warp % 4)
+constexpr int kWarpEpi = 4 * kGroups, kWarpMma = kWarpEpi + 4, kWarpTma = kWarpMma + 1, kWarpEpiB = kWarpTma + 1;
+constexpr int kThreads = 32 * (kWarpEpiB + 4);   // two epilogue groups of four warps (one warp per TMEM lane quarter: warp % 4)
+constexpr int kAcc = 48;       // message columns an epilogue thread keeps in registers (each group owns one half of the parent's columns)
 constexpr int kMaxStages = 8;
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -197,6 +201,15 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                  : "r"(taddr)
                  : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
 }
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
     const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
@@ -304,11 +317,12 @@ __global__ void __launch_bounds__(kThreads, 1) k3_kernel(const __grid_constant__
     p += (size_t)P.fan_floats * 4;
     float4* s_tab = reinterpret_cast<float4*>(p);   // nibble -> four 0/1 floats
     p += 256;
+    float* s_part = reinterpret_cast<float*>(p);    // the second epilogue group's share of the root's dot product, two tiles
+    p += 2 * kTile * 4;
     uint64_t* bars = reinterpret_cast<uint64_t*>(p);
     const uint32_t a_full0 = smem_u32(bars), a_empty0 = a_full0 + 8 * kMaxStages, b_full0 = a_empty0 + 8 * kMaxStages,
                    b_empty0 = b_full0 + 8 * kMaxStages, w_full0 = b_empty0 + 8 * kMaxStages, w_empty0 = w_full0 + 8 * kStagesW,
-                   d_full0 = w_empty0 + 8 * kStagesW, d_empty0 = d_full0 + 16, bits_free0 = d_empty0 + 16, fin_ready0 = bits_free0 + 16,
-                   fin_done0 = fin_ready0 + 8, lam_ready0 = fin_done0 + 8;
+                   d_full0 = w_empty0 + 8 * kStagesW, d_empty0 = d_full0 + 16, bits_free0 = d_empty0 + 16, lam_ready0 = bits_free0 + 32;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * kMaxStages + 2 * kStagesW + 8 + kMaxEdges + 1);
     long long* s_trace = reinterpret_cast<long long*>(bars + 4 * kMaxStages + 2 * kStagesW + 8 + kMaxEdges + 2);   // BC_K3_TRACE only
 
@@ -329,12 +343,10 @@ __global__ void __launch_bounds__(kThreads, 1) k3_kernel(const __grid_constant__
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(d_full0 + 8 * b, 1);
-            mbar_init(d_empty0 + 8 * b, 4);
-            mbar_init(bits_free0 + 8 * b, 4);
+            mbar_init(d_empty0 + 8 * b, 8);      // both epilogue groups
+            mbar_init(bits_free0 + 8 * b, 8);
         }
-        mbar_init(fin_ready0, 4);
-        mbar_init(fin_done0, 4);
-        for (int e = 0; e < P.n_edges; ++e) mbar_init(lam_ready0 + 8 * e, 4);
+        for (int e = 0; e < P.n_edges; ++e) mbar_init(lam_ready0 + 8 * e, 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -534,106 +546,164 @@ __global__ void __launch_bounds__(kThreads, 1) k3_kernel(const __grid_constant__
                 if ((warp & 3) == 0) K3_STAMP(1 + g, e, 1);
             }
         }
-    } else if (warp < kWarpMma) {
-        // ================= epilogue warps: Lambda_pa (*)= D in tensor memory, 32 columns per round trip; the root's dot product
+    } else {
+        // ================= epilogue warps, two groups of four (warps 8-11: the lower half of the parent's columns, warps 14-17: the
+        // upper half).  Over a RUN of consecutive edges into the same parent the message Lambda_pa stays in REGISTERS: per edge
+        // only D is read from tensor memory (TMEM reads run at ~190 B/clk/SM, a quarter of the write rate -- reading D and
+        // Lambda_pa and writing Lambda_pa back cost 1 250 clk per N = 84 edge and paced the leaves); the accumulator buffer is
+        // handed back to the MMA warp as soon as it has been read; at the end of a run the message goes to tensor memory for the
+        // producers of pa's own edge -- or, for the root, straight into the tile's result.
+        const int g = warp >= kWarpEpiB;
         const int ql = tid & (kTile - 1);
         const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         uint32_t ed = 0, tile_iter = 0;
+        float acc[kAcc];
+#pragma unroll
+        for (int i = 0; i < kAcc; ++i) acc[i] = 0.f;
         for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tile_iter) {
-            const size_t q = (size_t)tile * kTile + ql;
-            const size_t qc = q < P.nq ? q : P.nq - 1;
-            const uint32_t buf = tile_iter & 1u;
             for (int e = 0; e < P.n_edges; ++e, ++ed) {
                 const K3Edge& E = P.edge[e];
                 const uint32_t db = P.n_dbuf == 2 ? (ed & 1u) : 0u, dpar = (P.n_dbuf == 2 ? (ed >> 1) : ed) & 1u;
                 const uint32_t dcol = tlane + (uint32_t)(P.d_col + (int)db * P.d_stride), pcol = tlane + (uint32_t)E.col_pa;
-                const bool first = E.first;
+                const bool first = E.first, run_first = (E.flags & kRunFirst) != 0, run_last = (E.flags & kRunLast) != 0;
+                const bool regs = (E.flags & kRegs) != 0, root = E.publish == -2;
+                // this group's columns [lo, hi) of the parent's n8 (both multiples of 8; the split is a function of card(pa) only)
+                const int n8 = (E.N + 7) & ~7, half = ((n8 >> 1) + 15) & ~15, mid = half < n8 ? half : n8;
+                const int lo = g ? mid : 0, hi = g ? n8 : mid;
                 // optional correction of the truncating accumulator (off by default)
                 const bool a_exact = FMT == BC_DESC_BITS && E.col_v < 0 && !(E.fan_off >= 0 && P.fan_mask != nullptr);
                 const int n_mma = ((int)E.K + 7) / 8 * (a_exact ? 2 : 3);
                 const float debias = 1.f + (float)(n_mma - 1) * P.debias_unit;
                 mbar_wait(d_full0 + 8 * db, dpar);
-                if (E.fin_guard && tile_iter > 0) mbar_wait(fin_done0, (tile_iter - 1u) & 1u);   // the previous tile's result has been read out
                 tc_fence_after();
                 if (warp == kWarpEpi) K3_STAMP(3, e, 0);
-                const int n8 = (E.N + 7) & ~7;
-                for (int j = 0; j < n8; j += 32) {
-                    float dv[32], lv[32];
-                    if (j + 32 <= n8) {   // whole 32-column chunks with one instruction each
-                        tmem_ld32(dcol + (uint32_t)j, dv);
-                        if (!first) tmem_ld32(pcol + (uint32_t)j, lv);
-                    } else {
+                if (regs) {
+                    if (run_first) {   // acc = D (first message into pa) or acc = Lambda_pa (an earlier run's product, from tensor memory)
+                        const uint32_t src = first ? dcol : pcol;
 #pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                            if (j + 8 * c < n8) {
-                                tmem_ld8(dcol + (uint32_t)(j + 8 * c), dv + 8 * c);
-                                if (!first) tmem_ld8(pcol + (uint32_t)(j + 8 * c), lv + 8 * c);
+                        for (int r = 0; r < kAcc / 16; ++r) {
+                            const int j = lo + 16 * r;
+                            if (j + 16 <= hi) tmem_ld16(src + (uint32_t)j, acc + 16 * r);
+                            else if (j < hi) tmem_ld8(src + (uint32_t)j, acc + 16 * r);
+                        }
+                        if (first) {
+                            tmem_ld_wait();
+                            if (P.debias_unit != 0.f) {
+#pragma unroll
+                                for (int i = 0; i < kAcc; ++i) acc[i] *= debias;
                             }
+                        }
                     }
-                    tmem_ld_wait();
-                    if (!first) {
+                    if (!(run_first && first)) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) dv[i] *= lv[i] * debias;
-                    } else {
+                        for (int r = 0; r < kAcc / 8; ++r) {
+                            const int j = lo + 8 * r;
+                            if (j < hi) {
+                                float dv[8];
+                                tmem_ld8(dcol + (uint32_t)j, dv);
+                                tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) dv[i] *= debias;
+                                for (int i = 0; i < 8; ++i) acc[8 * r + i] *= dv[i] * debias;
+                            }
+                        }
                     }
-                    if (j + 32 <= n8) {
-                        tmem_st32(pcol + (uint32_t)j, dv);
-                    } else {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(d_empty0 + 8 * db);   // the accumulator has been read: the MMAs of the edge after next may start
+                    if (run_last && !root) {   // the message goes to tensor memory
 #pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                            if (j + 8 * c < n8) tmem_st8(pcol + (uint32_t)(j + 8 * c), dv + 8 * c);
+                        for (int r = 0; r < kAcc / 16; ++r) {
+                            const int j = lo + 16 * r;
+                            if (j + 16 <= hi) tmem_st16(pcol + (uint32_t)j, acc + 16 * r);
+                            else if (j < hi) tmem_st8(pcol + (uint32_t)j, acc + 16 * r);
+                        }
+                        tmem_st_wait();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0 && E.publish >= 0) mbar_arrive(lam_ready0 + 8 * E.publish);   // Lambda_pa is complete: pa's own edge may be built
+                    }
+                } else {
+                    // a parent domain beyond 2 x kAcc states: Lambda_pa (*)= D in tensor memory, 16 columns per round trip
+                    for (int j = lo; j < hi; j += 16) {
+                        float dv[16], lv[16];
+                        const bool whole = j + 16 <= hi;   // else 8 columns
+                        if (whole) {
+                            tmem_ld16(dcol + (uint32_t)j, dv);
+                            if (!first) tmem_ld16(pcol + (uint32_t)j, lv);
+                        } else {
+                            tmem_ld8(dcol + (uint32_t)j, dv);
+                            if (!first) tmem_ld8(pcol + (uint32_t)j, lv);
+                        }
+                        tmem_ld_wait();
+                        if (!first) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) dv[i] *= lv[i] * debias;
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) dv[i] *= debias;
+                        }
+                        if (whole) tmem_st16(pcol + (uint32_t)j, dv);
+                        else tmem_st8(pcol + (uint32_t)j, dv);
+                    }
+                    tmem_st_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(d_empty0 + 8 * db);
+                        if (E.publish >= 0) mbar_arrive(lam_ready0 + 8 * E.publish);
                     }
                 }
-                tmem_st_wait();
-                tc_fence_before();
-                __syncwarp();
                 if (warp == kWarpEpi) K3_STAMP(3, e, 1);
-                if (lane == 0) {
-                    mbar_arrive(d_empty0 + 8 * db);                              // the accumulator may be overwritten
-                    if (E.publish >= 0) mbar_arrive(lam_ready0 + 8 * E.publish);   // Lambda_pa is complete: pa's own edge may be built
-                    if (E.publish == -2) mbar_arrive(fin_ready0);                  // ... the finisher warps take the tile from here
-                }
-            }
-        }
-    } else if (warp >= kWarpFin) {
-        // ================= finisher warps: the root's dot product per tile, while the other roles are already in the next tile
-        // (measured and dropped in round 2, profiles/r2_k3_tail_ab.txt: folding the root's only child into this step in
-        //  registers -- the reader of the hub's message then sits on the next tile's critical path)
-        const int ql = tid & (kTile - 1);
-        const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-        uint32_t tile_iter = 0;
-        for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tile_iter) {
-            const size_t q = (size_t)tile * kTile + ql;
-            const size_t qc = q < P.nq ? q : P.nq - 1;
-            const uint32_t buf = tile_iter & 1u;
-            mbar_wait(fin_ready0, tile_iter & 1u);
-            tc_fence_after();
-            const uint32_t* my_bits = s_bits + buf * bits_tile + ql;
-            const float* drow = reinterpret_cast<const float*>(P.desc + qc * P.dstride);
-            const bool fan_root = P.root_fan_off >= 0 && P.fan_mask != nullptr && (s_fm[buf * fm_tile + ql] & 1u);
-            float res = 0.f;
-            // ---- root: sum_c w_0[c] * Lambda_0[c] * T_0[c]
-            for (int c0 = 0; c0 < P.root_card; c0 += 8) {
-                float lv[8], w[8];
-                tmem_ld8(tlane + (uint32_t)(P.root_col + c0), lv);
-                weights8<FMT>(my_bits, P.bits_words, drow, P.root_lam_off, P.root_bit_off, P.root_card, c0, w);
-                tmem_ld_wait();
+                if (root) {
+                    // ---- the tile's result: sum_c w_0[c] * Lambda_0[c] * T_0[c], each group over its own columns
+                    const size_t q = (size_t)tile * kTile + ql;
+                    const size_t qc = q < P.nq ? q : P.nq - 1;
+                    const uint32_t buf = tile_iter & 1u;
+                    const uint32_t* my_bits = s_bits + buf * bits_tile + ql;
+                    const float* drow = reinterpret_cast<const float*>(P.desc + qc * P.dstride);
+                    const bool fan_root = P.root_fan_off >= 0 && P.fan_mask != nullptr && (s_fm[buf * fm_tile + ql] & 1u);
+                    float res = 0.f;
+                    if (regs) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (c0 + j < P.root_card) {
-                        float x = lv[j] * w[j];
-                        if (fan_root) x *= s_fan[P.root_fan_off + c0 + j];
-                        res = fmaf(x, __ldg(P.root_T + c0 + j), res);
+                        for (int r = 0; r < kAcc / 8; ++r) {
+                            const int c0 = lo + 8 * r;
+                            if (c0 < hi && c0 < P.root_card) {
+                                float w[8];
+                                weights8<FMT>(my_bits, P.bits_words, drow, P.root_lam_off, P.root_bit_off, P.root_card, c0, w);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j)
+                                    if (c0 + j < P.root_card) {
+                                        float x = acc[8 * r + j] * w[j];
+                                        if (fan_root) x *= s_fan[P.root_fan_off + c0 + j];
+                                        res = fmaf(x, __ldg(P.root_T + c0 + j), res);
+                                    }
+                            }
+                        }
+                    } else {
+                        tc_fence_after();
+                        for (int c0 = lo; c0 < hi && c0 < P.root_card; c0 += 8) {
+                            float lv[8], w[8];
+                            tmem_ld8(tlane + (uint32_t)(P.root_col + c0), lv);
+                            weights8<FMT>(my_bits, P.bits_words, drow, P.root_lam_off, P.root_bit_off, P.root_card, c0, w);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                if (c0 + j < P.root_card) {
+                                    float x = lv[j] * w[j];
+                                    if (fan_root) x *= s_fan[P.root_fan_off + c0 + j];
+                                    res = fmaf(x, __ldg(P.root_T + c0 + j), res);
+                                }
+                        }
                     }
-            }
-            if (q < P.nq) P.out[q] = res;
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(fin_done0);               // the node's columns may be overwritten by the next tile
-                mbar_arrive(bits_free0 + 8 * buf);    // this tile's BITS rows / mask words are no longer read
+                    if (mid < n8) {   // the upper half's share travels through shared memory (two tiles deep: the groups drift by at most one)
+                        if (g) s_part[buf * kTile + ql] = res;
+                        asm volatile("bar.sync 2, 256;" ::: "memory");
+                        if (!g) res += s_part[buf * kTile + ql];
+                    }
+                    if (!g && q < P.nq) P.out[q] = res;
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bits_free0 + 8 * buf);   // this tile's BITS rows / mask words are no longer read
+                }
             }
         }
     }
@@ -733,12 +803,15 @@ int k3_prepare(bc_model* m) {
     for (int v = 0; v < n; ++v)
         if (first_child_edge[v] >= 0) order.push_back(v);
     std::sort(order.begin(), order.end(), [&](int a, int b) { return first_child_edge[a] < first_child_edge[b]; });
-    // The ROOT's message is read by the finisher warps after the tile's last epilogue, while the other
-    // roles are already in the next tile: with `excl` its columns are reserved for the whole tile (nobody shares them);
-    // otherwise the epilogue of the first edge of a tile that writes into an overlapping range waits for the finisher
-    // (K3Edge::fin_guard) -- correct, but that wait sits at the start of the next tile.
-    const int fin_node = 0;
-    auto assign = [&](int a_stages, int n_dbuf, bool excl = true) -> int {   // columns used, or -1 (col[] is only written when every node found a place)
+    // Runs: maximal sequences of consecutive edges into the same parent; the epilogue warps keep the parent's message in
+    // registers over a run (domains of up to 2 x kAcc states).  The ROOT's message then never visits tensor memory unless its
+    // runs are interrupted (two internal children) or its domain is too large for the registers.
+    auto pa_of = [&](int e) { return (int)m->nodes[sched[e]].parent; };
+    int root_runs = 0;
+    for (int e = 0; e < n_edges; ++e)
+        if (pa_of(e) == 0 && (e == 0 || pa_of(e - 1) != 0)) ++root_runs;
+    const bool root_in_regs = bc_round_up(m->nodes[0].card, 16) <= 2 * kAcc && root_runs == 1;
+    auto assign = [&](int a_stages, int n_dbuf) -> int {   // columns used, or -1 (col[] is only written when every node found a place)
         std::vector<int> place(n, -1);
         const int units_total = 512 / 8;
         std::vector<int> busy_until(units_total, -1);   // last edge index that uses the unit
@@ -747,8 +820,9 @@ int k3_prepare(bc_model* m) {
         for (int u = 0; u < fixed_units; ++u) busy_until[u] = 1 << 30;
         int units_used = fixed_units;
         for (int v : order) {
+            if (v == 0 && root_in_regs) continue;
             const int need = (int)bc_round_up(m->nodes[v].card, 8) / 8;
-            const int start = (excl && v == fin_node) ? 0 : first_child_edge[v];
+            const int start = first_child_edge[v];
             const int end = own_edge[v] < 0 ? (1 << 30) : own_edge[v];   // (the root: to the end)
             int at = -1;
             for (int u0 = 0; u0 + need <= units_total && at < 0; ++u0) {
@@ -766,18 +840,17 @@ int k3_prepare(bc_model* m) {
         return units_used * 8;
     };
     // preference: a deep A ring and two accumulators; give up ring depth first, the second accumulator last
-    static const int kTry[][3] = {{4, 2, 1}, {3, 2, 1}, {4, 2, 0}, {3, 2, 0}, {2, 2, 1}, {2, 2, 0}, {4, 1, 1}, {4, 1, 0}, {3, 1, 0}, {2, 1, 0}};
+    static const int kTry[][2] = {{4, 2}, {3, 2}, {2, 2}, {4, 1}, {3, 1}, {2, 1}};
     int a_stages = 0, n_dbuf = 0;
     for (const auto& t : kTry)
-        if (assign(t[0], t[1], t[2] != 0) > 0) { a_stages = t[0]; n_dbuf = t[1]; break; }
+        if (assign(t[0], t[1]) > 0) { a_stages = t[0]; n_dbuf = t[1]; break; }
     if (const char* e = std::getenv("BC_K3_PLAN")) {   // experiments: "<a_stages>,<n_dbuf>"
         int wa = 0, wd = 0;
         if (std::sscanf(e, "%d,%d", &wa, &wd) == 2 && wa >= 2 && wa <= kMaxStages && (wd == 1 || wd == 2) && assign(wa, wd) > 0) {
             a_stages = wa;
             n_dbuf = wd;
         } else if (a_stages) {
-            for (const auto& t : kTry)
-                if (assign(t[0], t[1], t[2] != 0) > 0) break;
+            assign(a_stages, n_dbuf);
         }
     }
     if (!a_stages) return fail("live messages exceed the 512 columns of tensor memory");
@@ -811,18 +884,10 @@ int k3_prepare(bc_model* m) {
         E.nkb = (nd.card + kBK - 1) / kBK;
         E.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(E.n_pad >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
         E.publish = last_child_edge[nd.parent] != e ? -1 : (nd.parent == 0 ? -2 : own_edge[nd.parent]);
+        E.flags = ((e == 0 || pa_of(e - 1) != nd.parent) ? kRunFirst : 0) | ((e == n_edges - 1 || pa_of(e + 1) != nd.parent) ? kRunLast : 0) |
+                  (E.n_pad <= 2 * kAcc ? kRegs : 0);
         E.bimg_off = total;
         total += (size_t)E.nkb * E.n_pad * 128;
-    }
-    {   // the first edge of a tile whose epilogue writes into the columns the finisher warps read
-        const int f0 = col[fin_node], f1 = f0 + (int)bc_round_up(m->nodes[fin_node].card, 8);
-        for (K3Edge& E : k->edges) {
-            const int p0 = E.col_pa, p1 = p0 + (int)bc_round_up(E.N, 8);
-            if (E.first && p0 < f1 && f0 < p1) {
-                E.fin_guard = 1;
-                break;
-            }
-        }
     }
     std::vector<uint8_t> img(total, 0);
     for (const K3Edge& E : k->edges) {
@@ -851,7 +916,7 @@ int k3_prepare(bc_model* m) {
     // ---- shared memory: B ring (as deep as fits, at most 4), DENSE weight ring, BITS rows and fan-out mask words of two tiles
     const size_t fan_floats = (size_t)bc_round_up((int64_t)m->fan.size(), 4);
     const size_t per_fmt = std::max((size_t)kStagesW * kWBytes, (size_t)2 * m->bits_words * kTile * 4);
-    const size_t fixed = per_fmt + (size_t)2 * m->mask_words * kTile * 4 + fan_floats * 4 + 256 /* nibble table */ +
+    const size_t fixed = per_fmt + (size_t)2 * m->mask_words * kTile * 4 + fan_floats * 4 + 256 /* nibble table */ + 2 * kTile * 4 /* root partial sums */ +
                          8 * (4 * kMaxStages + 2 * kStagesW + 8 + kMaxEdges + 2) /* barriers, TMEM slot */ + 8 * kTraceSteps * 8 /* trace */ +
                          1024 /* alignment */;
     const size_t smem_optin = m->device >= 0 ? (size_t)m->smem_optin : (size_t)227 * 1024;   // host-only model: the sm_100 value

@@ -449,6 +449,11 @@ def test_fused_kernel_plan_invariants(name):
     for node, start in first_seen.items():
         end = n_edges if node == 0 or node == tail else own[node]
         width = -(-int(m.card[node]) // 8) * 8
+        if node == 0 and col_of[node] < 0:
+            # the root's message stays in the epilogue warps' registers: all edges into the root are consecutive
+            into_root = [e for e, v in enumerate(child) if parent[int(v)] == 0]
+            assert into_root == list(range(into_root[0], into_root[-1] + 1)) and int(m.card[0]) <= 96
+            continue
         spans.append((node, col_of[node], col_of[node] + width, start, end))
     for i, (a, a0, a1, as_, ae) in enumerate(spans):
         assert 0 <= a0 < a1 <= tmem_cols, (a, a0, a1)
