@@ -17,13 +17,13 @@
 //     port; with A in TENSOR memory it runs at the floor for every N >= 32;
 //   * tcgen05.ld moves ~190 B/clk/SM and neither slows the MMAs down nor is slowed by them.
 // Hence (round 2): the operand U_v is written by the producer warps straight into a ring of TENSOR-MEMORY columns
-// (tcgen05.st: hi and lo TF32 halves, 16 columns each per block of 16 child states) and read from there by the MMAs;
+// (tcgen05.st: hi and lo TF32 halves, 32 columns each per block of 32 child states) and read from there by the MMAs;
 // shared memory only carries T_v^T (TMA) and the staged query weights.
 //
 // Roles (576 threads, one CTA per SM, all 512 tensor-memory columns):
 //   * warps 0-3 / 4-7  TWO PRODUCER GROUPS (thread = query = TMEM lane) build alternate blocks: weights from the BITS tile
 //     in shared memory or, for DENSE_F32 rows, from a shared-memory ring that the TMA warp fills with 2-D tensor-map loads
-//     (128 queries x 16 floats, 64-byte swizzle) -- no global-memory latency in the loop; times the fan-out vector, times
+//     (128 queries x 32 floats, 128-byte swizzle) -- no global-memory latency in the loop; times the fan-out vector, times
 //     Lambda_v (tcgen05.ld) for an internal node; split into TF32 hi (round to nearest) and lo = x - hi; tcgen05.st into the
 //     A ring; one mbarrier arrive per warp;
 //   * warps 8-11 / 14-17  TWO EPILOGUE GROUPS, each owning one half of the parent's columns: over a run of consecutive edges
@@ -58,7 +58,7 @@ struct K3Edge {            // 64 bytes, in the kernel parameter bank
     int32_t col_v;         // TMEM column of Lambda_v, -1 for a leaf
     int32_t col_pa;        // TMEM column of Lambda_pa
     int32_t first;         // this edge is the first message into Lambda_pa
-    int32_t nkb;           // blocks of 16 child states
+    int32_t nkb;           // blocks of 32 child states
     uint32_t idesc;        // tcgen05 instruction descriptor (M = 128, N = n_pad, TF32 x TF32 -> F32, K-major)
     uint64_t bimg_off;     // byte offset of the edge's operand images
     int32_t publish;       // >= 0: this edge is the LAST message into Lambda_pa, pa's own edge is `publish` (its producers may
@@ -76,7 +76,7 @@ struct BcK3Plan {
     size_t bimg_bytes = 0;
     int npad_max = 16;
     int tmem_cols = 512;
-    int a_col = 0, a_stages = 4;   // A ring: a_stages x 32 columns (16 hi + 16 lo)
+    int a_col = 0, a_stages = 2;   // A ring: a_stages x 64 columns (32 hi + 32 lo)
     int d_col = 0, n_dbuf = 2;
     int b_stages = 4;
     int root_col = 0;
@@ -89,8 +89,8 @@ namespace {
 
 constexpr int kTile = 128;     // queries per CTA tile = TMEM lanes = UMMA M
 constexpr int kMaxEdges = 127; // trees of up to 128 columns
-constexpr int kBK = 16;        // child states per ring step
-constexpr int kStagesW = 8;    // DENSE weight ring (8 KB per slot): deep, the loads come from HBM
+constexpr int kBK = 32;        // child states per ring step: one 128-byte row of T_v^T / of the weight box (128-byte swizzle), 4 k-steps of 8
+constexpr int kStagesW = 4;    // DENSE weight ring (16 KB per slot): the loads come from HBM
 constexpr int kWBytes = kTile * kBK * 4;
 constexpr int kGroups = 2;     // producer groups of four warps, alternate blocks
 constexpr int kWarpEpi = 4 * kGroups, kWarpMma = kWarpEpi + 4, kWarpTma = kWarpMma + 1, kWarpEpiB = kWarpTma + 1;
@@ -118,7 +118,7 @@ struct K3Params {
     size_t nq;
     long long n_tiles;
     int bits_words;
-    int b_slot_bytes;          // 2 * npad_max * 64
+    int b_slot_bytes;          // 2 * npad_max * 128
     int a_col, a_stages, b_stages;
     int d_col, d_stride, n_dbuf;
     int mask_words;            // fan-out mask words per query
@@ -177,7 +177,7 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
         : "memory");
 }
-// D[tmem] (+)= A[tmem: 128 lanes x 8 columns] . B[smem, K-major, 64-byte swizzle: rows of 64 B, 8-row groups 512 B apart (SBO),
+// D[tmem] (+)= A[tmem: 128 lanes x 8 columns] . B[smem, K-major, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO),
 // layout type 4, version 1 (sm_100)].  Called by the WHOLE (converged) issuer warp; elect.sync inside picks the lane, so ptxas
 // keeps every operand in uniform registers instead of wrapping each instruction in a divergence loop.
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_c, uint32_t tmem_a, uint32_t b_lo32, uint32_t desc_hi32, uint32_t idesc,
@@ -266,6 +266,15 @@ __device__ __forceinline__ uint32_t bits16(const uint32_t* my_bits, int bits_wor
     const uint32_t w1 = my_bits[(idx + 1 < bits_words ? idx + 1 : idx) * kTile];
     const int valid = card - c0;
     return __funnelshift_r(w0, w1, sh) & (valid >= 16 ? 0xFFFFu : ((1u << valid) - 1u));
+}
+
+// ... of states [c0, c0 + 32)
+__device__ __forceinline__ uint32_t bits32(const uint32_t* my_bits, int bits_words, int bit_off, int card, int c0) {
+    const int b0 = bit_off + c0, idx = b0 >> 5, sh = b0 & 31;
+    const uint32_t w0 = my_bits[idx * kTile];
+    const uint32_t w1 = my_bits[(idx + 1 < bits_words ? idx + 1 : idx) * kTile];
+    const int valid = card - c0;
+    return __funnelshift_r(w0, w1, sh) & (valid >= 32 ? 0xFFFFFFFFu : ((1u << valid) - 1u));
 }
 
 // weights of 8 consecutive states [c0, c0 + 8) of a column for this thread's query (the root's dot product)
@@ -365,7 +374,7 @@ __global__ void __launch_bounds__(kThreads, 1) k3_kernel(const __grid_constant__
             for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x)
                 for (int e = 0; e < P.n_edges; ++e) {
                     const K3Edge& E = P.edge[e];
-                    const unsigned bytes = (unsigned)E.n_pad * 128u;   // hi + lo, 64 B per row each
+                    const unsigned bytes = (unsigned)E.n_pad * 256u;   // hi + lo, 128 B per row each
                     for (int kb = 0; kb < E.nkb; ++kb) {
                         if (FMT == BC_DESC_DENSE_F32) {
                             mbar_wait(w_empty0 + 8 * rw.s, rw.par ^ 1u);
@@ -387,7 +396,7 @@ __global__ void __launch_bounds__(kThreads, 1) k3_kernel(const __grid_constant__
         Ring ra, rb;
         uint32_t ed = 0, tile_iter = 0;   // edge counter (D buffer = ed % n_dbuf)
         const uint32_t SA = (uint32_t)P.a_stages, SB = (uint32_t)P.b_stages, b_slot = (uint32_t)P.b_slot_bytes;
-        const uint32_t desc_hi = (uint32_t)(512 >> 4) | (1u << 14) | (4u << 29);   // SBO, version 1, 64-byte swizzle
+        const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO (8 rows of 128 B), version 1, 128-byte swizzle
         const uint32_t a_base = tmem + (uint32_t)P.a_col, b_base = (((b_ring & 0x3FFFFu) >> 4) | (1u << 16));
         for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tile_iter)
             for (int e = 0; e < P.n_edges; ++e, ++ed) {
@@ -395,32 +404,34 @@ __global__ void __launch_bounds__(kThreads, 1) k3_kernel(const __grid_constant__
                 const bool a_exact = FMT == BC_DESC_BITS && E.col_v < 0 && !(E.fan_off >= 0 && P.fan_mask != nullptr);
                 const uint32_t db = P.n_dbuf == 2 ? (ed & 1u) : 0u, dpar = (P.n_dbuf == 2 ? (ed >> 1) : ed) & 1u;
                 const uint32_t d = tmem + (uint32_t)(P.d_col + (int)db * P.d_stride);
-                const uint32_t idesc = E.idesc, b_lo_off = (uint32_t)E.n_pad * 4u;   // n_pad * 64 B in 16-byte units
+                const uint32_t idesc = E.idesc, b_lo_off = (uint32_t)E.n_pad * 8u;   // n_pad * 128 B in 16-byte units
                 const int K = E.K, nkb = E.nkb;
                 mbar_wait(d_empty0 + 8 * db, dpar ^ 1u);   // the epilogue of the edge that used this accumulator is done
                 K3_STAMP(0, e, 0);
                 for (int kb = 0; kb < nkb; ++kb) {
-                    const uint32_t a_hi = a_base + ra.s * 32u, a_lo = a_hi + 16u;
+                    const uint32_t a_hi = a_base + ra.s * 64u, a_lo = a_hi + 32u;
                     // low word of the B descriptors: start address >> 4 | LBO = 1
                     const uint32_t b_hi = b_base + ((rb.s * b_slot) >> 4), b_lo = b_hi + b_lo_off;
-                    const bool two = K - kb * kBK > 8;
+                    const int ks = min(4, (K - kb * kBK + 7) >> 3);   // k-steps of 8 states with anything in them
                     mbar_wait(b_full0 + 8 * rb.s, rb.par);
                     mbar_wait(a_full0 + 8 * ra.s, ra.par);
                     tc_fence_after();
                     // error-compensated product, the small terms first; a k-step is 8 TF32: 8 columns of A, 32 bytes (+2) of B
                     if (!a_exact) {
-                        umma_tf32_ts(d, a_lo, b_hi, desc_hi, idesc, kb != 0);
-                        umma_tf32_ts(d, a_hi, b_lo, desc_hi, idesc, 1);
-                        if (two) {
-                            umma_tf32_ts(d, a_lo + 8, b_hi + 2, desc_hi, idesc, 1);
-                            umma_tf32_ts(d, a_hi + 8, b_lo + 2, desc_hi, idesc, 1);
-                        }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (k < ks) {
+                                umma_tf32_ts(d, a_lo + 8u * k, b_hi + 2u * k, desc_hi, idesc, kb != 0 || k != 0);
+                                umma_tf32_ts(d, a_hi + 8u * k, b_lo + 2u * k, desc_hi, idesc, 1);
+                            }
                     } else {
-                        umma_tf32_ts(d, a_hi, b_lo, desc_hi, idesc, kb != 0);
-                        if (two) umma_tf32_ts(d, a_hi + 8, b_lo + 2, desc_hi, idesc, 1);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (k < ks) umma_tf32_ts(d, a_hi + 8u * k, b_lo + 2u * k, desc_hi, idesc, kb != 0 || k != 0);
                     }
-                    umma_tf32_ts(d, a_hi, b_hi, desc_hi, idesc, 1);
-                    if (two) umma_tf32_ts(d, a_hi + 8, b_hi + 2, desc_hi, idesc, 1);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (k < ks) umma_tf32_ts(d, a_hi + 8u * k, b_hi + 2u * k, desc_hi, idesc, 1);
                     umma_commit(a_empty0 + 8 * ra.s);
                     umma_commit(b_empty0 + 8 * rb.s);
                     if (kb == nkb - 1) umma_commit(d_full0 + 8 * db);
@@ -433,7 +444,7 @@ __global__ void __launch_bounds__(kThreads, 1) k3_kernel(const __grid_constant__
         // ================= producer warps: thread = query = TMEM lane; group g builds the blocks with (step & 1) == g
         const int g = warp >> 2, ql = tid & (kTile - 1);
         const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-        const uint32_t sw = ((uint32_t)ql >> 1) & 3u;    // 64-byte swizzle: chunk j of row r lives at r * 64 + ((j ^ ((r >> 1) & 3)) << 4)
+        const uint32_t sw = (uint32_t)ql & 7u;    // 128-byte swizzle: chunk j of row r lives at r * 128 + ((j ^ (r & 7)) << 4)
         Ring ra, rw;
         uint32_t it = 0, tile_iter = 0;
         for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tile_iter) {
@@ -474,19 +485,19 @@ __global__ void __launch_bounds__(kThreads, 1) k3_kernel(const __grid_constant__
                     if ((it & 1u) != (uint32_t)g) continue;
                     const int c0 = kb * kBK;
                     if ((warp & 3) == 0) K3_STEP(0);
-                    float u[16];
+                    float u[kBK];
                     if (FMT == BC_DESC_BITS) {
-                        const uint32_t m = bits16(my_bits, P.bits_words, E.bit_off, K, c0);
+                        const uint32_t m = bits32(my_bits, P.bits_words, E.bit_off, K, c0);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
+                        for (int j = 0; j < 8; ++j) {
                             const float4 t = s_tab[(m >> (4 * j)) & 15u];
                             u[4 * j] = t.x; u[4 * j + 1] = t.y; u[4 * j + 2] = t.z; u[4 * j + 3] = t.w;
                         }
                     } else {
                         mbar_wait(w_full0 + 8 * rw.s, rw.par);
-                        const uint8_t* row = w_ring_ptr + rw.s * kWBytes + ql * 64;
+                        const uint8_t* row = w_ring_ptr + rw.s * kWBytes + ql * 128;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
+                        for (int j = 0; j < 8; ++j) {
                             const float4 t = *reinterpret_cast<const float4*>(row + (((uint32_t)j ^ sw) << 4));
                             u[4 * j] = t.x; u[4 * j + 1] = t.y; u[4 * j + 2] = t.z; u[4 * j + 3] = t.w;
                         }
@@ -495,47 +506,57 @@ __global__ void __launch_bounds__(kThreads, 1) k3_kernel(const __grid_constant__
                     }
                     if (fan_on) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
+                        for (int j = 0; j < 8; ++j)
                             if (c0 + 4 * j < K) {
                                 const float4 f = *reinterpret_cast<const float4*>(s_fan + E.fan_off + c0 + 4 * j);
                                 u[4 * j] *= f.x; u[4 * j + 1] *= f.y; u[4 * j + 2] *= f.z; u[4 * j + 3] *= f.w;
                             }
                     }
                     if ((warp & 3) == 0) K3_STEP(1);
-                    if (!leaf) {
-                        float lv[16];
-                        tmem_ld8(tlane + (uint32_t)(E.col_v + c0), lv);
-                        if (K - c0 > 8) tmem_ld8(tlane + (uint32_t)(E.col_v + c0 + 8), lv + 8);
-                        else {
+                    if (!leaf) {   // times Lambda_v, 16 columns per round trip (the node's columns are allocated in units of 8: never read past them)
 #pragma unroll
-                            for (int j = 8; j < 16; ++j) lv[j] = 0.f;
+                        for (int hs = 0; hs < 2; ++hs) {
+                            const int c = c0 + 16 * hs;
+                            if (c < K) {
+                                float lv[16];
+                                if (c + 8 < K) tmem_ld16(tlane + (uint32_t)(E.col_v + c), lv);
+                                else {
+                                    tmem_ld8(tlane + (uint32_t)(E.col_v + c), lv);
+#pragma unroll
+                                    for (int j = 8; j < 16; ++j) lv[j] = 0.f;
+                                }
+                                tmem_ld_wait();
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) u[16 * hs + j] *= lv[j];
+                            }
                         }
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) u[j] *= lv[j];
                     }
                     if (c0 + kBK > K) {   // last block: states >= K must be exact zeros (stale Lambda columns, row padding, the next column's weights)
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
+                        for (int j = 0; j < kBK; ++j)
                             if (c0 + j >= K) u[j] = 0.f;
                     }
-                    const uint32_t a_hi = tlane + (uint32_t)(P.a_col + (int)ra.s * 32);
+                    const uint32_t a_hi = tlane + (uint32_t)(P.a_col + (int)ra.s * 64);
                     if ((warp & 3) == 0) K3_STEP(2);
                     if (a_exact) {
                         // unit weights on a leaf: U is a 0/1 matrix, exact in TF32 -- no lo half
                         mbar_wait(a_empty0 + 8 * ra.s, ra.par ^ 1u);   // the MMAs that read this slot are done
                         if ((warp & 3) == 0) K3_STEP(3);
                         tc_fence_after();
-                        tmem_st16(a_hi, u);
+                        tmem_st32(a_hi, u);
                     } else {
-                        float h[16], l[16];
+                        float l[kBK];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) split_tf32(u[j], h[j], l[j]);
+                        for (int j = 0; j < kBK; ++j) {
+                            float h;
+                            split_tf32(u[j], h, l[j]);
+                            u[j] = h;
+                        }
                         mbar_wait(a_empty0 + 8 * ra.s, ra.par ^ 1u);
                         if ((warp & 3) == 0) K3_STEP(3);
                         tc_fence_after();
-                        tmem_st16(a_hi, h);
-                        tmem_st16(a_hi + 16u, l);
+                        tmem_st32(a_hi, u);
+                        tmem_st32(a_hi + 32u, l);
                     }
                     tmem_st_wait();
                     tc_fence_before();
@@ -594,16 +615,23 @@ __global__ void __launch_bounds__(kThreads, 1) k3_kernel(const __grid_constant__
                             }
                         }
                     }
-                    if (!(run_first && first)) {
+                    if (!(run_first && first)) {   // a TMEM read round trip costs ~150 clk under load whatever its size: 24 columns per wait
 #pragma unroll
-                        for (int r = 0; r < kAcc / 8; ++r) {
-                            const int j = lo + 8 * r;
+                        for (int r = 0; r < kAcc / 24; ++r) {
+                            const int j = lo + 24 * r;
                             if (j < hi) {
-                                float dv[8];
-                                tmem_ld8(dcol + (uint32_t)j, dv);
+                                float dv[24];
+#pragma unroll
+                                for (int c = 0; c < 3; ++c) {
+                                    if (j + 8 * c < hi) tmem_ld8(dcol + (uint32_t)(j + 8 * c), dv + 8 * c);
+                                    else {
+#pragma unroll
+                                        for (int i = 0; i < 8; ++i) dv[8 * c + i] = 1.f;
+                                    }
+                                }
                                 tmem_ld_wait();
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) acc[8 * r + i] *= dv[i] * debias;
+                                for (int i = 0; i < 24; ++i) acc[24 * r + i] *= dv[i] * debias;
                             }
                         }
                     }
@@ -792,7 +820,7 @@ int k3_prepare(bc_model* m) {
         if (np > 256) return fail("a parent domain exceeds 256 states");
         if (np > npad_max) npad_max = np;
     }
-    // ---- TMEM columns (one CTA per SM owns all 512): [A ring: a_stages x 32][accumulators: n_dbuf x npad_max][Lambda of
+    // ---- TMEM columns (one CTA per SM owns all 512): [A ring: a_stages x 64][accumulators: n_dbuf x npad_max][Lambda of
     //      every internal node by first fit over lifetimes [edge of its first child, its own edge] (the root lives to the
     //      end), in units of 8 columns].  Lifetimes may be reused back to back although the roles run at different places
     //      of the step sequence: a node's columns are first WRITTEN by the epilogue of its first child's edge, which follows
@@ -815,7 +843,7 @@ int k3_prepare(bc_model* m) {
         std::vector<int> place(n, -1);
         const int units_total = 512 / 8;
         std::vector<int> busy_until(units_total, -1);   // last edge index that uses the unit
-        const int fixed_units = (a_stages * 32 + n_dbuf * npad_max) / 8;
+        const int fixed_units = (a_stages * 64 + n_dbuf * npad_max) / 8;
         if (fixed_units > units_total) return -1;
         for (int u = 0; u < fixed_units; ++u) busy_until[u] = 1 << 30;
         int units_used = fixed_units;
@@ -840,7 +868,7 @@ int k3_prepare(bc_model* m) {
         return units_used * 8;
     };
     // preference: a deep A ring and two accumulators; give up ring depth first, the second accumulator last
-    static const int kTry[][2] = {{4, 2}, {3, 2}, {2, 2}, {4, 1}, {3, 1}, {2, 1}};
+    static const int kTry[][2] = {{3, 2}, {2, 2}, {3, 1}, {2, 1}};
     int a_stages = 0, n_dbuf = 0;
     for (const auto& t : kTry)
         if (assign(t[0], t[1]) > 0) { a_stages = t[0]; n_dbuf = t[1]; break; }
@@ -858,10 +886,10 @@ int k3_prepare(bc_model* m) {
     k->npad_max = npad_max;
     k->a_col = 0;
     k->a_stages = a_stages;
-    k->d_col = a_stages * 32;
+    k->d_col = a_stages * 64;
     k->n_dbuf = n_dbuf;
     k->root_col = col[0];
-    // ---- operand images: per edge and block of 16 child states, T_v^T hi then lo, 64-byte swizzled rows
+    // ---- operand images: per edge and block of 32 child states, T_v^T hi then lo, 128-byte swizzled rows
     size_t total = 0;
     k->edges.resize(n_edges);
     std::vector<int> last_child_edge(n, -1);
@@ -887,15 +915,15 @@ int k3_prepare(bc_model* m) {
         E.flags = ((e == 0 || pa_of(e - 1) != nd.parent) ? kRunFirst : 0) | ((e == n_edges - 1 || pa_of(e + 1) != nd.parent) ? kRunLast : 0) |
                   (E.n_pad <= 2 * kAcc ? kRegs : 0);
         E.bimg_off = total;
-        total += (size_t)E.nkb * E.n_pad * 128;
+        total += (size_t)E.nkb * E.n_pad * 256;
     }
     std::vector<uint8_t> img(total, 0);
     for (const K3Edge& E : k->edges) {
         const BcNodeRec& nd = m->nodes[E.v];
         const float* T = m->arena.data() + nd.cpt_off;
         for (int kb = 0; kb < E.nkb; ++kb) {
-            uint8_t* hi = img.data() + E.bimg_off + (size_t)kb * E.n_pad * 128;
-            uint8_t* lo = hi + (size_t)E.n_pad * 64;
+            uint8_t* hi = img.data() + E.bimg_off + (size_t)kb * E.n_pad * 256;
+            uint8_t* lo = hi + (size_t)E.n_pad * 128;
             for (int p = 0; p < E.N; ++p)
                 for (int kk = 0; kk < kBK; ++kk) {
                     const int c = kb * kBK + kk;
@@ -906,7 +934,7 @@ int k3_prepare(bc_model* m) {
                     std::memcpy(&h, &hb, 4);
                     const float l = x - h;
                     const uint32_t lb = host_tf32_hi(l);
-                    const size_t off = (size_t)p * 64 + ((size_t)((kk >> 2) ^ ((p >> 1) & 3)) << 4) + (size_t)(kk & 3) * 4;
+                    const size_t off = (size_t)p * 128 + ((size_t)((kk >> 2) ^ (p & 7)) << 4) + (size_t)(kk & 3) * 4;   // 128-byte swizzle
                     std::memcpy(hi + off, &hb, 4);
                     std::memcpy(lo + off, &lb, 4);
                 }
@@ -922,10 +950,10 @@ int k3_prepare(bc_model* m) {
     const size_t smem_optin = m->device >= 0 ? (size_t)m->smem_optin : (size_t)227 * 1024;   // host-only model: the sm_100 value
     int b_stages = kMaxStages;
     if (const char* e = std::getenv("BC_K3_BSTAGES")) b_stages = std::max(2, std::min(kMaxStages, std::atoi(e)));
-    while (b_stages > 1 && (size_t)b_stages * npad_max * 128 + fixed > smem_optin) --b_stages;
-    if ((size_t)b_stages * npad_max * 128 + fixed > smem_optin || b_stages < 2) return fail("operand rings exceed shared memory");
+    while (b_stages > 1 && (size_t)b_stages * npad_max * 256 + fixed > smem_optin) --b_stages;
+    if ((size_t)b_stages * npad_max * 256 + fixed > smem_optin || b_stages < 2) return fail("operand rings exceed shared memory");
     k->b_stages = b_stages;
-    k->smem = (size_t)b_stages * npad_max * 128 + fixed;
+    k->smem = (size_t)b_stages * npad_max * 256 + fixed;
     k->ctas_per_sm = 1;
     if (m->device >= 0) {   // (a host-only model keeps the plan for inspection: bc_model_fused_plan)
         cudaDriverEntryPointQueryResult qr;
@@ -1000,7 +1028,7 @@ int bc_k3_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32
     P.nq = nq;
     P.n_tiles = (long long)((nq + kTile - 1) / kTile);
     P.bits_words = m->bits_words;
-    P.b_slot_bytes = k->npad_max * 128;
+    P.b_slot_bytes = k->npad_max * 256;
     P.a_col = k->a_col;
     P.a_stages = k->a_stages;
     P.b_stages = k->b_stages;
@@ -1051,14 +1079,14 @@ int bc_k3_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32
     CUtensorMap tm_w;
     std::memset(&tm_w, 0, sizeof(tm_w));
     if (fmt == BC_DESC_DENSE_F32) {
-        // DENSE_F32 rows as a 2-D tensor [nq rows x lam_total floats]; one box = 128 queries x 16 states, 64-byte swizzle (the
+        // DENSE_F32 rows as a 2-D tensor [nq rows x lam_total floats]; one box = 128 queries x 32 states, 128-byte swizzle (the
         // producers read their own row conflict free); rows past the batch and columns past the row read as zeros
         const cuuint64_t dims[2] = {(cuuint64_t)m->lam_total, (cuuint64_t)nq};
         const cuuint64_t strides[1] = {(cuuint64_t)m->lam_total * 4};
         const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)kTile};
         const cuuint32_t estr[2] = {1, 1};
         const CUresult cr = reinterpret_cast<EncodeTiledFn>(k->encode)(&tm_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(desc), dims, strides,
-                                                                       box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                                                                       box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                                                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) {
             bc_set_error("cuTensorMapEncodeTiled failed (%d) for %zu DENSE_F32 rows of %d floats", (int)cr, nq, m->lam_total);

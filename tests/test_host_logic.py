@@ -425,7 +425,7 @@ def test_fused_kernel_plan_invariants(name):
     n_edges, tmem_cols, ctas, smem, d_col, d_cols, root_col, _ = (int(x) for x in info)
     tail = None
     assert n_edges == m.n_nodes - 1 - (tail is not None) and tmem_cols == 512 and ctas == 1 and smem <= 227 * 1024
-    assert d_col in (64, 96, 128) and d_col % 32 == 0    # the A ring (2-4 stages of 16 hi + 16 lo columns) sits below the accumulators
+    assert d_col in (128, 192)    # the A ring (2-3 stages of 32 hi + 32 lo columns) sits below the accumulators
     child = edges[:, 0]
     assert sorted(child.tolist()) == [v for v in range(1, m.n_nodes) if v != tail]
     own = {int(v): e for e, v in enumerate(child)}
@@ -433,7 +433,7 @@ def test_fused_kernel_plan_invariants(name):
     first_seen = {}
     for e, (v, K, N, n_pad, col_v, col_pa, first, nkb) in enumerate(edges.tolist()):
         pa = parent[v]
-        assert K == int(m.card[v]) and N == int(m.card[pa]) and n_pad == -(-N // 16) * 16 and nkb == -(-K // 16)
+        assert K == int(m.card[v]) and N == int(m.card[pa]) and n_pad == -(-N // 16) * 16 and nkb == -(-K // 32)
         assert pa == 0 or pa == tail or own[pa] > e        # children before parents
         assert bool(first) == (pa not in first_seen)       # the first message overwrites, the others multiply
         first_seen.setdefault(pa, e)
