@@ -72,13 +72,15 @@ static_assert(sizeof(K3Edge) == 64, "K3Edge layout");
 struct BcK3Plan {
     int failed = 0;
     std::vector<K3Edge> edges;
+    std::vector<uint8_t> seq;      // step sequence of one pass (K3Params::seq)
+    int n_tail = 0;
     uint8_t* d_bimg = nullptr;
     size_t bimg_bytes = 0;
     int npad_max = 16;
     int tmem_cols = 512;
     int a_col = 0, a_stages = 2;   // A ring: a_stages x 64 columns (32 hi + 32 lo)
     int d_col = 0, n_dbuf = 2;
-    int b_stages = 4;
+    int b_stages = 4, w_stages = 4;
     int root_col = 0;
     int ctas_per_sm = 1;
     size_t smem = 0;
@@ -90,7 +92,7 @@ namespace {
 constexpr int kTile = 128;     // queries per CTA tile = TMEM lanes = UMMA M
 constexpr int kMaxEdges = 127; // trees of up to 128 columns
 constexpr int kBK = 32;        // child states per ring step: one 128-byte row of T_v^T / of the weight box (128-byte swizzle), 4 k-steps of 8
-constexpr int kStagesW = 4;    // DENSE weight ring (16 KB per slot): the loads come from HBM
+constexpr int kStagesW = 8;    // DENSE weight ring: at most this many slots of 16 KB (K3Params::w_stages are used; the loads come from HBM)
 constexpr int kWBytes = kTile * kBK * 4;
 constexpr int kGroups = 2;     // producer groups of four warps, alternate blocks
 constexpr int kWarpEpi = 4 * kGroups, kWarpMma = kWarpEpi + 4, kWarpTma = kWarpMma + 1, kWarpEpiB = kWarpTma + 1;
@@ -105,6 +107,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 struct K3Params {
     K3Edge edge[kMaxEdges];    // in the kernel parameter bank (8 KB of the 32 KB sm_100 allows): uniform loads, warp-uniform control flow
     int n_edges;
+    // the step sequence of one pass: entry = edge index | 0x80 for a TAIL edge, which belongs to the PREVIOUS tile of this CTA
+    // (the chain at the top of the tree is folded under the next tile's leaves; see k3_prepare)
+    uint8_t seq[kMaxEdges + 1];
+    int n_seq, n_tail;
     const uint8_t* bimg;
     const uint8_t* desc;
     size_t dstride;
@@ -119,7 +125,7 @@ struct K3Params {
     long long n_tiles;
     int bits_words;
     int b_slot_bytes;          // 2 * npad_max * 128
-    int a_col, a_stages, b_stages;
+    int a_col, a_stages, b_stages, w_stages;
     int d_col, d_stride, n_dbuf;
     int mask_words;            // fan-out mask words per query
     float debias_unit;         // optional correction of the accumulator's truncation (BC_K3_DEBIAS, 0 = off = default)
@@ -159,11 +165,19 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, unsigned bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// (with the default time limit a failed try_wait comes back after ~50 clk and the spin loops of the 18 warps are 21 % of all
+//  issued instructions -- ncu, profiles/r2_ncu_29_k3_bits_imdb1.json; with a suspend-time hint ptxas emits NANOSLEEP.SYNCS and the
+//  spinning stops.  Measured: no change in throughput for hints of 100 ns ... 20 us -- the spinning warps only took issue slots
+//  nobody else wanted -- so this is about power, not speed)
+#ifndef BC_K3_SUSPEND_NS
+#define BC_K3_SUSPEND_NS 500
+#endif
+constexpr unsigned kSuspendNs = BC_K3_SUSPEND_NS;
 __device__ __forceinline__ void mbar_wait(uint32_t bar, unsigned parity) {
     asm volatile(
         "{\n.reg .pred p;\nWAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(bar), "r"(parity)
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(bar), "r"(parity), "r"(kSuspendNs)
         : "memory");
 }
 __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, unsigned bytes, uint32_t bar) {
@@ -296,6 +310,20 @@ __device__ __forceinline__ void weights8(const uint32_t* my_bits, int bits_words
     }
 }
 
+// Every role walks the same static sequence of (edge, tile) steps: pass `iter` of a CTA runs the body edges of its tile number
+// `iter` interleaved with the TAIL edges (K3Params::seq) of tile `iter - 1`; one extra pass drains the last tile's tail.
+#define K3_PASS_HEAD                                                                  \
+    const long long tile_cur = (long long)blockIdx.x + (long long)iter * gridDim.x;   \
+    const bool cur_ok = tile_cur < P.n_tiles;                                         \
+    if (!cur_ok && (iter == 0 || P.n_tail == 0)) break;
+#define K3_STEP_HEAD                                                                  \
+    const int e = P.seq[si] & 127;                                                    \
+    const bool back = (P.seq[si] & 128) != 0;                                         \
+    if (back ? iter == 0 : !cur_ok) continue;                                         \
+    const long long tile = back ? tile_cur - (long long)gridDim.x : tile_cur;         \
+    const uint32_t tile_iter = back ? iter - 1u : iter;                               \
+    (void)tile; (void)tile_iter;
+
 struct Ring {   // slot / parity cursor of a ring of `n` slots advanced once per step
     uint32_t s = 0, par = 0;
     __device__ __forceinline__ void next(uint32_t n) {
@@ -315,7 +343,7 @@ __global__ void __launch_bounds__(kThreads, 1) k3_kernel(const __grid_constant__
     p += (size_t)P.b_stages * P.b_slot_bytes;
     const uint32_t w_ring = smem_u32(p);
     const uint8_t* w_ring_ptr = p;
-    p += (FMT == BC_DESC_DENSE_F32 ? (size_t)kStagesW * kWBytes : 0);
+    p += (FMT == BC_DESC_DENSE_F32 ? (size_t)P.w_stages * kWBytes : 0);
     uint32_t* s_bits = reinterpret_cast<uint32_t*>(p);
     const size_t bits_tile = (FMT == BC_DESC_BITS ? (size_t)P.bits_words * kTile : 0);
     p += 2 * bits_tile * 4;
@@ -371,8 +399,10 @@ __global__ void __launch_bounds__(kThreads, 1) k3_kernel(const __grid_constant__
         // ================= TMA warp: keeps the B ring (and the DENSE weight ring) full; the step sequence is static
         if (lane == 0) {
             Ring rb, rw;
-            for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x)
-                for (int e = 0; e < P.n_edges; ++e) {
+            for (uint32_t iter = 0;; ++iter) {
+                K3_PASS_HEAD
+                for (int si = 0; si < P.n_seq; ++si) {
+                    K3_STEP_HEAD
                     const K3Edge& E = P.edge[e];
                     const unsigned bytes = (unsigned)E.n_pad * 256u;   // hi + lo, 128 B per row each
                     for (int kb = 0; kb < E.nkb; ++kb) {
@@ -380,7 +410,7 @@ __global__ void __launch_bounds__(kThreads, 1) k3_kernel(const __grid_constant__
                             mbar_wait(w_empty0 + 8 * rw.s, rw.par ^ 1u);
                             mbar_expect_tx(w_full0 + 8 * rw.s, kWBytes);
                             tma_load_2d(w_ring + rw.s * kWBytes, &tm_w, E.lam_off + kb * kBK, (int)(tile * kTile), w_full0 + 8 * rw.s);
-                            rw.next(kStagesW);
+                            rw.next(P.w_stages);
                         }
                         mbar_wait(b_empty0 + 8 * rb.s, rb.par ^ 1u);
                         mbar_expect_tx(b_full0 + 8 * rb.s, bytes);
@@ -388,21 +418,26 @@ __global__ void __launch_bounds__(kThreads, 1) k3_kernel(const __grid_constant__
                         rb.next(P.b_stages);
                     }
                 }
+                if (!cur_ok) break;
+            }
         }
     } else if (warp == kWarpMma) {
         // ================= MMA issuer warp: the whole warp runs the (uniform) loop, one elected lane issues.  (The issue
         // queue is deep and neither the commits nor the fence stall it -- tools/microbench/umma_issue.cu -- but this warp
         // shares its scheduler with three busy warps: every instruction of this loop costs the tensor pipe time.)
         Ring ra, rb;
-        uint32_t ed = 0, tile_iter = 0;   // edge counter (D buffer = ed % n_dbuf)
+        uint32_t ed = 0;   // step counter (D buffer = ed % n_dbuf)
         const uint32_t SA = (uint32_t)P.a_stages, SB = (uint32_t)P.b_stages, b_slot = (uint32_t)P.b_slot_bytes;
         const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO (8 rows of 128 B), version 1, 128-byte swizzle
         const uint32_t a_base = tmem + (uint32_t)P.a_col, b_base = (((b_ring & 0x3FFFFu) >> 4) | (1u << 16));
-        for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tile_iter)
-            for (int e = 0; e < P.n_edges; ++e, ++ed) {
+        for (uint32_t iter = 0;; ++iter) {
+            K3_PASS_HEAD
+            for (int si = 0; si < P.n_seq; ++si) {
+                K3_STEP_HEAD
                 const K3Edge& E = P.edge[e];
                 const bool a_exact = FMT == BC_DESC_BITS && E.col_v < 0 && !(E.fan_off >= 0 && P.fan_mask != nullptr);
                 const uint32_t db = P.n_dbuf == 2 ? (ed & 1u) : 0u, dpar = (P.n_dbuf == 2 ? (ed >> 1) : ed) & 1u;
+                ++ed;   // (executed steps only)
                 const uint32_t d = tmem + (uint32_t)(P.d_col + (int)db * P.d_stride);
                 const uint32_t idesc = E.idesc, b_lo_off = (uint32_t)E.n_pad * 8u;   // n_pad * 128 B in 16-byte units
                 const int K = E.K, nkb = E.nkb;
@@ -440,38 +475,45 @@ __global__ void __launch_bounds__(kThreads, 1) k3_kernel(const __grid_constant__
                 }
                 K3_STAMP(0, e, 1);
             }
+            if (!cur_ok) break;
+        }
     } else if (warp < kWarpEpi) {
         // ================= producer warps: thread = query = TMEM lane; group g builds the blocks with (step & 1) == g
         const int g = warp >> 2, ql = tid & (kTile - 1);
         const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         const uint32_t sw = (uint32_t)ql & 7u;    // 128-byte swizzle: chunk j of row r lives at r * 128 + ((j ^ (r & 7)) << 4)
         Ring ra, rw;
-        uint32_t it = 0, tile_iter = 0;
-        for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tile_iter) {
-            const size_t q = (size_t)tile * kTile + ql;
-            const size_t qc = q < P.nq ? q : P.nq - 1;
-            const uint32_t buf = tile_iter & 1u;
-            uint32_t* bits_t = s_bits + buf * bits_tile;
-            uint32_t* fm_t = s_fm + buf * fm_tile;
-            // ---- this tile's BITS rows and fan-out mask words -> shared memory (the two groups share the work)
-            if (tile_iter >= 2) mbar_wait(bits_free0 + 8 * buf, ((tile_iter >> 1) - 1u) & 1u);   // the epilogue warps are done with the tile that used this buffer
-            if (FMT == BC_DESC_BITS) {
-                const uint32_t* grow = reinterpret_cast<const uint32_t*>(P.desc + qc * P.dstride);
-                for (int w4 = 4 * g; w4 < P.bits_words; w4 += 4 * kGroups) {   // bits_words is a multiple of 4
-                    const uint4 x = __ldg(reinterpret_cast<const uint4*>(grow + w4));
-                    bits_t[(w4 + 0) * kTile + ql] = x.x;
-                    bits_t[(w4 + 1) * kTile + ql] = x.y;
-                    bits_t[(w4 + 2) * kTile + ql] = x.z;
-                    bits_t[(w4 + 3) * kTile + ql] = x.w;
+        uint32_t it = 0;
+        for (uint32_t iter = 0;; ++iter) {
+            K3_PASS_HEAD
+            if (cur_ok) {
+                // ---- this pass's tile: BITS rows and fan-out mask words -> shared memory (the two groups share the work)
+                const size_t q = (size_t)tile_cur * kTile + ql;
+                const size_t qc = q < P.nq ? q : P.nq - 1;
+                const uint32_t buf = iter & 1u;
+                uint32_t* bits_t = s_bits + buf * bits_tile;
+                uint32_t* fm_t = s_fm + buf * fm_tile;
+                if (iter >= 2) mbar_wait(bits_free0 + 8 * buf, ((iter >> 1) - 1u) & 1u);   // the epilogue warps are done with the tile that used this buffer
+                if (FMT == BC_DESC_BITS) {
+                    const uint32_t* grow = reinterpret_cast<const uint32_t*>(P.desc + qc * P.dstride);
+                    for (int w4 = 4 * g; w4 < P.bits_words; w4 += 4 * kGroups) {   // bits_words is a multiple of 4
+                        const uint4 x = __ldg(reinterpret_cast<const uint4*>(grow + w4));
+                        bits_t[(w4 + 0) * kTile + ql] = x.x;
+                        bits_t[(w4 + 1) * kTile + ql] = x.y;
+                        bits_t[(w4 + 2) * kTile + ql] = x.z;
+                        bits_t[(w4 + 3) * kTile + ql] = x.w;
+                    }
                 }
+                if (P.fan_mask != nullptr && g == 0)
+                    for (int w = 0; w < P.mask_words; ++w) fm_t[w * kTile + ql] = __ldg(P.fan_mask + qc * (size_t)P.mask_words + w);
             }
-            if (P.fan_mask != nullptr && g == 0)
-                for (int w = 0; w < P.mask_words; ++w) fm_t[w * kTile + ql] = __ldg(P.fan_mask + qc * (size_t)P.mask_words + w);
             asm volatile("bar.sync 1, %0;" ::"n"(32 * kWarpEpi) : "memory");   // the eight producer warps
-            const uint32_t* my_bits = bits_t + ql;
             int step_in_tile = 0;
-            for (int e = 0; e < P.n_edges; ++e) {
+            for (int si = 0; si < P.n_seq; ++si) {
+                K3_STEP_HEAD
                 const K3Edge& E = P.edge[e];
+                const uint32_t* my_bits = s_bits + (tile_iter & 1u) * bits_tile + ql;
+                const uint32_t* fm_t = s_fm + (tile_iter & 1u) * fm_tile;
                 const bool leaf = E.col_v < 0;
                 const bool a_exact = FMT == BC_DESC_BITS && leaf && !(E.fan_off >= 0 && P.fan_mask != nullptr);
                 const bool fan_on = E.fan_off >= 0 && P.fan_mask != nullptr && ((fm_t[(E.v >> 5) * kTile + ql] >> (E.v & 31)) & 1u);
@@ -481,11 +523,16 @@ __global__ void __launch_bounds__(kThreads, 1) k3_kernel(const __grid_constant__
                     mbar_wait(lam_ready0 + 8 * e, tile_iter & 1u);
                     tc_fence_after();
                 }
-                for (int kb = 0; kb < nkb; ++kb, ++it, ++step_in_tile, ra.next(P.a_stages), rw.next(kStagesW)) {
-                    if ((it & 1u) != (uint32_t)g) continue;
+                for (int kb = 0; kb < nkb; ++kb, ++it, ++step_in_tile, ra.next(P.a_stages), rw.next(P.w_stages)) {
+                    if ((it % (uint32_t)kGroups) != (uint32_t)g) continue;
                     const int c0 = kb * kBK;
                     if ((warp & 3) == 0) K3_STEP(0);
-                    float u[kBK];
+                    float u[kBK], lv[kBK];
+                    if (!leaf) {   // Lambda_v first: the TMEM round trip (~250 clk under load) hides behind the wait for the weights
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)   // (the node's columns are allocated in units of 8: never read past them)
+                            if (c0 + 8 * c < K) tmem_ld8(tlane + (uint32_t)(E.col_v + c0 + 8 * c), lv + 8 * c);
+                    }
                     if (FMT == BC_DESC_BITS) {
                         const uint32_t m = bits32(my_bits, P.bits_words, E.bit_off, K, c0);
 #pragma unroll
@@ -513,23 +560,11 @@ __global__ void __launch_bounds__(kThreads, 1) k3_kernel(const __grid_constant__
                             }
                     }
                     if ((warp & 3) == 0) K3_STEP(1);
-                    if (!leaf) {   // times Lambda_v, 16 columns per round trip (the node's columns are allocated in units of 8: never read past them)
+                    if (!leaf) {
+                        tmem_ld_wait();
 #pragma unroll
-                        for (int hs = 0; hs < 2; ++hs) {
-                            const int c = c0 + 16 * hs;
-                            if (c < K) {
-                                float lv[16];
-                                if (c + 8 < K) tmem_ld16(tlane + (uint32_t)(E.col_v + c), lv);
-                                else {
-                                    tmem_ld8(tlane + (uint32_t)(E.col_v + c), lv);
-#pragma unroll
-                                    for (int j = 8; j < 16; ++j) lv[j] = 0.f;
-                                }
-                                tmem_ld_wait();
-#pragma unroll
-                                for (int j = 0; j < 16; ++j) u[16 * hs + j] *= lv[j];
-                            }
-                        }
+                        for (int j = 0; j < kBK; ++j)
+                            if (c0 + (j & ~7) < K) u[j] *= lv[j];
                     }
                     if (c0 + kBK > K) {   // last block: states >= K must be exact zeros (stale Lambda columns, row padding, the next column's weights)
 #pragma unroll
@@ -566,6 +601,7 @@ __global__ void __launch_bounds__(kThreads, 1) k3_kernel(const __grid_constant__
                 }
                 if ((warp & 3) == 0) K3_STAMP(1 + g, e, 1);
             }
+            if (!cur_ok) break;
         }
     } else {
         // ================= epilogue warps, two groups of four (warps 8-11: the lower half of the parent's columns, warps 14-17: the
@@ -577,14 +613,17 @@ __global__ void __launch_bounds__(kThreads, 1) k3_kernel(const __grid_constant__
         const int g = warp >= kWarpEpiB;
         const int ql = tid & (kTile - 1);
         const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-        uint32_t ed = 0, tile_iter = 0;
+        uint32_t ed = 0;
         float acc[kAcc];
 #pragma unroll
         for (int i = 0; i < kAcc; ++i) acc[i] = 0.f;
-        for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++tile_iter) {
-            for (int e = 0; e < P.n_edges; ++e, ++ed) {
+        for (uint32_t iter = 0;; ++iter) {
+            K3_PASS_HEAD
+            for (int si = 0; si < P.n_seq; ++si) {
+                K3_STEP_HEAD
                 const K3Edge& E = P.edge[e];
                 const uint32_t db = P.n_dbuf == 2 ? (ed & 1u) : 0u, dpar = (P.n_dbuf == 2 ? (ed >> 1) : ed) & 1u;
+                ++ed;   // (executed steps only)
                 const uint32_t dcol = tlane + (uint32_t)(P.d_col + (int)db * P.d_stride), pcol = tlane + (uint32_t)E.col_pa;
                 const bool first = E.first, run_first = (E.flags & kRunFirst) != 0, run_last = (E.flags & kRunLast) != 0;
                 const bool regs = (E.flags & kRegs) != 0, root = E.publish == -2;
@@ -651,34 +690,40 @@ __global__ void __launch_bounds__(kThreads, 1) k3_kernel(const __grid_constant__
                         if (lane == 0 && E.publish >= 0) mbar_arrive(lam_ready0 + 8 * E.publish);   // Lambda_pa is complete: pa's own edge may be built
                     }
                 } else {
-                    // a parent domain beyond 2 x kAcc states: Lambda_pa (*)= D in tensor memory, 16 columns per round trip
-                    for (int j = lo; j < hi; j += 16) {
-                        float dv[16], lv[16];
-                        const bool whole = j + 16 <= hi;   // else 8 columns
-                        if (whole) {
-                            tmem_ld16(dcol + (uint32_t)j, dv);
-                            if (!first) tmem_ld16(pcol + (uint32_t)j, lv);
-                        } else {
+                    // Lambda_pa (*)= D in tensor memory without touching the register accumulator: a parent domain beyond 2 x kAcc
+                    // states, or a TAIL edge (the only message into its parent, interleaved with another tile's run).  The root's
+                    // only message is not copied at all: the result is read off the accumulator below.
+                    if (!(first && root)) {
+                        for (int j = lo; j < hi; j += 16) {
+                            float dv[16];
                             tmem_ld8(dcol + (uint32_t)j, dv);
-                            if (!first) tmem_ld8(pcol + (uint32_t)j, lv);
-                        }
-                        tmem_ld_wait();
-                        if (!first) {
+                            if (j + 8 < hi) tmem_ld8(dcol + (uint32_t)(j + 8), dv + 8);
+                            tmem_ld_wait();
+                            if (!first) {
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) dv[i] *= lv[i] * debias;
-                        } else {
+                                for (int h8 = 0; h8 < 2; ++h8)
+                                    if (j + 8 * h8 < hi) {
+                                        float lv[8];
+                                        tmem_ld8(pcol + (uint32_t)(j + 8 * h8), lv);
+                                        tmem_ld_wait();
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) dv[i] *= debias;
+                                        for (int i = 0; i < 8; ++i) dv[8 * h8 + i] *= lv[i];
+                                    }
+                            }
+                            if (P.debias_unit != 0.f) {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) dv[i] *= debias;
+                            }
+                            tmem_st8(pcol + (uint32_t)j, dv);
+                            if (j + 8 < hi) tmem_st8(pcol + (uint32_t)(j + 8), dv + 8);
                         }
-                        if (whole) tmem_st16(pcol + (uint32_t)j, dv);
-                        else tmem_st8(pcol + (uint32_t)j, dv);
-                    }
-                    tmem_st_wait();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) {
-                        mbar_arrive(d_empty0 + 8 * db);
-                        if (E.publish >= 0) mbar_arrive(lam_ready0 + 8 * E.publish);
+                        tmem_st_wait();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) {
+                            mbar_arrive(d_empty0 + 8 * db);
+                            if (E.publish >= 0) mbar_arrive(lam_ready0 + 8 * E.publish);
+                        }
                     }
                 }
                 if (warp == kWarpEpi) K3_STAMP(3, e, 1);
@@ -708,19 +753,25 @@ __global__ void __launch_bounds__(kThreads, 1) k3_kernel(const __grid_constant__
                             }
                         }
                     } else {
-                        tc_fence_after();
+                        // from tensor memory: the root's columns, or straight from the accumulator when this edge is the root's only message
+                        const uint32_t src = first ? dcol : tlane + (uint32_t)P.root_col;
                         for (int c0 = lo; c0 < hi && c0 < P.root_card; c0 += 8) {
                             float lv[8], w[8];
-                            tmem_ld8(tlane + (uint32_t)(P.root_col + c0), lv);
+                            tmem_ld8(src + (uint32_t)c0, lv);
                             weights8<FMT>(my_bits, P.bits_words, drow, P.root_lam_off, P.root_bit_off, P.root_card, c0, w);
                             tmem_ld_wait();
 #pragma unroll
                             for (int j = 0; j < 8; ++j)
                                 if (c0 + j < P.root_card) {
-                                    float x = lv[j] * w[j];
+                                    float x = lv[j] * w[j] * (first ? debias : 1.f);
                                     if (fan_root) x *= s_fan[P.root_fan_off + c0 + j];
                                     res = fmaf(x, __ldg(P.root_T + c0 + j), res);
                                 }
+                        }
+                        if (first) {   // the accumulator has been read
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(d_empty0 + 8 * db);
                         }
                     }
                     if (mid < n8) {   // the upper half's share travels through shared memory (two tiles deep: the groups drift by at most one)
@@ -733,6 +784,7 @@ __global__ void __launch_bounds__(kThreads, 1) k3_kernel(const __grid_constant__
                     if (lane == 0) mbar_arrive(bits_free0 + 8 * buf);   // this tile's BITS rows / mask words are no longer read
                 }
             }
+            if (!cur_ok) break;
         }
     }
 
@@ -835,10 +887,24 @@ int k3_prepare(bc_model* m) {
     // registers over a run (domains of up to 2 x kAcc states).  The ROOT's message then never visits tensor memory unless its
     // runs are interrupted (two internal children) or its domain is too large for the registers.
     auto pa_of = [&](int e) { return (int)m->nodes[sched[e]].parent; };
+    std::vector<int> n_msgs(n, 0);
+    for (int e = 0; e < n_edges; ++e) ++n_msgs[pa_of(e)];
+    // TAIL: the chain at the top of the tree -- the maximal suffix of the schedule made of edges that are the ONLY message into
+    // their parent.  Each of them waits for the complete result of the one before (drain, epilogue, producers, MMAs: ~2 500 clk
+    // per hop with the tensor pipe idle: 35-40 % of a tile on the IMDB models).  They are taken out of the tile's own pass and
+    // interleaved with the body of the CTA's NEXT tile; their epilogue never touches the register accumulator (the body's run
+    // is alive in it), the nodes they read and write keep their tensor-memory columns for the whole pass.
+    int n_tail = 0;
+    if (!std::getenv("BC_K3_NO_SKEW"))
+        while (n_tail < n_edges - 1 && n_msgs[pa_of(n_edges - 1 - n_tail)] == 1) ++n_tail;
+    const int n_body = n_edges - n_tail;
+    std::vector<char> pinned(n, 0);   // nodes whose columns live across passes
+    for (int e = n_body; e < n_edges; ++e) pinned[sched[e]] = pinned[pa_of(e)] = 1;
     int root_runs = 0;
     for (int e = 0; e < n_edges; ++e)
         if (pa_of(e) == 0 && (e == 0 || pa_of(e - 1) != 0)) ++root_runs;
-    const bool root_in_regs = bc_round_up(m->nodes[0].card, 16) <= 2 * kAcc && root_runs == 1;
+    const bool root_only_msg = n_msgs[0] == 1;   // read straight off the accumulator
+    const bool root_in_regs = root_only_msg || (bc_round_up(m->nodes[0].card, 16) <= 2 * kAcc && root_runs == 1);
     auto assign = [&](int a_stages, int n_dbuf) -> int {   // columns used, or -1 (col[] is only written when every node found a place)
         std::vector<int> place(n, -1);
         const int units_total = 512 / 8;
@@ -850,8 +916,8 @@ int k3_prepare(bc_model* m) {
         for (int v : order) {
             if (v == 0 && root_in_regs) continue;
             const int need = (int)bc_round_up(m->nodes[v].card, 8) / 8;
-            const int start = first_child_edge[v];
-            const int end = own_edge[v] < 0 ? (1 << 30) : own_edge[v];   // (the root: to the end)
+            const int start = pinned[v] ? 0 : first_child_edge[v];
+            const int end = (own_edge[v] < 0 || pinned[v]) ? (1 << 30) : own_edge[v];   // (the root: to the end)
             int at = -1;
             for (int u0 = 0; u0 + need <= units_total && at < 0; ++u0) {
                 bool ok = true;
@@ -913,9 +979,34 @@ int k3_prepare(bc_model* m) {
         E.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(E.n_pad >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
         E.publish = last_child_edge[nd.parent] != e ? -1 : (nd.parent == 0 ? -2 : own_edge[nd.parent]);
         E.flags = ((e == 0 || pa_of(e - 1) != nd.parent) ? kRunFirst : 0) | ((e == n_edges - 1 || pa_of(e + 1) != nd.parent) ? kRunLast : 0) |
-                  (E.n_pad <= 2 * kAcc ? kRegs : 0);
+                  ((E.n_pad <= 2 * kAcc && e < n_body) ? kRegs : 0);
         E.bimg_off = total;
         total += (size_t)E.nkb * E.n_pad * 256;
+    }
+    {   // step sequence of one pass: the body in order, the previous tile's tail edges spread over it by estimated tensor time
+        // (one hop of the chain needs the result of the one before: leave ~2 500 clk of body work between them)
+        auto cost = [&](const K3Edge& E) { return (long long)((E.K + 7) / 8) * 3 * std::max(E.n_pad / 2, 40); };
+        long long cum = 0;
+        int t = 0;
+        long long gap = 2500;
+        if (const char* e = std::getenv("BC_K3_GAP")) gap = std::max(1, std::atoi(e));
+        // the first tail edge READS the message of the node below the chain while the body's runs into that node REWRITE it for
+        // the next tile: it must come before the body edge that ends the first of those runs (then its producers have read
+        // the old message before that edge's MMAs, hence before its epilogue's write)
+        int limit0 = n_body;
+        if (n_tail > 0) {
+            const int hub = sched[n_body];
+            for (int e = 0; e < n_body; ++e)
+                if (pa_of(e) == hub && (k->edges[e].flags & kRunLast)) { limit0 = e; break; }
+        }
+        for (int e = 0; e < n_body; ++e) {
+            if (t == 0 && n_tail > 0 && e == limit0) k->seq.push_back((uint8_t)(128 | (n_body + t++)));
+            k->seq.push_back((uint8_t)e);
+            cum += cost(k->edges[e]);
+            while (t < n_tail && cum >= gap / 2 + (long long)t * gap) k->seq.push_back((uint8_t)(128 | (n_body + t++)));
+        }
+        while (t < n_tail) k->seq.push_back((uint8_t)(128 | (n_body + t++)));
+        k->n_tail = n_tail;
     }
     std::vector<uint8_t> img(total, 0);
     for (const K3Edge& E : k->edges) {
@@ -943,7 +1034,9 @@ int k3_prepare(bc_model* m) {
     k->bimg_bytes = total;
     // ---- shared memory: B ring (as deep as fits, at most 4), DENSE weight ring, BITS rows and fan-out mask words of two tiles
     const size_t fan_floats = (size_t)bc_round_up((int64_t)m->fan.size(), 4);
-    const size_t per_fmt = std::max((size_t)kStagesW * kWBytes, (size_t)2 * m->bits_words * kTile * 4);
+    int w_stages = 4;
+    if (const char* e = std::getenv("BC_K3_WSTAGES")) w_stages = std::max(2, std::min(kStagesW, std::atoi(e)));
+    const size_t per_fmt = std::max((size_t)w_stages * kWBytes, (size_t)2 * m->bits_words * kTile * 4);
     const size_t fixed = per_fmt + (size_t)2 * m->mask_words * kTile * 4 + fan_floats * 4 + 256 /* nibble table */ + 2 * kTile * 4 /* root partial sums */ +
                          8 * (4 * kMaxStages + 2 * kStagesW + 8 + kMaxEdges + 2) /* barriers, TMEM slot */ + 8 * kTraceSteps * 8 /* trace */ +
                          1024 /* alignment */;
@@ -953,6 +1046,7 @@ int k3_prepare(bc_model* m) {
     while (b_stages > 1 && (size_t)b_stages * npad_max * 256 + fixed > smem_optin) --b_stages;
     if ((size_t)b_stages * npad_max * 256 + fixed > smem_optin || b_stages < 2) return fail("operand rings exceed shared memory");
     k->b_stages = b_stages;
+    k->w_stages = w_stages;
     k->smem = (size_t)b_stages * npad_max * 256 + fixed;
     k->ctas_per_sm = 1;
     if (m->device >= 0) {   // (a host-only model keeps the plan for inspection: bc_model_fused_plan)
@@ -1010,6 +1104,9 @@ int bc_k3_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32
     K3Params P{};
     P.n_edges = (int)k->edges.size();
     std::memcpy(P.edge, k->edges.data(), sizeof(K3Edge) * k->edges.size());
+    P.n_seq = (int)k->seq.size();
+    P.n_tail = k->n_tail;
+    std::memcpy(P.seq, k->seq.data(), k->seq.size());
     P.bimg = k->d_bimg;
     P.desc = static_cast<const uint8_t*>(desc);
     P.dstride = (size_t)bc_model_desc_stride(m, fmt);
@@ -1032,6 +1129,7 @@ int bc_k3_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32
     P.a_col = k->a_col;
     P.a_stages = k->a_stages;
     P.b_stages = k->b_stages;
+    P.w_stages = k->w_stages;
     P.d_col = k->d_col;
     P.d_stride = k->npad_max;
     P.n_dbuf = k->n_dbuf;
