@@ -576,8 +576,6 @@ extern "C" int bc_query_batch_host(bc_model* m, const void* desc, size_t nq, int
         }
         BC_CUDA_CHECK(cudaMemcpyAsync(dst, p->d_out[s], cq * 4, cudaMemcpyDeviceToHost, p->s_out));
         BC_CUDA_CHECK(cudaEventRecord(p->ev_out[s], p->s_out));
-        // the next use of this slot's device buffers must also wait for this D2H
-        BC_CUDA_CHECK(cudaStreamWaitEvent(p->s_in, p->ev_out[s], 0));
     }
     BC_CUDA_CHECK(cudaStreamSynchronize(p->s_out));
     drain.armed = false;   // s_out waited for every kernel and copy of the call
@@ -761,7 +759,6 @@ static int sparse_host_impl(bc_model* m, const uint32_t* row_off, const uint32_t
         }
         BC_CUDA_CHECK(cudaMemcpyAsync(dst, p->d_out[s], cq * 4, cudaMemcpyDeviceToHost, p->s_out));
         BC_CUDA_CHECK(cudaEventRecord(p->ev_out[s], p->s_out));
-        BC_CUDA_CHECK(cudaStreamWaitEvent(p->s_in, p->ev_out[s], 0));
     }
     BC_CUDA_CHECK(cudaStreamSynchronize(p->s_out));
     drain.armed = false;   // s_out waited for every kernel and copy of the call
@@ -865,7 +862,9 @@ extern "C" int bc_query_batch_packed_host(bc_model* m, const uint8_t* klen, cons
     int rc = bc_model_packed_geometry(m, &w, &cb, &sb);
     if (rc) return rc;
     BC_CUDA_CHECK(cudaSetDevice(m->device));
-    size_t chunk = 1024 * 1024;
+    // 512 K queries per chunk: a 1 M-query call then overlaps the second chunk's H2D with the first chunk's kernels and read-back
+    // (profiles/r2_e2e_packed_chunk_sweep.txt: one chunk 1.41e9, two 2.10e9, four 1.97e9, eight 1.88e9 queries/s on the same box)
+    size_t chunk = 512 * 1024;
     if (const char* env = std::getenv("BC_PACKED_CHUNK")) {
         const long long v = std::atoll(env);
         if (v >= BC_PACKED_BLOCK) chunk = (size_t)v / BC_PACKED_BLOCK * BC_PACKED_BLOCK;
@@ -928,7 +927,6 @@ extern "C" int bc_query_batch_packed_host(bc_model* m, const uint8_t* klen, cons
         BC_CUDA_CHECK(cudaStreamWaitEvent(p->s_out, p->ev_k[s], 0));
         BC_CUDA_CHECK(cudaMemcpyAsync(out + q0, p->d_out[s], cq * 4, cudaMemcpyDeviceToHost, p->s_out));
         BC_CUDA_CHECK(cudaEventRecord(p->ev_out[s], p->s_out));
-        BC_CUDA_CHECK(cudaStreamWaitEvent(p->s_in, p->ev_out[s], 0));
     }
     BC_CUDA_CHECK(cudaStreamSynchronize(p->s_out));
     drain.armed = false;
