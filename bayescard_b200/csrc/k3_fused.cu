@@ -166,7 +166,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 // (with the default time limit a failed try_wait comes back after ~50 clk and the spin loops of the 18 warps are 21 % of all
-//  issued instructions -- ncu, profiles/r2_ncu_29_k3_bits_imdb1.json; with a suspend-time hint ptxas emits NANOSLEEP.SYNCS and the
+//  issued instructions -- ncu, profiles/r2_ncu_29_k3_dense_imdb1.json; with a suspend-time hint ptxas emits NANOSLEEP.SYNCS and the
 //  spinning stops.  Measured: no change in throughput for hints of 100 ns ... 20 us -- the spinning warps only took issue slots
 //  nobody else wanted -- so this is about power, not speed)
 #ifndef BC_K3_SUSPEND_NS
@@ -566,10 +566,17 @@ __global__ void __launch_bounds__(kThreads, 1) k3_kernel(const __grid_constant__
                         for (int j = 0; j < kBK; ++j)
                             if (c0 + (j & ~7) < K) u[j] *= lv[j];
                     }
-                    if (c0 + kBK > K) {   // last block: states >= K must be exact zeros (stale Lambda columns, row padding, the next column's weights)
+                    // States >= K of the last block: their rows of T_v^T are zeros in the operand image and whole k-steps past K are not
+                    // issued, so any FINITE value there contributes 0 -- BITS rows (bits past the domain are cleared, the message's
+                    // padding columns hold the zeros the epilogue wrote) need no masking at all.  DENSE rows could carry NaN / Inf in
+                    // the next column or in caller-owned row padding: zeroed by one compare + select per state.  (The old
+                    // per-element compare + select over all 32 states was 7.5 % of the instructions of this issue-bound kernel:
+                    // ncu, profiles/r2_ncu_36_k3_bits_imdb1.json.)
+                    if (FMT == BC_DESC_DENSE_F32 && c0 + kBK > K) {
+                        int valid = K - c0;
+                        asm volatile("" : "+r"(valid));   // a vector register: one ISETP + one FSEL per state instead of the uniform-predicate dance
 #pragma unroll
-                        for (int j = 0; j < kBK; ++j)
-                            if (c0 + j >= K) u[j] = 0.f;
+                        for (int j = 0; j < kBK; ++j) u[j] = j < valid ? u[j] : 0.f;
                     }
                     const uint32_t a_hi = tlane + (uint32_t)(P.a_col + (int)ra.s * 64);
                     if ((warp & 3) == 0) K3_STEP(2);
@@ -669,8 +676,12 @@ __global__ void __launch_bounds__(kThreads, 1) k3_kernel(const __grid_constant__
                                     }
                                 }
                                 tmem_ld_wait();
+                                if (P.debias_unit != 0.f) {
 #pragma unroll
-                                for (int i = 0; i < 24; ++i) acc[24 * r + i] *= dv[i] * debias;
+                                    for (int i = 0; i < 24; ++i) dv[i] *= debias;
+                                }
+#pragma unroll
+                                for (int i = 0; i < 24; ++i) acc[24 * r + i] *= dv[i];
                             }
                         }
                     }
