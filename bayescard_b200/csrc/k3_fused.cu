@@ -169,6 +169,9 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 //  issued instructions -- ncu, profiles/r2_ncu_29_k3_dense_imdb1.json; with a suspend-time hint ptxas emits NANOSLEEP.SYNCS and the
 //  spinning stops.  Measured: no change in throughput for hints of 100 ns ... 20 us -- the spinning warps only took issue slots
 //  nobody else wanted -- so this is about power, not speed)
+#ifndef BC_K3_SPLIT_CVT
+#define BC_K3_SPLIT_CVT 0
+#endif
 #ifndef BC_K3_SUSPEND_NS
 #define BC_K3_SUSPEND_NS 500
 #endif
@@ -269,7 +272,13 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 // x = hi + lo, hi = x rounded to the nearest TF32 number (ties away from zero: two integer instructions); lo = x - hi is
 // exact in fp32 and symmetric around zero, so the tensor core's truncation of its low bits is unbiased
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+#if BC_K3_SPLIT_CVT
+    uint32_t h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));   // round to nearest, ties away: one instruction
+    hi = __uint_as_float(h);
+#else
     hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+#endif
     lo = x - hi;
 }
 
