@@ -218,35 +218,58 @@ class NativeJobLight:
         for c in getattr(self, "sqlc", []):
             c.close()
 
-    def plan(self, sqls: Sequence[str]):
+    @staticmethod
+    def join_texts(sqls: Sequence[str]):
+        """A batch of SQL strings as ONE buffer + offsets (what ``bc_joblight_plan_text`` reads): ``(bytes, uint64[n + 1])``."""
+        import numpy as np
+
+        n = len(sqls)
+        blob = "\n".join(sqls).encode("utf-8")
+        lens = np.fromiter(map(len, sqls), dtype=np.uint64, count=n)
+        if n and int(lens.sum()) + n - 1 != len(blob):   # non-ASCII text: byte lengths differ from character counts
+            lens = np.fromiter((len(s.encode("utf-8")) for s in sqls), dtype=np.uint64, count=n)
+        off = np.zeros(n + 1, dtype=np.uint64)
+        if n:
+            np.cumsum(lens + np.uint64(1), out=off[1:])
+            off[n] -= np.uint64(1)
+        return blob, off
+
+    def plan(self, sqls, text_off=None):
         """The factor table of a batch: dict of numpy arrays (``status, join_size, first_factor, factor_bn, factor_inverse,
-        factor_fan_mask, pred_off, pred_col, pred_kind, pred_a, pred_b``)."""
+        factor_fan_mask, pred_off, pred_col, pred_kind, pred_a, pred_b``).  ``sqls``: a sequence of SQL strings, or one
+        ``bytes`` buffer with ``text_off`` (``uint64[n + 1]``: query q is ``sqls[text_off[q]:text_off[q + 1]]``)."""
         import ctypes as C
 
         import numpy as np
 
         from . import _lib as L
 
-        n = len(sqls)
-        raw = [s.encode("utf-8") for s in sqls]
-        arr = (C.c_char_p * max(1, n))(*raw)
+        if isinstance(sqls, (bytes, bytearray, memoryview)):
+            blob, off = bytes(sqls) if not isinstance(sqls, bytes) else sqls, np.ascontiguousarray(text_off, dtype=np.uint64)
+        else:
+            blob, off = self.join_texts(sqls)
+        n = int(off.size) - 1
+        if n > 0 and int(off[n]) > len(blob):
+            raise ValueError("text_off runs past the text buffer")
+        # (a query ends one byte before the next one's offset when the buffer was joined with a separator: the parser strips it)
+        text = C.c_char_p(blob)
         status = np.zeros(n, dtype=np.uint8)
         join = np.zeros(n, dtype=np.float64)
         first = np.zeros(n + 1, dtype=np.uint32)
-        cap_f, cap_p = max(16, 4 * n), max(64, 16 * n)
+        cap_f, cap_p = max(16, 3 * n), max(64, 10 * n)
         while True:
-            f_bn = np.zeros(cap_f, dtype=np.int32)
-            f_inv = np.zeros(cap_f, dtype=np.uint8)
-            f_fan = np.zeros(cap_f, dtype=np.uint32)
-            p_off = np.zeros(cap_f + 1, dtype=np.uint32)
-            p_col = np.zeros(cap_p, dtype=np.int32)
-            p_kind = np.zeros(cap_p, dtype=np.uint8)
-            p_a = np.zeros(cap_p, dtype=np.float64)
-            p_b = np.zeros(cap_p, dtype=np.float64)
+            f_bn = np.empty(cap_f, dtype=np.int32)
+            f_inv = np.empty(cap_f, dtype=np.uint8)
+            f_fan = np.empty(cap_f, dtype=np.uint32)
+            p_off = np.empty(cap_f + 1, dtype=np.uint32)
+            p_col = np.empty(cap_p, dtype=np.int32)
+            p_kind = np.empty(cap_p, dtype=np.uint8)
+            p_a = np.empty(cap_p, dtype=np.float64)
+            p_b = np.empty(cap_p, dtype=np.float64)
             nf, npred = C.c_size_t(), C.c_size_t()
-            rc = L.lib().bc_joblight_plan(self._h, n, C.cast(arr, C.c_void_p), status.ctypes.data, join.ctypes.data, first.ctypes.data,
-                                          cap_f, f_bn.ctypes.data, f_inv.ctypes.data, f_fan.ctypes.data, p_off.ctypes.data, cap_p,
-                                          p_col.ctypes.data, p_kind.ctypes.data, p_a.ctypes.data, p_b.ctypes.data, C.byref(nf), C.byref(npred))
+            rc = L.lib().bc_joblight_plan_text(self._h, n, text, off.ctypes.data, status.ctypes.data, join.ctypes.data, first.ctypes.data,
+                                               cap_f, f_bn.ctypes.data, f_inv.ctypes.data, f_fan.ctypes.data, p_off.ctypes.data, cap_p,
+                                               p_col.ctypes.data, p_kind.ctypes.data, p_a.ctypes.data, p_b.ctypes.data, C.byref(nf), C.byref(npred))
             if rc == L.ELIMIT and (nf.value > cap_f or npred.value > cap_p):
                 cap_f, cap_p = max(cap_f, nf.value), max(cap_p, npred.value)
                 continue
@@ -255,7 +278,7 @@ class NativeJobLight:
         nf, npred = nf.value, npred.value
         return {"status": status, "join_size": join, "first_factor": first, "factor_bn": f_bn[:nf], "factor_inverse": f_inv[:nf],
                 "factor_fan_mask": f_fan[:nf], "pred_off": p_off[:nf + 1], "pred_col": p_col[:npred], "pred_kind": p_kind[:npred],
-                "pred_a": p_a[:npred], "pred_b": p_b[:npred]}
+                "pred_a": p_a[:npred], "pred_b": p_b[:npred], "n_queries": n}
 
     def factor_rows(self, plan, wsparse: bool = False):
         """Per BN: ``(factor ids, kind, BITS rows, DENSE rows | WSPARSE (row_off, words), dense index)`` of the planned factors."""
@@ -270,36 +293,59 @@ class NativeJobLight:
                                                            plan["pred_b"], plan["factor_fan_mask"], wsparse)
         return out
 
-    def cardinality_sql_batch(self, sqls: Sequence[str]):
+    def cardinality_sql_batch(self, sqls, text_off=None, timing=None):
+        """Cardinalities of a batch of job-light SQL texts (a sequence of strings, or one ``bytes`` buffer + ``text_off``).
+        ``timing``: optional dict that receives the seconds spent per phase."""
+        import time
+
         import numpy as np
 
         from . import _lib as L
 
-        plan = self.plan(sqls)
+        t0 = time.perf_counter()
+        plan = self.plan(sqls, text_off)
+        nq = plan["n_queries"]
+        t1 = time.perf_counter()
         nf = plan["factor_bn"].size
         prob = np.zeros(nf, dtype=np.float64)
         python_factors = []
-        for b, (ids, kind, bits, ws, didx) in self.factor_rows(plan, wsparse=True).items():
+        rows = self.factor_rows(plan, wsparse=True)
+        t2 = time.perf_counter()
+        for b, (ids, kind, bits, ws, didx) in rows.items():
             m = self.machines[b]
             mask = plan["factor_fan_mask"][ids].reshape(-1, 1)
-            sel = np.nonzero(kind == L.SQLC_BITS)[0]
-            if sel.size:
-                prob[ids[sel]] = m.dev.run_host(bits[sel], L.DESC_BITS, np.ascontiguousarray(mask[sel]), m.kernel)
+            n_bits = int(np.count_nonzero(kind == L.SQLC_BITS))
+            if n_bits:
+                # every row of the BN goes through the kernel (rows of the other kinds hold arbitrary selection bits: finite
+                # results that are not used) -- cheaper than gathering the BITS rows on the host
+                p_all = m.dev.run_host(bits, L.DESC_BITS, mask, m.kernel)
+                sel = np.nonzero(kind == L.SQLC_BITS)[0]
+                prob[ids[sel]] = p_all[sel]
             if didx.size:   # fractional weights: weighted runs over PCIe (~100 B per factor), DENSE rows built on the device
                 prob[ids[didx]] = m.dev.run_wsparse_host(ws[0], ws[1], np.ascontiguousarray(mask[didx]), m.kernel)
-            python_factors.extend(int(i) for i in ids[np.nonzero(kind == L.SQLC_PYTHON)[0]])
+            bad = (kind == L.SQLC_PYTHON) | ((kind == L.SQLC_ZERO) & (mask[:, 0] != 0))
             # SQLC_ZERO: probability 0 (already) -- except on an EXPECTATION factor: Bayescard_BN.expectation has no guard for an
             # undecodable predicate and the reference fails there (Models/Bayescard_BN.py:581-583); the mirror raises the same
-            python_factors.extend(int(i) for i in ids[np.nonzero((kind == L.SQLC_ZERO) & (mask[:, 0] != 0))[0]])
-        out = np.zeros(len(sqls), dtype=np.float64)
+            if bad.any():
+                python_factors.extend(ids[np.nonzero(bad)[0]].tolist())
+        t3 = time.perf_counter()
+        out = np.zeros(nq, dtype=np.float64)
         redo = set(np.nonzero(plan["status"])[0].tolist())
         if python_factors:   # a factor the native decoder declined: its whole query goes through the mirror
             owner = np.searchsorted(plan["first_factor"], np.asarray(python_factors), side="right") - 1
             redo.update(int(q) for q in owner)
-        L.check(L.lib().bc_joblight_combine(len(sqls), plan["status"].ctypes.data, plan["join_size"].ctypes.data,
+        L.check(L.lib().bc_joblight_combine(nq, plan["status"].ctypes.data, plan["join_size"].ctypes.data,
                                             plan["first_factor"].ctypes.data, plan["factor_inverse"].ctypes.data, prob.ctypes.data,
                                             out.ctypes.data))
-        for q in sorted(redo):
-            tq = self.ens.parse_query_all([plan_star_query(sqls[q], self.join_sizes)])[0]
-            out[q] = float(np.asarray(self.ens.cardinality(tq)).reshape(-1)[0])
+        if redo:
+            if isinstance(sqls, (bytes, bytearray, memoryview)):
+                off = np.asarray(text_off, dtype=np.uint64)
+                text_of = lambda q: bytes(sqls[int(off[q]):int(off[q + 1])]).decode("utf-8")
+            else:
+                text_of = lambda q: sqls[q]
+            for q in sorted(redo):
+                tq = self.ens.parse_query_all([plan_star_query(text_of(q), self.join_sizes)])[0]
+                out[q] = float(np.asarray(self.ens.cardinality(tq)).reshape(-1)[0])
+        if timing is not None:
+            timing.update(plan=t1 - t0, decode_pack=t2 - t1, device=t3 - t2, combine=time.perf_counter() - t3, factors=int(nf))
         return out

@@ -334,6 +334,14 @@ BC_API int bc_joblight_plan(const bc_joblight* h, size_t n, const char* const* s
                             uint32_t* first_factor, size_t factor_capacity, int32_t* factor_bn, uint8_t* factor_inverse,
                             uint32_t* factor_fan_mask, uint32_t* pred_off, size_t pred_capacity, int32_t* pred_col, uint8_t* pred_kind,
                             double* pred_a, double* pred_b, size_t* n_factors, size_t* n_preds);
+/* The same over one text buffer: query q is text[text_off[q], text_off[q+1]) (n + 1 offsets; separators between queries are
+ * whitespace / ';' to the parser).  Turning a batch of host-language strings into a char* array costs about as much as planning
+ * them; a joined buffer does not. */
+BC_API int bc_joblight_plan_text(const bc_joblight* h, size_t n, const char* text, const uint64_t* text_off, uint8_t* status,
+                                 double* join_size, uint32_t* first_factor, size_t factor_capacity, int32_t* factor_bn,
+                                 uint8_t* factor_inverse, uint32_t* factor_fan_mask, uint32_t* pred_off, size_t pred_capacity,
+                                 int32_t* pred_col, uint8_t* pred_kind, double* pred_a, double* pred_b, size_t* n_factors,
+                                 size_t* n_preds);
 /* BN_ensemble.cardinality (Models/BN_ensemble_model.py:228-252): join_size * prod(p | 1/p), a zero factor gives 1, clamp >= 1. */
 BC_API int bc_joblight_combine(size_t n, const uint8_t* status, const double* join_size, const uint32_t* first_factor,
                                const uint8_t* factor_inverse, const double* factor_prob, double* out);

@@ -235,8 +235,27 @@ def test_native_planner_and_factor_rows_equal_the_python_mirror():
     # what the native planner declines goes to the mirror
     bad = nat.plan(["SELECT COUNT(*) FROM title t,name n WHERE t.id=n.id", "SELECT 1", sqls[0]])
     assert bad["status"].tolist() == [1, 1, 0]
-    # combine: BN_ensemble.cardinality's rules
+    # the three ways in -- a list of strings, one text buffer + offsets, the char* array of bc_joblight_plan -- give one factor table
     import ctypes as C
+    blob, off = nat.join_texts(sqls)
+    plan_b = nat.plan(blob, off)
+    raw = [x.encode() for x in sqls]
+    arr = (C.c_char_p * len(raw))(*raw)
+    n = len(sqls)
+    st, jn, ff = np.zeros(n, np.uint8), np.zeros(n), np.zeros(n + 1, np.uint32)
+    nf, npred = plan["factor_bn"].size, plan["pred_col"].size
+    fb, fi, fm, po = np.zeros(nf, np.int32), np.zeros(nf, np.uint8), np.zeros(nf, np.uint32), np.zeros(nf + 1, np.uint32)
+    pc, pk, pa, pb = np.zeros(npred, np.int32), np.zeros(npred, np.uint8), np.zeros(npred), np.zeros(npred)
+    gf, gp = C.c_size_t(), C.c_size_t()
+    L.check(L.lib().bc_joblight_plan(nat._h, n, C.cast(arr, C.c_void_p), st.ctypes.data, jn.ctypes.data, ff.ctypes.data, nf, fb.ctypes.data,
+                                     fi.ctypes.data, fm.ctypes.data, po.ctypes.data, npred, pc.ctypes.data, pk.ctypes.data, pa.ctypes.data,
+                                     pb.ctypes.data, C.byref(gf), C.byref(gp)))
+    plan_c = {"status": st, "join_size": jn, "first_factor": ff, "factor_bn": fb, "factor_inverse": fi, "factor_fan_mask": fm, "pred_off": po,
+              "pred_col": pc, "pred_kind": pk, "pred_a": pa, "pred_b": pb}
+    for key, want in plan_c.items():
+        assert np.array_equal(plan[key], want) and np.array_equal(plan_b[key], want), key
+    assert (gf.value, gp.value) == (nf, npred)
+    # combine: BN_ensemble.cardinality's rules
     first = np.asarray([0, 2, 4, 5], dtype=np.uint32)
     inv = np.asarray([0, 1, 0, 0, 0], dtype=np.uint8)
     prob = np.asarray([0.5, 0.25, 0.0, 0.5, 1e-9], dtype=np.float64)

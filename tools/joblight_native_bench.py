@@ -49,6 +49,7 @@ def main():
         bad.update((np.searchsorted(plan0["first_factor"], z, side="right") - 1).tolist())
     sqls = [s for i, s in enumerate(sqls) if i not in bad]
     nat.cardinality_sql_batch(sqls[:4096])   # warm-up (K3 plans, pipes)
+    nat.cardinality_sql_batch(sqls)
     t = time.perf_counter()
     plan = nat.plan(sqls)
     t_plan = time.perf_counter() - t
@@ -56,9 +57,17 @@ def main():
     t = time.perf_counter()
     rows = nat.factor_rows(plan)
     t_rows = time.perf_counter() - t
+    phases = {}
     t = time.perf_counter()
-    est = nat.cardinality_sql_batch(sqls)
+    est = nat.cardinality_sql_batch(sqls, timing=phases)
     t_all = time.perf_counter() - t
+    # the same from ONE text buffer (what a caller that already holds the workload as text hands over)
+    blob, off = nat.join_texts(sqls)
+    phases_text = {}
+    t = time.perf_counter()
+    est_text = nat.cardinality_sql_batch(blob, off, timing=phases_text)
+    t_text = time.perf_counter() - t
+    assert np.array_equal(est, est_text)
     # the Python path on a subset (it is ~100x slower)
     sub = sqls[: args.python_queries]
     t = time.perf_counter()
@@ -71,7 +80,8 @@ def main():
     qe = np.maximum(est70 / true, true / est70)
     rec = {"queries": len(sqls), "factors": nf, "dense_factors": int(sum(len(r[4]) for r in rows.values())),
            "native": {"seconds": t_all, "queries_per_s": len(sqls) / t_all, "factors_per_s": nf / t_all,
-                      "plan_seconds": t_plan, "decode_pack_seconds": t_rows},
+                      "plan_seconds": t_plan, "decode_pack_seconds": t_rows, "phases": phases},
+           "native_text_buffer": {"seconds": t_text, "queries_per_s": len(sqls) / t_text, "factors_per_s": nf / t_text, "phases": phases_text},
            "python": {"queries": len(sub), "factors": nf_sub, "seconds": t_py, "queries_per_s": len(sub) / t_py, "factors_per_s": nf_sub / t_py},
            "max_rel_diff_native_vs_python": rel,
            "job_light_q_error_50_90_95_100": [float(np.percentile(qe, p)) for p in (50, 90, 95, 100)]}
