@@ -1016,8 +1016,10 @@ int k3_prepare(bc_model* m) {
         int limit0 = n_body;
         if (n_tail > 0) {
             const int hub = sched[n_body];
+            // (register accumulators: the message is written at the end of a run; a wider parent is updated in tensor memory
+            //  by every edge into it, so the tail edge must come before the first of them)
             for (int e = 0; e < n_body; ++e)
-                if (pa_of(e) == hub && (k->edges[e].flags & kRunLast)) { limit0 = e; break; }
+                if (pa_of(e) == hub && ((k->edges[e].flags & kRunLast) || !(k->edges[e].flags & kRegs))) { limit0 = e; break; }
         }
         for (int e = 0; e < n_body; ++e) {
             if (t == 0 && n_tail > 0 && e == limit0) k->seq.push_back((uint8_t)(128 | (n_body + t++)));

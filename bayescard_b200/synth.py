@@ -12,13 +12,18 @@ import numpy as np
 from .loader import TreeModel
 
 
-def make_tree_model(n_cols: int, card, seed: int = 0, alpha: float = 0.5, dtype=np.float64) -> TreeModel:
-    """``card`` is an int (every column) or a sequence of n_cols ints."""
+def make_tree_model(n_cols: int, card, seed: int = 0, alpha: float = 0.5, dtype=np.float64, parent=None) -> TreeModel:
+    """``card`` is an int (every column) or a sequence of n_cols ints; ``parent``: the tree (parent[0] = -1, parent[i] < i),
+    random when omitted."""
     rng = np.random.default_rng(seed)
     cards = np.full(n_cols, card, dtype=np.int32) if np.isscalar(card) else np.asarray(card, dtype=np.int32)
-    parent = np.full(n_cols, -1, dtype=np.int32)
-    for i in range(1, n_cols):
-        parent[i] = rng.integers(0, i)
+    if parent is None:
+        parent = np.full(n_cols, -1, dtype=np.int32)
+        for i in range(1, n_cols):
+            parent[i] = rng.integers(0, i)
+    else:
+        parent = np.asarray(parent, dtype=np.int32)
+        assert parent.shape == (n_cols,) and parent[0] == -1 and all(0 <= parent[i] < i for i in range(1, n_cols))
     cpts = []
     for v in range(n_cols):
         node_rng = np.random.default_rng([seed, v])

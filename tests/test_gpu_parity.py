@@ -304,6 +304,57 @@ def test_fused_kernel_wide_model_and_refusals():
     dw.close()
 
 
+K3_SHAPES = {
+    # name: (parent, cards) -- each one drives a different path of the fused kernel's epilogue / step sequence
+    "star_root_split": ([-1, 0, 0, 0, 0, 0, 0], [40, 50, 33, 64, 7, 50, 21]),            # no tail; the root's message in both epilogue groups (32 + 8 columns)
+    "chain": ([-1, 0, 1, 2, 3], [8, 40, 60, 50, 33]),                                     # every edge is the only message into its parent: tail = all but one
+    "root_two_internal": ([-1, 0, 0, 1, 1, 2, 2, 0], [30, 45, 52, 20, 61, 33, 17, 9]),    # the root's runs are interrupted: its message visits tensor memory
+    "hub_112_columns": ([-1, 0, 1, 1, 1, 1], [5, 110, 40, 50, 60, 70]),                   # a parent beyond the register accumulators: message (*)= D in tensor memory
+    "root_100_states": ([-1, 0, 0, 0, 3], [100, 20, 30, 40, 50]),                         # the same for the root + an internal child
+    "deep_hub_tail": ([-1, 0, 1, 2, 3, 3, 3, 3], [3, 12, 70, 84, 80, 9, 77, 50]),         # IMDB-2-like: hub under a chain of three
+    "two_hubs": ([-1, 0, 1, 1, 1, 0, 5, 5, 5], [6, 60, 30, 40, 50, 72, 20, 64, 33]),      # two internal children with leaves each
+}
+
+
+@pytest.mark.parametrize("shape", sorted(K3_SHAPES))
+@pytest.mark.parametrize("nq", [3000, 60000])
+def test_fused_kernel_tree_shapes(shape, nq):
+    """K3 on synthetic trees chosen to walk every branch of its planner and epilogue (register accumulators split over two warp
+    groups, tensor-memory fallback for wide parents, the root folded in registers or read from tensor memory, tail edges
+    interleaved with the next tile, one tile per CTA and several passes per CTA), BITS and DENSE_F32 rows, against the fp64 oracle."""
+    from bayescard_b200.synth import make_tree_model, pack_ranges_u16, random_range_queries
+
+    parent, cards = K3_SHAPES[shape]
+    tm = make_tree_model(len(cards), cards, seed=len(cards) * 7 + nq % 5, dtype=np.float32, parent=parent)
+    dm = DeviceModel(tm, device=0, specialize=False)
+    lo, hi = random_range_queries(tm, nq, seed=3, kmax=len(cards))
+    w = O.range_weights(tm, lo, hi)
+    ref = O.dense_tree(tm, w)
+    rows = pack_ranges_u16(lo, hi)
+    try:
+        got = dm.run_host(rows, L.DESC_RANGE_U16, None, L.KERNEL_FUSED)
+    except L.BayesCardError as e:
+        dm.close()
+        pytest.skip(f"K3 declines this model: {e}")
+    assert_close(got, ref, f"{shape}: BITS rows through the fused kernel")
+    # DENSE_F32 rows with fractional weights: every selected state's weight scaled by a per-(query, column) factor
+    rng = np.random.default_rng(5)
+    width = dm.dense_width
+    dense = np.zeros((nq, width), dtype=np.float32)
+    scale = 1.0
+    wf = []
+    for v in range(tm.n_nodes):
+        f = (0.25 + 0.75 * rng.random((nq, 1))).astype(np.float32)
+        wv = (np.asarray(w[v], dtype=np.float32) * f).astype(np.float32)
+        wf.append(wv.astype(np.float64))
+        o = int(dm.dense_offset[v])
+        dense[:, o:o + int(tm.card[v])] = wv
+    ref_d = O.dense_tree(tm, wf)
+    got_d = dm.run_host(dense, L.DESC_DENSE_F32, None, L.KERNEL_FUSED)
+    assert_close(got_d, ref_d, f"{shape}: DENSE rows through the fused kernel")
+    dm.close()
+
+
 @pytest.mark.parametrize("name", ["dmv", "census", "imdb1"])
 def test_synthetic_batch_generic_vs_spec_vs_oracle(name):
     """Config 2/5 generator: device == host twin bit for bit; both kernels vs the fp64 dense oracle."""
