@@ -77,6 +77,9 @@ _SIGS = {
     "bc_expand_packed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "bc_query_batch_packed_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p,
                                              C.c_void_p, C.c_int]),
+    "bc_query_batch_packed_host_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p,
+                                                    C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]),
+    "bc_pipe_wait": (C.c_int, [C.c_void_p, C.c_uint64]),
     "bc_expand_wsparse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "bc_query_batch_wsparse_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
                                               C.c_int]),

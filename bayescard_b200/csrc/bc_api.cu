@@ -52,7 +52,20 @@ struct BcHostPipe {
     uint32_t* d_blk[kSlots]{};
     uint32_t* d_pay[kSlots]{};
     size_t cap_pq = 0, cap_pay = 0;
+    // asynchronous submissions (bc_query_batch_packed_host_submit): chunks take slots round robin ACROSS calls
+    uint64_t n_chunks = 0;          // chunks enqueued so far = the ticket of the latest submission
+    bool pending = false;           // work of an un-waited submission may still be in flight
+    bool slot_used[kSlots]{};
 };
+
+// Everything enqueued on the pipe has finished (every chunk ends with its D2H on s_out): the synchronous pipelines start from here.
+static int pipe_quiesce(BcHostPipe* p) {
+    if (!p || !p->pending) return BC_OK;
+    BC_CUDA_CHECK(cudaStreamSynchronize(p->s_out));
+    p->pending = false;
+    for (bool& u : p->slot_used) u = false;
+    return BC_OK;
+}
 
 static void pipe_free(BcHostPipe* p) {
     if (!p) return;
@@ -523,6 +536,7 @@ extern "C" int bc_query_batch_host(bc_model* m, const void* desc, size_t nq, int
     chunk = chunk < 4096 ? 4096 : chunk;
     if (chunk > nq) chunk = nq;
     std::lock_guard<std::mutex> lock(m->pipe_mu);
+    if ((rc = pipe_quiesce(m->pipe))) return rc;   // (asynchronous PACKED submissions share the slots)
     rc = pipe_ensure(m, chunk, stride);
     if (rc) return rc;
     BcHostPipe* p = m->pipe;
@@ -681,7 +695,9 @@ static int sparse_host_impl(bc_model* m, const uint32_t* row_off, const uint32_t
         if (ne > max_entries) max_entries = ne;
     }
     std::lock_guard<std::mutex> lock(m->pipe_mu);
-    int rc = sparse_ensure(m, chunk, max_entries);
+    int rc = pipe_quiesce(m->pipe);   // (asynchronous PACKED submissions share the slots)
+    if (rc) return rc;
+    rc = sparse_ensure(m, chunk, max_entries);
     if (rc) return rc;
     BcHostPipe* p = m->pipe;
     PipeDrain drain(p);
@@ -853,9 +869,13 @@ extern "C" int bc_expand_packed(bc_model* m, const uint8_t* klen, const uint32_t
 // enqueue / event latency -- 1 M queries: one chunk 1.69e9 q/s, four chunks 1.42e9, sixteen 0.60e9), so a 1 M-query call
 // is one H2D copy of 15 MB, two kernels and one D2H copy; what it gains over SPARSE is the bytes: 15.4 B instead of 31 B per
 // Census query.
-extern "C" int bc_query_batch_packed_host(bc_model* m, const uint8_t* klen, const uint32_t* blk_off, const void* payload, size_t payload_bytes,
-                                          size_t nq, const uint32_t* fan_mask, float* out, int kernel) {
+// PACKED entries -> H2D -> expand -> infer -> D2H in chunks over the three slots.  `ticket` == nullptr: synchronous (returns when `out`
+// is complete).  Otherwise the call returns once everything is ENQUEUED and *ticket identifies the submission for
+// bc_pipe_wait: consecutive submissions then overlap (the copy of batch i + 1 runs under the kernels and the read-back of batch i).
+static int packed_host_run(bc_model* m, const uint8_t* klen, const uint32_t* blk_off, const void* payload, size_t payload_bytes, size_t nq,
+                           const uint32_t* fan_mask, float* out, int kernel, uint64_t* ticket) {
     if (!m || m->device < 0) { bc_set_error("model has no device (host-only model)"); return BC_EINVAL; }
+    if (ticket) *ticket = 0;
     if (nq == 0) return BC_OK;
     if (!klen || !blk_off || !payload || !out) { bc_set_error("klen/blk_off/payload/out is NULL"); return BC_EINVAL; }
     int w, cb, sb;
@@ -885,9 +905,14 @@ extern "C" int bc_query_batch_packed_host(bc_model* m, const uint8_t* klen, cons
         if (w1 - w0 > max_words) max_words = w1 - w0;
     }
     std::lock_guard<std::mutex> lock(m->pipe_mu);
-    rc = sparse_ensure(m, chunk, 1);
+    rc = pipe_streams(m);
     if (rc) return rc;
     BcHostPipe* p = m->pipe;
+    const size_t need_mask = chunk * m->mask_words * 4;
+    if (chunk > p->cap_sq || chunk > p->cap_q || need_mask > p->cap_mask || chunk > p->cap_pq || max_words * 4 > p->cap_pay)
+        if ((rc = pipe_quiesce(p))) return rc;   // buffers are about to be re-allocated: nothing may be in flight
+    rc = sparse_ensure(m, chunk, 1);
+    if (rc) return rc;
     if (chunk > p->cap_pq || max_words * 4 > p->cap_pay) {
         p->cap_pq = 0;
         p->cap_pay = 0;
@@ -903,12 +928,15 @@ extern "C" int bc_query_batch_packed_host(bc_model* m, const uint8_t* klen, cons
     }
     PipeDrain drain(p);
     for (size_t ci = 0; ci < nchunks; ++ci) {
-        const int s = (int)(ci % BcHostPipe::kSlots);
+        const int s = (int)(p->n_chunks % BcHostPipe::kSlots);
         const size_t q0 = ci * chunk, cq = (q0 + chunk <= nq) ? chunk : nq - q0;
         const size_t b0 = q0 / BC_PACKED_BLOCK, nb = (cq + BC_PACKED_BLOCK - 1) / BC_PACKED_BLOCK;
-        if (ci >= (size_t)BcHostPipe::kSlots) BC_CUDA_CHECK(cudaEventSynchronize(p->ev_out[s]));   // the slot's buffers are free again
+        if (p->slot_used[s]) BC_CUDA_CHECK(cudaEventSynchronize(p->ev_out[s]));   // the slot's buffers are free again
         const size_t w0 = ((size_t)blk_off[b0] * w) >> 5, w1 = (((size_t)blk_off[b0 + nb] * w + 31) >> 5) + 2;
         drain.armed = true;
+        p->pending = true;
+        p->slot_used[s] = true;
+        ++p->n_chunks;
         BC_CUDA_CHECK(cudaMemcpyAsync(p->d_klen[s], klen + q0, cq, cudaMemcpyHostToDevice, p->s_in));
         BC_CUDA_CHECK(cudaMemcpyAsync(p->d_blk[s], blk_off + b0, (nb + 1) * 4, cudaMemcpyHostToDevice, p->s_in));
         BC_CUDA_CHECK(cudaMemcpyAsync(p->d_pay[s], pay + w0, (w1 - w0) * 4, cudaMemcpyHostToDevice, p->s_in));
@@ -928,8 +956,47 @@ extern "C" int bc_query_batch_packed_host(bc_model* m, const uint8_t* klen, cons
         BC_CUDA_CHECK(cudaMemcpyAsync(out + q0, p->d_out[s], cq * 4, cudaMemcpyDeviceToHost, p->s_out));
         BC_CUDA_CHECK(cudaEventRecord(p->ev_out[s], p->s_out));
     }
+    if (ticket) {
+        *ticket = p->n_chunks;
+        drain.armed = false;
+        return BC_OK;
+    }
     BC_CUDA_CHECK(cudaStreamSynchronize(p->s_out));
+    p->pending = false;
+    for (bool& u : p->slot_used) u = false;
     drain.armed = false;
+    return BC_OK;
+}
+
+extern "C" int bc_query_batch_packed_host(bc_model* m, const uint8_t* klen, const uint32_t* blk_off, const void* payload, size_t payload_bytes,
+                                          size_t nq, const uint32_t* fan_mask, float* out, int kernel) {
+    return packed_host_run(m, klen, blk_off, payload, payload_bytes, nq, fan_mask, out, kernel, nullptr);
+}
+
+extern "C" int bc_query_batch_packed_host_submit(bc_model* m, const uint8_t* klen, const uint32_t* blk_off, const void* payload,
+                                                 size_t payload_bytes, size_t nq, const uint32_t* fan_mask, float* out, int kernel,
+                                                 uint64_t* ticket) {
+    if (!ticket) { bc_set_error("ticket is NULL"); return BC_EINVAL; }
+    if (m && nq && !is_pinned(out)) { bc_set_error("an asynchronous submission reads its results back into PINNED host memory"); return BC_EINVAL; }
+    return packed_host_run(m, klen, blk_off, payload, payload_bytes, nq, fan_mask, out, kernel, ticket);
+}
+
+extern "C" int bc_pipe_wait(bc_model* m, uint64_t ticket) {
+    if (!m || m->device < 0) { bc_set_error("model has no device (host-only model)"); return BC_EINVAL; }
+    if (ticket == 0) return BC_OK;
+    cudaEvent_t ev;
+    {
+        std::lock_guard<std::mutex> lock(m->pipe_mu);
+        BcHostPipe* p = m->pipe;
+        if (ticket > (p ? p->n_chunks : 0)) { bc_set_error("ticket %llu was not issued by this model", (unsigned long long)ticket); return BC_EINVAL; }
+        if (!p->pending) return BC_OK;
+        BC_CUDA_CHECK(cudaSetDevice(m->device));
+        if (ticket == p->n_chunks) return pipe_quiesce(p);
+        // chunks finish in order; the slot's event belongs to chunk ticket - 1 or to a later chunk that reused the slot (then it
+        // waits for more than it has to, never for less)
+        ev = p->ev_out[(ticket - 1) % BcHostPipe::kSlots];
+    }
+    BC_CUDA_CHECK(cudaEventSynchronize(ev));
     return BC_OK;
 }
 

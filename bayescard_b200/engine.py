@@ -247,6 +247,37 @@ class DeviceModel:
                                                    payload.nbytes, n, mask.ctypes.data if mask is not None else None, out.ctypes.data, kernel))
         return out
 
+    def submit_packed_host(self, klen: np.ndarray, blk_off: np.ndarray, payload: np.ndarray, out: np.ndarray,
+                           mask: Optional[np.ndarray] = None, kernel: int = L.KERNEL_AUTO) -> int:
+        """Asynchronous ``run_packed_host``: returns a ticket as soon as the batch is enqueued; ``out`` (pinned, float32[n]) is
+        complete after ``wait(ticket)``.  The arrays must be the caller's own contiguous buffers (nothing is copied) and stay
+        untouched until then.  Consecutive submissions overlap -- batch i + 1 is copied in while batch i is computed and read
+        back -- so a serving loop keeps two batches in flight::
+
+            t_prev = None
+            for bufs in batches:                      # double-buffered host memory
+                t = dm.submit_packed_host(*bufs.inputs, out=bufs.out)
+                if t_prev is not None: dm.wait(t_prev); consume(prev.out)
+                t_prev, prev = t, bufs
+        """
+        n = klen.size
+        for a, dt in ((klen, np.uint8), (blk_off, np.uint32), (payload, np.uint8), (out, np.float32)):
+            if a.dtype != dt or not a.flags["C_CONTIGUOUS"]:
+                raise ValueError("submit_packed_host takes contiguous arrays of the wire dtypes (no copies are made)")
+        if blk_off.size != (n + 127) // 128 + 1 or out.size != n:
+            raise ValueError("blk_off / out do not match klen")
+        if mask is not None and (mask.dtype != np.uint32 or not mask.flags["C_CONTIGUOUS"] or mask.size != n * self.mask_words):
+            raise ValueError("fan-out mask has the wrong dtype or size")
+        ticket = C.c_uint64()
+        L.check(L.lib().bc_query_batch_packed_host_submit(self._h, klen.ctypes.data if n else None, blk_off.ctypes.data, payload.ctypes.data,
+                                                          payload.nbytes, n, mask.ctypes.data if mask is not None else None, out.ctypes.data,
+                                                          kernel, C.byref(ticket)))
+        return int(ticket.value)
+
+    def wait(self, ticket: int) -> None:
+        """Blocks until the submission ``ticket`` (and every earlier one) has written its results."""
+        L.check(L.lib().bc_pipe_wait(self._h, int(ticket)))
+
     def gen_sparse_queries_host(self, seed: int, first: int, n: int, kmin: int, kmax: int):
         card = np.ascontiguousarray(self.tm.card, dtype=np.int32)
         row_off = np.zeros(n + 1, dtype=np.uint32)

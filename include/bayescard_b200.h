@@ -205,6 +205,15 @@ BC_API int bc_expand_packed(bc_model* m, const uint8_t* klen_dev, const uint32_t
  * three streams (H2D | expansion + inference | D2H overlap across chunks of a larger batch). */
 BC_API int bc_query_batch_packed_host(bc_model* m, const uint8_t* klen, const uint32_t* blk_off, const void* payload, size_t payload_bytes,
                                       size_t n_queries, const uint32_t* fanout_mask, float* out_prob, int kernel);
+/* Asynchronous form: returns when the batch is ENQUEUED (copies, expansion, inference, read-back on the model's three streams) and
+ * stores a ticket; `out` (PINNED host memory) is complete after bc_pipe_wait(m, ticket).  klen / blk_off / payload / fan_mask / out
+ * must stay untouched until then.  Consecutive submissions overlap: the H2D copy of batch i + 1 runs under the kernels and the
+ * read-back of batch i (a serving loop keeps two batches in flight).  Tickets complete in order; any synchronous *_host call on the
+ * same model first waits for everything submitted. */
+BC_API int bc_query_batch_packed_host_submit(bc_model* m, const uint8_t* klen, const uint32_t* blk_off, const void* payload,
+                                             size_t payload_bytes, size_t nq, const uint32_t* fan_mask, float* out, int kernel,
+                                             uint64_t* ticket);
+BC_API int bc_pipe_wait(bc_model* m, uint64_t ticket);
 
 /* ---- results beyond the fp32 range --------------------------------------------------------------------------------
  * The reference computes every product in fp64 (Pgmpy/inference/ExactInference.py:157-177, np.dot / np.prod on fp64

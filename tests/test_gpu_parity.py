@@ -582,6 +582,51 @@ def test_packed_wire_format_equals_sparse(name):
     assert dm.run_packed_host(klen[:0], blk[:1], payload[:8]).size == 0
 
 
+@pytest.mark.gpu
+def test_packed_submissions_in_flight():
+    """bc_query_batch_packed_host_submit / bc_pipe_wait: several batches enqueued back to back (more chunks than pipeline slots,
+    different sizes, so slots are reused and buffers re-allocated while work is in flight), results equal the synchronous call;
+    a synchronous call of another wire format in between first drains the pipe; pageable result buffers are refused."""
+    import os
+
+    import torch
+
+    dm = dev_model("census")
+    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
+    batches = []
+    for i, n in enumerate([128 * 40 + 5, 128 * 9, 128 * 64 + 77, 300, 128 * 40 + 5]):
+        row_off, entries = dm.gen_sparse_queries_host(20 + i, 0, n, 0, 12)
+        klen, blk, payload = dm.pack_sparse(row_off, entries)
+        want = dm.run_sparse_host(row_off, entries)
+        batches.append((pin(klen), pin(blk), pin(payload), pin(np.zeros(n, dtype=np.float32)), want, (row_off, entries)))
+    os.environ["BC_PACKED_CHUNK"] = "2048"   # 1-5 chunks per batch over three slots
+    try:
+        tickets = [dm.submit_packed_host(k, b, p, out=o) for k, b, p, o, _, _ in batches]
+        assert tickets == sorted(tickets) and tickets[0] > 0
+        dm.wait(tickets[1])
+        assert np.array_equal(batches[0][3], batches[0][4]) and np.array_equal(batches[1][3], batches[1][4])
+        dm.wait(tickets[-1])
+        for k, b, p, o, want, _ in batches:
+            assert np.array_equal(o, want)
+        # two in flight, then a synchronous call of another format: it waits for them first
+        for _, _, _, o, _, _ in batches:
+            o[:] = -1
+        t0 = dm.submit_packed_host(*batches[2][:3], out=batches[2][3])
+        t1 = dm.submit_packed_host(*batches[0][:3], out=batches[0][3])
+        again = dm.run_sparse_host(*batches[3][5])
+        assert np.array_equal(again, batches[3][4])
+        assert np.array_equal(batches[2][3], batches[2][4]) and np.array_equal(batches[0][3], batches[0][4])
+        dm.wait(t1)
+        dm.wait(t0)          # an old ticket: nothing to wait for
+        dm.wait(0)
+    finally:
+        del os.environ["BC_PACKED_CHUNK"]
+    with pytest.raises(L.BayesCardError, match="PINNED"):
+        dm.submit_packed_host(*batches[1][:3], out=np.zeros(batches[1][0].size, dtype=np.float32))
+    with pytest.raises(L.BayesCardError, match="not issued"):
+        dm.wait(10 ** 12)
+
+
 def _rare_equality_queries(m, nq, n_pred, seed, pairs=False):
     """Equality predicates on ``n_pred`` columns whose joint probability is far below the fp32 range: either many columns,
     each on a state from the rarer half of its CPT's row mass (``pairs=False``), or parent-child PAIRS where the child's
