@@ -12,11 +12,15 @@ has no exchange step, so no collective runs inside the timed region -- NCCL is u
 and the max-over-ranks reduction only).
 
   value        whole-job q/s, BITS descriptors (one bit per column state) already resident in HBM,
-               CUDA events around K steps
+               CUDA events around K steps; the steps are independent batches and are launched on two
+               streams in turn (--streams), so a launch's first CTAs fill the SMs the previous launch's
+               last round leaves idle; the one-stream figure is printed in roofline.single_stream
   sustained    the same launch repeated back to back for >= 2 s (clocks settle below the burst clock)
-  e2e          same metric through the host-buffer C-ABI call: pinned host queries -> H2D -> expand to
-               BITS -> kernel -> D2H of the fp32 results, all inside the timed region; `h2d_peak` is a
-               plain pinned cudaMemcpy of the same byte count measured in the same run on every rank
+  e2e          same metric through the host-buffer C-ABI: pinned host queries -> H2D -> expand to BITS ->
+               kernel -> D2H of the fp32 results, every step, all inside the timed region, two batches
+               in flight (submit step i, wait for step i - 1); the one-synchronous-call-per-step figure
+               beside it; `h2d_peak` is a plain pinned cudaMemcpy of the same byte count measured in
+               the same run on every rank
   roofline     dominant kernel: FMA-pipe issue slots against the FFMA rate measured in this same run
                (the kernel keeps the CPTs in the instruction stream; HBM view in roofline_hbm)
   dmv_large_batch   BASELINE configs[4]: --dmv-queries device-generated DMV range queries, sharded over
@@ -63,6 +67,7 @@ def parse_args():
     ap.add_argument("--sustained-seconds", type=float, default=2.0)
     ap.add_argument("--dmv-queries", type=float, default=1e9, help="total queries of the DMV large-batch leg (0 = skip)")
     ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--streams", type=int, default=2, help="launch consecutive (independent) steps on this many streams in turn")
     ap.add_argument("--inproc", action="store_true", help="add the in-process multi-GPU leg (one process, all visible GPUs)")
     return ap.parse_args()
 
@@ -576,8 +581,30 @@ def run_ours(args):
     torch.cuda.synchronize()
     del tmp
 
+    # Consecutive steps are independent batches: with --streams 2 they are launched on two streams in turn, so the first CTAs of
+    # step k + 1 fill the SMs that the last round of step k leaves idle (a launch of 90 us spends ~8 % of it ramping up and
+    # draining: ncu, FMA pipe 80.6 % of active but 72 % of elapsed cycles).  Each stream has its own result buffer.
+    n_streams = max(1, int(args.streams))
+    side = [torch.cuda.Stream(device=dev) for _ in range(n_streams - 1)]
+    lanes = [stream] + side
+    outs = [out] + [torch.empty(B, dtype=torch.float32, device=dev) for _ in side]
+    join_ev = [torch.cuda.Event() for _ in side]
+
     def step(k):
-        dm.run_device(descs[k % NBUF].data_ptr(), B, fmt, out.data_ptr(), kernel=kernel, stream=st)
+        lane = k % n_streams
+        dm.run_device(descs[k % NBUF].data_ptr(), B, fmt, outs[lane].data_ptr(), kernel=kernel, stream=lanes[lane].cuda_stream)
+
+    def fork():   # the side streams start after everything recorded on the main stream so far
+        if side:
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            for s_ in side:
+                s_.wait_event(ev)
+
+    def join():   # ... and the main stream continues after their last launch
+        for s_, ev in zip(side, join_ev):
+            ev.record(s_)
+            stream.wait_event(ev)
 
     # ---- FP32 peak of this device, measured before the timed region ---------------------------
     fp32_peak, _ = measure_fp32_peak(local)
@@ -585,16 +612,30 @@ def run_ours(args):
     # ---- device-resident throughput --------------------------------------------------------
     for k in range(max(args.warmup, 3)):
         step(k)
+    torch.cuda.synchronize()
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     time.sleep(0.25 if sampler else 0)
     launches0 = launch_count()
+    single_ms = None
+    if n_streams > 1:   # the same steps on ONE stream, for the record (every launch waits for the one before to drain)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a0.record(stream)
+        for k in range(args.steps):
+            dm.run_device(descs[k % NBUF].data_ptr(), B, fmt, out.data_ptr(), kernel=kernel, stream=st)
+        a1.record(stream)
+        barrier()
+        single_ms = max_over_ranks(a0.elapsed_time(a1))
+        launches0 = launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t0 = time.perf_counter()
     e0.record(stream)
+    fork()
     for k in range(args.steps):
         step(k)
+    join()
     e1.record(stream)
     barrier()
     t1 = time.perf_counter()
@@ -610,8 +651,10 @@ def run_ours(args):
         ts0 = time.perf_counter()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record(stream)
+        fork()
         for k in range(n_sus):
             step(k)
+        join()
         s1.record(stream)
         barrier()
         ts1 = time.perf_counter()
@@ -759,6 +802,12 @@ def run_ours(args):
             "kernel": kname, "what": "FMA-pipe issue-slot fraction",
             "fma_issue_slots_per_query": slots_q, "flop_per_query_counted": flop_q, "flop_per_query_dense": dm.flops_dense,
             "peak_source": "FFMA micro-benchmark (bc_measure_fp32_peak) in this run",
+            "launch_overlap": (f"consecutive steps (independent batches) are launched on {n_streams} streams in turn: the first CTAs of a launch fill the "
+                               "SMs the last round of the launch before leaves idle; achieved = flops of the K steps / time of the timed region"
+                               if n_streams > 1 else "one stream"),
+            "single_stream": ({"value": world * B * args.steps / (single_ms * 1e-3), "ms_per_step": single_ms / args.steps,
+                               "frac": (flop_q * B / (single_ms * 1e-3 / args.steps) / 1e12 / fp32_peak) if fp32_peak else None}
+                              if single_ms else None),
             "note": "achieved = FMA-pipe instructions the generated kernel contains per query (one per non-zero CPT entry: "
                     "FFMA, or a predicated FADD / seed FMUL that occupies the same pipe slot) x 2 flop x q/s; predicated-off "
                     "instructions still occupy their issue slot, so this is pipe utilisation, not useful flops; exact zeros "
@@ -776,7 +825,7 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": cfg,
-            "path": {"descriptor": "BITS (resident) / PACKED bit-packed entries (e2e)", "bytes_per_query": bytes_q,
+            "path": {"descriptor": "BITS (resident) / PACKED bit-packed entries (e2e)", "bytes_per_query": bytes_q, "streams": n_streams,
                      "l2": f"inputs rotate over {NBUF} resident batches = {NBUF * B * stride / 1e6:.0f} MB > 126 MB L2",
                      "kernel": roof["kernel"], "parallelism": f"replica x{world}, batch sharded, no collective"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": B * 4,
