@@ -403,6 +403,33 @@ class ShardedModel:
 
         return self._fan_out(n, work, align=128, out=out)
 
+    def submit_packed_host(self, klen: np.ndarray, blk_off: np.ndarray, payload: np.ndarray, out: np.ndarray,
+                           mask: Optional[np.ndarray] = None, kernel: int = L.KERNEL_AUTO):
+        """Asynchronous ``run_packed_host``: every replica's slice is enqueued on its device (``DeviceModel.submit_packed_host``,
+        from the replica's own host thread) and the tickets come back; ``out`` (pinned) is complete after ``wait(tickets)``.
+        Two batches in flight per device overlap each device's next copy with its kernels and read-back."""
+        n = klen.size
+        if mask is not None:
+            mask = mask.reshape(n, self.mask_words)
+        parts = [(rep, a, b) for rep, (a, b) in zip(self.replicas, self.split(n, len(self.replicas), 128)) if b > a]
+        futs = [self._pool.submit(rep.submit_packed_host, klen[a:b], blk_off[a // 128:(b + 127) // 128 + 1], payload, out[a:b],
+                                  None if mask is None else mask[a:b].reshape(-1), kernel) for rep, a, b in parts]
+        tickets, err = [], None
+        for (rep, _, _), f in zip(parts, futs):
+            e = f.exception()
+            if e is None:
+                tickets.append((rep, f.result()))
+            elif err is None:
+                err = e
+        if err is not None:
+            self.wait(tickets)   # nothing may still write into `out` when the error surfaces
+            raise err
+        return tickets
+
+    def wait(self, tickets) -> None:
+        for rep, t in tickets:
+            rep.wait(t)
+
     def close(self):
         self._pool.shutdown(wait=True)
         for r in self.replicas:

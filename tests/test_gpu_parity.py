@@ -743,6 +743,18 @@ def test_sharded_model_same_device():
     klen, blk, payload = dm.pack_sparse(row_off, entries)
     assert np.array_equal(sm.run_packed_host(klen, blk, payload), want)
     assert sm.run_sparse_host(np.zeros(1, dtype=np.uint32), np.zeros(0, dtype=np.uint32)).size == 0
+    # asynchronous submissions: two batches in flight on every replica
+    import torch
+
+    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
+    pk, pb, pp = pin(klen), pin(blk), pin(payload)
+    outs = [pin(np.zeros(n, dtype=np.float32)) for _ in range(2)]
+    t0 = sm.submit_packed_host(pk, pb, pp, out=outs[0])
+    t1 = sm.submit_packed_host(pk, pb, pp, out=outs[1])
+    sm.wait(t0)
+    assert np.array_equal(outs[0], want)
+    sm.wait(t1)
+    assert np.array_equal(outs[1], want)
     sm.close()
 
 
