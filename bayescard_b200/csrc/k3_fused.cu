@@ -533,7 +533,13 @@ __global__ void __launch_bounds__(kThreads, 1) k3_kernel(const __grid_constant__
                     tc_fence_after();
                 }
                 for (int kb = 0; kb < nkb; ++kb, ++it, ++step_in_tile, ra.next(P.a_stages), rw.next(P.w_stages)) {
-                    if ((it % (uint32_t)kGroups) != (uint32_t)g) continue;
+                    if ((it % (uint32_t)kGroups) != (uint32_t)g) {
+                        // Parity waits only tell ADJACENT phases apart: a group that writes a slot every other time it comes round
+                        // (slots not a multiple of the groups) must still see every phase of the slot's barrier, or its own wait
+                        // two phases later passes on the stale parity and it overwrites an operand the MMAs have not read yet.
+                        if (P.a_stages % kGroups != 0) mbar_wait(a_empty0 + 8 * ra.s, ra.par ^ 1u);
+                        continue;
+                    }
                     const int c0 = kb * kBK;
                     if ((warp & 3) == 0) K3_STEP(0);
                     float u[kBK], lv[kBK];
