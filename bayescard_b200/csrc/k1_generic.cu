@@ -177,9 +177,13 @@ __global__ void __launch_bounds__(512) k1_kernel(const K1Params P) {
                     constrained |= !((sdesc32[b >> 5] >> (b & 31)) & 1u);
                 if (fm && ((fm[v >> 5] >> (v & 31)) & 1u) && nd.fan_off >= 0) constrained = true;
                 if (constrained) {
+                    // lanes climbing from different evidence nodes meet on the way up: the mark is set with an atomic OR on the
+                    // byte's word (act is 16-byte aligned per warp), the first lane to arrive goes on, the others stop
                     int u = v;
-                    while (u >= 0 && !act[u]) {
-                        act[u] = 1;
+                    while (u >= 0) {
+                        const unsigned bit = 1u << (8 * (u & 3));
+                        const unsigned old = atomicOr(reinterpret_cast<unsigned*>(const_cast<unsigned char*>(act)) + (u >> 2), bit);
+                        if (old & (0xFFu << (8 * (u & 3)))) break;
                         u = s_nodes[u].parent;
                     }
                 }
@@ -225,9 +229,13 @@ __global__ void __launch_bounds__(512) k1_kernel(const K1Params P) {
                 bool constrained = lo > 0 || hi < nd.card - 1;
                 if (fm && ((fm[v >> 5] >> (v & 31)) & 1u) && nd.fan_off >= 0) constrained = true;
                 if (constrained) {
+                    // lanes climbing from different evidence nodes meet on the way up: the mark is set with an atomic OR on the
+                    // byte's word (act is 16-byte aligned per warp), the first lane to arrive goes on, the others stop
                     int u = v;
-                    while (u >= 0 && !act[u]) {
-                        act[u] = 1;
+                    while (u >= 0) {
+                        const unsigned bit = 1u << (8 * (u & 3));
+                        const unsigned old = atomicOr(reinterpret_cast<unsigned*>(const_cast<unsigned char*>(act)) + (u >> 2), bit);
+                        if (old & (0xFFu << (8 * (u & 3)))) break;
                         u = s_nodes[u].parent;
                     }
                 }
