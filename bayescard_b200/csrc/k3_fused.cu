@@ -111,6 +111,7 @@ struct K3Params {
     // (the chain at the top of the tree is folded under the next tile's leaves; see k3_prepare)
     uint8_t seq[kMaxEdges + 1];
     int n_seq, n_tail;
+    int prefetch;              // fetch the next tile's BITS rows / mask words one pass ahead (BC_K3_NO_PREFETCH=1 turns it off)
     const uint8_t* bimg;
     const uint8_t* desc;
     size_t dstride;
@@ -493,6 +494,30 @@ __global__ void __launch_bounds__(kThreads, 1) k3_kernel(const __grid_constant__
         const uint32_t sw = (uint32_t)ql & 7u;    // 128-byte swizzle: chunk j of row r lives at r * 128 + ((j ^ (r & 7)) << 4)
         Ring ra, rw;
         uint32_t it = 0;
+        // A tile's BITS rows and fan-out mask words come from global memory, in front of the pass with their latency exposed (every
+        // producer warp waits on the barrier behind them).  The mask word is fetched ONE PASS AHEAD into a register and only written
+        // to shared memory at the start of its own pass.
+        constexpr int kPre = 2;   // uint4 per thread kept in registers
+        // Measured on one box (tools/runs/_r2_run54.sh): the mask word ahead is +2.7 % on DENSE + fan-out rows; the BITS rows ahead
+        // (8 more live registers in the producers, at the 96-register cap) are -3 % -- so only the mask word travels ahead.
+        const bool pre_ok = P.prefetch && FMT != BC_DESC_BITS && P.mask_words <= 1;
+        uint4 nb[kPre];
+        uint32_t nfm = 0;
+#pragma unroll
+        for (int i = 0; i < kPre; ++i) nb[i] = make_uint4(0u, 0u, 0u, 0u);
+        auto fetch = [&](long long tile_f) {   // global -> registers
+            const size_t q = (size_t)tile_f * kTile + ql;
+            const size_t qc = q < P.nq ? q : P.nq - 1;
+            if (FMT == BC_DESC_BITS) {
+                const uint32_t* grow = reinterpret_cast<const uint32_t*>(P.desc + qc * P.dstride);
+#pragma unroll
+                for (int i = 0; i < kPre; ++i) {
+                    const int w4 = 4 * g + 4 * kGroups * i;
+                    if (w4 < P.bits_words) nb[i] = __ldg(reinterpret_cast<const uint4*>(grow + w4));
+                }
+            }
+            if (P.fan_mask != nullptr && g == 0) nfm = __ldg(P.fan_mask + qc * (size_t)P.mask_words);
+        };
         for (uint32_t iter = 0;; ++iter) {
             K3_PASS_HEAD
             if (cur_ok) {
@@ -502,19 +527,37 @@ __global__ void __launch_bounds__(kThreads, 1) k3_kernel(const __grid_constant__
                 const uint32_t buf = iter & 1u;
                 uint32_t* bits_t = s_bits + buf * bits_tile;
                 uint32_t* fm_t = s_fm + buf * fm_tile;
+                if (pre_ok && iter == 0) fetch(tile_cur);
                 if (iter >= 2) mbar_wait(bits_free0 + 8 * buf, ((iter >> 1) - 1u) & 1u);   // the epilogue warps are done with the tile that used this buffer
-                if (FMT == BC_DESC_BITS) {
-                    const uint32_t* grow = reinterpret_cast<const uint32_t*>(P.desc + qc * P.dstride);
-                    for (int w4 = 4 * g; w4 < P.bits_words; w4 += 4 * kGroups) {   // bits_words is a multiple of 4
-                        const uint4 x = __ldg(reinterpret_cast<const uint4*>(grow + w4));
-                        bits_t[(w4 + 0) * kTile + ql] = x.x;
-                        bits_t[(w4 + 1) * kTile + ql] = x.y;
-                        bits_t[(w4 + 2) * kTile + ql] = x.z;
-                        bits_t[(w4 + 3) * kTile + ql] = x.w;
+                if (pre_ok) {
+                    if (FMT == BC_DESC_BITS) {
+#pragma unroll
+                        for (int i = 0; i < kPre; ++i) {
+                            const int w4 = 4 * g + 4 * kGroups * i;
+                            if (w4 < P.bits_words) {
+                                bits_t[(w4 + 0) * kTile + ql] = nb[i].x;
+                                bits_t[(w4 + 1) * kTile + ql] = nb[i].y;
+                                bits_t[(w4 + 2) * kTile + ql] = nb[i].z;
+                                bits_t[(w4 + 3) * kTile + ql] = nb[i].w;
+                            }
+                        }
                     }
+                    if (P.fan_mask != nullptr && g == 0) fm_t[ql] = nfm;
+                    if (tile_cur + (long long)gridDim.x < P.n_tiles) fetch(tile_cur + (long long)gridDim.x);   // the next pass's tile
+                } else {
+                    if (FMT == BC_DESC_BITS) {
+                        const uint32_t* grow = reinterpret_cast<const uint32_t*>(P.desc + qc * P.dstride);
+                        for (int w4 = 4 * g; w4 < P.bits_words; w4 += 4 * kGroups) {   // bits_words is a multiple of 4
+                            const uint4 x = __ldg(reinterpret_cast<const uint4*>(grow + w4));
+                            bits_t[(w4 + 0) * kTile + ql] = x.x;
+                            bits_t[(w4 + 1) * kTile + ql] = x.y;
+                            bits_t[(w4 + 2) * kTile + ql] = x.z;
+                            bits_t[(w4 + 3) * kTile + ql] = x.w;
+                        }
+                    }
+                    if (P.fan_mask != nullptr && g == 0)
+                        for (int w = 0; w < P.mask_words; ++w) fm_t[w * kTile + ql] = __ldg(P.fan_mask + qc * (size_t)P.mask_words + w);
                 }
-                if (P.fan_mask != nullptr && g == 0)
-                    for (int w = 0; w < P.mask_words; ++w) fm_t[w * kTile + ql] = __ldg(P.fan_mask + qc * (size_t)P.mask_words + w);
             }
             asm volatile("bar.sync 1, %0;" ::"n"(32 * kWarpEpi) : "memory");   // the eight producer warps
             int step_in_tile = 0;
@@ -583,15 +626,27 @@ __global__ void __launch_bounds__(kThreads, 1) k3_kernel(const __grid_constant__
                     }
                     // States >= K of the last block: their rows of T_v^T are zeros in the operand image and whole k-steps past K are not
                     // issued, so any FINITE value there contributes 0 -- BITS rows (bits past the domain are cleared, the message's
-                    // padding columns hold the zeros the epilogue wrote) need no masking at all.  DENSE rows could carry NaN / Inf in
-                    // the next column or in caller-owned row padding: zeroed by one compare + select per state.  (The old
-                    // per-element compare + select over all 32 states was 7.5 % of the instructions of this issue-bound kernel:
-                    // ncu, profiles/r2_ncu_36_k3_bits_imdb1.json.)
-                    if (FMT == BC_DESC_DENSE_F32 && c0 + kBK > K) {
-                        int valid = K - c0;
-                        asm volatile("" : "+r"(valid));   // a vector register: one ISETP + one FSEL per state instead of the uniform-predicate dance
-#pragma unroll
-                        for (int j = 0; j < kBK; ++j) u[j] = j < valid ? u[j] : 0.f;
+                    // padding columns hold the zeros the epilogue wrote) need no masking at all.  In a DENSE row the floats past the
+                    // domain are the column's own pad floats (caller-owned: could be NaN / Inf), then the NEXT column's weights (if
+                    // those are not finite the query's result is not finite anyway) and, past the row, the zeros TMA fills in.
+                    // (The first version's compare + select over all 32 states was 7.5 % of the instructions of this issue-bound
+                    // kernel: ncu, profiles/r2_ncu_36_k3_bits_imdb1.json.)
+                    if (FMT == BC_DESC_DENSE_F32 && (K & 3) != 0 && c0 + kBK > K) {
+                        // only the column's own pad floats (a column occupies round_up(card, 4) floats of the row) can hold anything
+                        // the caller did not mean: one float4 group, picked by a uniform switch
+                        const int r = K - c0, k = r & 3;   // first state past the domain, 1 <= k <= 3 inside its group
+#define K3_MASK_GROUP(G)                                              \
+    case G:                                                           \
+        if (k <= 1) u[4 * G + 1] = 0.f;                               \
+        if (k <= 2) u[4 * G + 2] = 0.f;                               \
+        u[4 * G + 3] = 0.f;                                           \
+        break;
+                        switch (r >> 2) {
+                            K3_MASK_GROUP(0) K3_MASK_GROUP(1) K3_MASK_GROUP(2) K3_MASK_GROUP(3)
+                            K3_MASK_GROUP(4) K3_MASK_GROUP(5) K3_MASK_GROUP(6) K3_MASK_GROUP(7)
+                            default: break;
+                        }
+#undef K3_MASK_GROUP
                     }
                     const uint32_t a_hi = tlane + (uint32_t)(P.a_col + (int)ra.s * 64);
                     if ((warp & 3) == 0) K3_STEP(2);
@@ -1134,6 +1189,7 @@ int bc_k3_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32
     std::memcpy(P.edge, k->edges.data(), sizeof(K3Edge) * k->edges.size());
     P.n_seq = (int)k->seq.size();
     P.n_tail = k->n_tail;
+    P.prefetch = std::getenv("BC_K3_NO_PREFETCH") ? 0 : 1;
     std::memcpy(P.seq, k->seq.data(), k->seq.size());
     P.bimg = k->d_bimg;
     P.desc = static_cast<const uint8_t*>(desc);

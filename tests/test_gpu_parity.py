@@ -340,8 +340,7 @@ def test_fused_kernel_tree_shapes(shape, nq):
     # DENSE_F32 rows with fractional weights: every selected state's weight scaled by a per-(query, column) factor
     rng = np.random.default_rng(5)
     width = dm.dense_width
-    dense = np.zeros((nq, width), dtype=np.float32)
-    scale = 1.0
+    dense = np.full((nq, width), np.nan, dtype=np.float32)   # the pad floats between columns are the caller's: whatever they hold must not matter
     wf = []
     for v in range(tm.n_nodes):
         f = (0.25 + 0.75 * rng.random((nq, 1))).astype(np.float32)

@@ -1,0 +1,17 @@
+#!/bin/bash
+# round 2, run 55: K3 DENSE rows: only the column's own pad floats are masked (NaN pads in the test rows); mask word fetched ahead
+timeout 300 python -m pytest tests/test_gpu_parity.py -x -q --tb=short -k "fused or FUSED or k3 or tensor or census_through or tree_shapes" 2>&1 | tail -4
+for rep in 1 2; do
+timeout 100 python tools/k3_check.py --models imdb1,imdb3,dmv --nq 1048576 --skip-parity 2>&1 | python -c "
+import sys,json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print('  ', d['model'], [d.get(k) for k in ('bits_k3_qps','dense_k3_qps','dense_fan_k3_qps')])
+"
+done
+timeout 100 python tools/k3_check.py --models imdb1 --nq 262144 --skip-parity --reps 20 2>&1 | python -c "
+import sys,json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print('   262144', d['model'], [d.get(k) for k in ('bits_k3_qps','dense_k3_qps','dense_fan_k3_qps')])
+"
