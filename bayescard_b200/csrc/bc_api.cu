@@ -327,6 +327,23 @@ static int check_format(const bc_model* m, int fmt) {
     return BC_OK;
 }
 
+// K3 reads BITS or DENSE_F32 rows: range rows are converted into stream-ordered scratch first
+static int fused_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32_t* fan_mask, float* out, cudaStream_t st,
+                        int32_t* out_exp) {
+    if (fmt != BC_DESC_RANGE_U8 && fmt != BC_DESC_RANGE_U16) return bc_k3_launch(m, desc, nq, fmt, fan_mask, out, st, out_exp);
+    {   // (decline before allocating anything when the model is not served)
+        int32_t info[8];
+        int rc = bc_model_fused_plan(m, info, nullptr, 0);
+        if (rc) return rc;
+    }
+    void* scratch = nullptr;
+    BC_CUDA_CHECK(cudaMallocAsync(&scratch, nq * (size_t)m->bits_words * 4, st));
+    int rc = bc_convert_launch(m, desc, fmt, scratch, BC_DESC_BITS, nq, st);
+    if (rc == BC_OK) rc = bc_k3_launch(m, scratch, nq, BC_DESC_BITS, fan_mask, out, st, out_exp);
+    cudaFreeAsync(scratch, st);
+    return rc;
+}
+
 extern "C" int bc_query_batch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32_t* fan_mask,
                               float* out, int kernel, void* stream) {
     if (!m || m->device < 0) { bc_set_error("model has no device (host-only model)"); return BC_EINVAL; }
@@ -368,16 +385,7 @@ extern "C" int bc_query_batch(bc_model* m, const void* desc, size_t nq, int fmt,
             return rc;
         }
     }
-    if (kernel == BC_KERNEL_FUSED) {
-        auto launch = bc_k3_launch;
-        if (!is_range) return launch(m, desc, nq, fmt, fan_mask, out, st);
-        void* scratch = nullptr;   // range rows -> BITS rows in stream-ordered scratch
-        BC_CUDA_CHECK(cudaMallocAsync(&scratch, nq * (size_t)m->bits_words * 4, st));
-        rc = bc_convert_launch(m, desc, fmt, scratch, BC_DESC_BITS, nq, st);
-        if (rc == BC_OK) rc = launch(m, scratch, nq, BC_DESC_BITS, fan_mask, out, st);
-        cudaFreeAsync(scratch, st);
-        return rc;
-    }
+    if (kernel == BC_KERNEL_FUSED) return fused_launch(m, desc, nq, fmt, fan_mask, out, st, nullptr);
     if (kernel == BC_KERNEL_GEMM || kernel == BC_KERNEL_GEMM_SIMT)
         return bc_k2_launch(m, desc, nq, fmt, fan_mask, out, kernel == BC_KERNEL_GEMM, st);
     // no image: large domains go to the batched path (K1 re-reads every CPT once per query)
@@ -398,12 +406,19 @@ extern "C" int bc_query_batch_scaled(bc_model* m, const void* desc, size_t nq, i
     BC_CUDA_CHECK(cudaSetDevice(m->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool is_range = fmt == BC_DESC_RANGE_U8 || fmt == BC_DESC_RANGE_U16;
+    if (kernel == BC_KERNEL_AUTO && nq > 32 && m->flops_dense >= 20000 && m->n <= 128 && m->max_card <= 256) {
+        // the fused tensor-core kernel where it serves the model (it carries the exponent through its epilogue); it declines what
+        // does not fit tensor memory
+        rc = fused_launch(m, desc, nq, fmt, fan_mask, out_mant, st, out_exp);
+        if (rc != BC_ELIMIT) return rc;
+    }
     if (kernel == BC_KERNEL_AUTO)   // large domains: the batched path (K1 re-reads every CPT once per query)
         kernel = (is_range && !fan_mask && (m->max_card > 256 || m->lam_total > 4096)) ? BC_KERNEL_GEMM : BC_KERNEL_GENERIC;
     if (kernel == BC_KERNEL_GEMM || kernel == BC_KERNEL_GEMM_SIMT)
         return bc_k2_launch(m, desc, nq, fmt, fan_mask, out_mant, kernel == BC_KERNEL_GEMM, st, out_exp);
     if (kernel == BC_KERNEL_GENERIC) return bc_k1_launch(m, desc, nq, fmt, fan_mask, out_mant, st, out_exp);
-    bc_set_error("scaled results are served by BC_KERNEL_GENERIC and BC_KERNEL_GEMM(_SIMT), not by kernel %d", kernel);
+    if (kernel == BC_KERNEL_FUSED) return fused_launch(m, desc, nq, fmt, fan_mask, out_mant, st, out_exp);
+    bc_set_error("scaled results are served by BC_KERNEL_GENERIC, BC_KERNEL_FUSED and BC_KERNEL_GEMM(_SIMT), not by kernel %d", kernel);
     return BC_EINVAL;
 }
 

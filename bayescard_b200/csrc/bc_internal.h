@@ -133,7 +133,8 @@ int bc_k2_umma_edge(bc_model* m, const uint8_t* desc, size_t dstride, int fmt, s
                     float* lam_v_lo, int ld_v, float* lam_pa, int ld_pa, int accumulate, cudaStream_t stream);
 void bc_k2_umma_free(bc_model* m);
 // k3_fused.cu: whole tree per 128-query tile on the tensor cores (BITS / DENSE_F32 rows); BC_ELIMIT = model not served
-int bc_k3_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32_t* fan_mask, float* out, cudaStream_t stream);
+int bc_k3_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32_t* fan_mask, float* out, cudaStream_t stream,
+                 int32_t* out_exp = nullptr);   // out_exp: scaled results (mantissa in out, exponent of two per query)
 void bc_k3_free(bc_model* m);
 // spec_codegen.cc
 std::string bc_spec_generate(const bc_model& m);

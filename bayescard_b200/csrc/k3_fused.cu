@@ -122,6 +122,7 @@ struct K3Params {
     const float* root_T;       // T_root in the arena
     int root_card, root_col, root_bit_off, root_lam_off, root_fan_off;
     float* out;
+    int32_t* out_exp;          // scaled results (k3_kernel<FMT, true>): out[q] * 2^out_exp[q]
     size_t nq;
     long long n_tiles;
     int bits_words;
@@ -341,7 +342,7 @@ struct Ring {   // slot / parity cursor of a ring of `n` slots advanced once per
     }
 };
 
-template <int FMT>
+template <int FMT, bool SCALED>
 __global__ void __launch_bounds__(kThreads, 1) k3_kernel(const __grid_constant__ K3Params P, const __grid_constant__ CUtensorMap tm_w) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -366,6 +367,8 @@ __global__ void __launch_bounds__(kThreads, 1) k3_kernel(const __grid_constant__
     p += 256;
     float* s_part = reinterpret_cast<float*>(p);    // the second epilogue group's share of the root's dot product, two tiles
     p += 2 * kTile * 4;
+    float* s_max = reinterpret_cast<float*>(p);     // SCALED: row maxima exchanged between the two epilogue groups [exchange parity][group][query]
+    p += 4 * kTile * 4;
     uint64_t* bars = reinterpret_cast<uint64_t*>(p);
     const uint32_t a_full0 = smem_u32(bars), a_empty0 = a_full0 + 8 * kMaxStages, b_full0 = a_empty0 + 8 * kMaxStages,
                    b_empty0 = b_full0 + 8 * kMaxStages, w_full0 = b_empty0 + 8 * kMaxStages, w_empty0 = w_full0 + 8 * kStagesW,
@@ -694,13 +697,37 @@ __global__ void __launch_bounds__(kThreads, 1) k3_kernel(const __grid_constant__
         float acc[kAcc];
 #pragma unroll
         for (int i = 0; i < kAcc; ++i) acc[i] = 0.f;
+        // SCALED (results beyond the fp32 range, reference arithmetic: fp64, ExactInference.py:157-177): after every update the
+        // message is renormalised to a row maximum in [1, 2) -- an exact power-of-two scale, agreed between the two epilogue
+        // groups through shared memory -- and the exponent is added to the tile's exponent (this tile's, or the previous tile's for
+        // a tail edge); the result leaves as mantissa and exponent.
+        int ex_cur = 0, ex_prev = 0;
+        uint32_t xc = 0;   // exchanges so far (parity = buffer)
+        auto scale_of = [&](float m_local, bool both, int& e_out) -> float {   // 2^-e, e = exponent of the row maximum
+            float M = m_local;
+            if (both) {
+                float* mine = s_max + ((xc & 1u) * 2u + (uint32_t)g) * kTile;
+                float* theirs = s_max + ((xc & 1u) * 2u + (uint32_t)(g ^ 1)) * kTile;
+                mine[ql] = m_local;
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                M = fmaxf(M, theirs[ql]);
+                ++xc;
+            }
+            const int eb = (int)((__float_as_uint(M) >> 23) & 0xFFu);
+            int e_ = (eb == 0 || eb == 0xFF) ? 0 : eb - 127;   // zero / subnormal / non-finite rows are left alone
+            if (e_ > 126) e_ = 126;
+            e_out = e_;
+            return __uint_as_float((uint32_t)(127 - e_) << 23);
+        };
         for (uint32_t iter = 0;; ++iter) {
             K3_PASS_HEAD
+            if (SCALED) { ex_prev = ex_cur; ex_cur = 0; }
             for (int si = 0; si < P.n_seq; ++si) {
                 K3_STEP_HEAD
                 const K3Edge& E = P.edge[e];
                 const uint32_t db = P.n_dbuf == 2 ? (ed & 1u) : 0u, dpar = (P.n_dbuf == 2 ? (ed >> 1) : ed) & 1u;
                 ++ed;   // (executed steps only)
+                int& ex = back ? ex_prev : ex_cur;
                 const uint32_t dcol = tlane + (uint32_t)(P.d_col + (int)db * P.d_stride), pcol = tlane + (uint32_t)E.col_pa;
                 const bool first = E.first, run_first = (E.flags & kRunFirst) != 0, run_last = (E.flags & kRunLast) != 0;
                 const bool regs = (E.flags & kRegs) != 0, root = E.publish == -2;
@@ -755,6 +782,22 @@ __global__ void __launch_bounds__(kThreads, 1) k3_kernel(const __grid_constant__
                             }
                         }
                     }
+                    if (SCALED) {
+                        float mloc = 0.f;
+#pragma unroll
+                        for (int r = 0; r < kAcc / 8; ++r)
+                            if (lo + 8 * r < hi) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) mloc = fmaxf(mloc, acc[8 * r + i]);
+                            }
+                        int e_;
+                        const float sc = scale_of(mloc, mid < n8, e_);
+                        if (e_ != 0) {
+#pragma unroll
+                            for (int i = 0; i < kAcc; ++i) acc[i] *= sc;
+                        }
+                        ex += e_;
+                    }
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(d_empty0 + 8 * db);   // the accumulator has been read: the MMAs of the edge after next may start
@@ -799,6 +842,30 @@ __global__ void __launch_bounds__(kThreads, 1) k3_kernel(const __grid_constant__
                             if (j + 8 < hi) tmem_st8(pcol + (uint32_t)(j + 8), dv + 8);
                         }
                         tmem_st_wait();
+                        if (SCALED) {   // second and third pass over the message's own columns: maximum, then the scale
+                            float mloc = 0.f;
+                            for (int j = lo; j < hi; j += 8) {
+                                float lv[8];
+                                tmem_ld8(pcol + (uint32_t)j, lv);
+                                tmem_ld_wait();
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) mloc = fmaxf(mloc, lv[i]);
+                            }
+                            int e_;
+                            const float sc = scale_of(mloc, mid < n8, e_);
+                            // (every thread has its own exponent; the tcgen05 loads and stores are warp-wide instructions, so the
+                            //  pass is unconditional: a thread with nothing to scale multiplies by 1)
+                            for (int j = lo; j < hi; j += 8) {
+                                float lv[8];
+                                tmem_ld8(pcol + (uint32_t)j, lv);
+                                tmem_ld_wait();
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) lv[i] *= sc;
+                                tmem_st8(pcol + (uint32_t)j, lv);
+                            }
+                            tmem_st_wait();
+                            ex += e_;
+                        }
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) {
@@ -860,7 +927,10 @@ __global__ void __launch_bounds__(kThreads, 1) k3_kernel(const __grid_constant__
                         asm volatile("bar.sync 2, 256;" ::: "memory");
                         if (!g) res += s_part[buf * kTile + ql];
                     }
-                    if (!g && q < P.nq) P.out[q] = res;
+                    if (!g && q < P.nq) {
+                        P.out[q] = res;
+                        if (SCALED) P.out_exp[q] = ex;
+                    }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bits_free0 + 8 * buf);   // this tile's BITS rows / mask words are no longer read
                 }
@@ -1120,7 +1190,7 @@ int k3_prepare(bc_model* m) {
     int w_stages = 4;
     if (const char* e = std::getenv("BC_K3_WSTAGES")) w_stages = std::max(2, std::min(kStagesW, std::atoi(e)));
     const size_t per_fmt = std::max((size_t)w_stages * kWBytes, (size_t)2 * m->bits_words * kTile * 4);
-    const size_t fixed = per_fmt + (size_t)2 * m->mask_words * kTile * 4 + fan_floats * 4 + 256 /* nibble table */ + 2 * kTile * 4 /* root partial sums */ +
+    const size_t fixed = per_fmt + (size_t)2 * m->mask_words * kTile * 4 + fan_floats * 4 + 256 /* nibble table */ + 2 * kTile * 4 /* root partial sums */ + 4 * kTile * 4 /* row maxima (scaled results) */ +
                          8 * (4 * kMaxStages + 2 * kStagesW + 8 + kMaxEdges + 2) /* barriers, TMEM slot */ + 8 * kTraceSteps * 8 /* trace */ +
                          1024 /* alignment */;
     const size_t smem_optin = m->device >= 0 ? (size_t)m->smem_optin : (size_t)227 * 1024;   // host-only model: the sm_100 value
@@ -1151,16 +1221,16 @@ int k3_prepare(bc_model* m) {
     return BC_OK;
 }
 
-template <int FMT>
+template <int FMT, bool SCALED>
 int k3_launch_fmt(bc_model* m, const K3Params& P, const CUtensorMap& tm_w, int grid, cudaStream_t st) {
     static bool attr_set[64] = {};
     int dev = 0;
     BC_CUDA_CHECK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        BC_CUDA_CHECK(cudaFuncSetAttribute(k3_kernel<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_optin));
+        BC_CUDA_CHECK(cudaFuncSetAttribute(k3_kernel<FMT, SCALED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_optin));
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
-    k3_kernel<FMT><<<grid, kThreads, m->k3->smem, st>>>(P, tm_w);
+    k3_kernel<FMT, SCALED><<<grid, kThreads, m->k3->smem, st>>>(P, tm_w);
     BC_CUDA_CHECK(cudaGetLastError());
     bc_count_launch();
     return BC_OK;
@@ -1168,7 +1238,7 @@ int k3_launch_fmt(bc_model* m, const K3Params& P, const CUtensorMap& tm_w, int g
 
 }  // namespace
 
-int bc_k3_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32_t* fan_mask, float* out, cudaStream_t st) {
+int bc_k3_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32_t* fan_mask, float* out, cudaStream_t st, int32_t* out_exp) {
     if (nq == 0) return BC_OK;
     if (fmt != BC_DESC_BITS && fmt != BC_DESC_DENSE_F32) {
         bc_set_error("the fused kernel reads BITS or DENSE_F32 rows (convert range rows with bc_convert_desc)");
@@ -1206,6 +1276,7 @@ int bc_k3_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32
     P.root_lam_off = r.lam_off;
     P.root_fan_off = r.fan_off;
     P.out = out;
+    P.out_exp = out_exp;
     P.nq = nq;
     P.n_tiles = (long long)((nq + kTile - 1) / kTile);
     P.bits_words = m->bits_words;
@@ -1274,9 +1345,10 @@ int bc_k3_launch(bc_model* m, const void* desc, size_t nq, int fmt, const uint32
             bc_set_error("cuTensorMapEncodeTiled failed (%d) for %zu DENSE_F32 rows of %d floats", (int)cr, nq, m->lam_total);
             return BC_ECUDA;
         }
-        return k3_launch_fmt<BC_DESC_DENSE_F32>(m, P, tm_w, (int)grid, st);
+        return out_exp ? k3_launch_fmt<BC_DESC_DENSE_F32, true>(m, P, tm_w, (int)grid, st)
+                       : k3_launch_fmt<BC_DESC_DENSE_F32, false>(m, P, tm_w, (int)grid, st);
     }
-    return k3_launch_fmt<BC_DESC_BITS>(m, P, tm_w, (int)grid, st);
+    return out_exp ? k3_launch_fmt<BC_DESC_BITS, true>(m, P, tm_w, (int)grid, st) : k3_launch_fmt<BC_DESC_BITS, false>(m, P, tm_w, (int)grid, st);
 }
 
 extern "C" int bc_model_fused_plan(bc_model* m, int32_t* info, int32_t* edges, size_t edges_capacity) {

@@ -678,7 +678,8 @@ def test_results_below_the_fp32_range(shape):
     tiny = (ref > 0) & (ref < 1e-45)
     assert tiny.sum() > nq // 2, (shape, float(np.median(ref)))   # the case the plain fp32 result cannot represent
     desc = pack_ranges_u16(lo, hi)
-    kernels = (L.KERNEL_GENERIC, L.KERNEL_AUTO) if path == "k1" else (L.KERNEL_GEMM_SIMT, L.KERNEL_GEMM, L.KERNEL_AUTO)
+    # (small domains: also the fused tensor-core kernel, which is what AUTO picks for them)
+    kernels = (L.KERNEL_GENERIC, L.KERNEL_FUSED, L.KERNEL_AUTO) if path == "k1" else (L.KERNEL_GEMM_SIMT, L.KERNEL_GEMM, L.KERNEL_AUTO)
     for kernel in kernels:
         got = dm.run_host_scaled(desc, L.DESC_RANGE_U16, None, kernel)
         assert got.dtype == np.float64 and got[1] == 0.0 and abs(got[0] - 1.0) < 1e-5
@@ -688,6 +689,29 @@ def test_results_below_the_fp32_range(shape):
     # the plain fp32 entry point flushes these to zero / denormals: that is what the scaled one is for
     plain = dm.run_host(desc, L.DESC_RANGE_U16, None, kernels[0])
     assert np.all(plain[tiny] < 1e-37)
+    dm.close()
+
+
+@pytest.mark.parametrize("shape", ["deep_hub_tail", "hub_112_columns", "two_hubs", "star_root_split"])
+def test_scaled_results_through_the_fused_kernel(shape):
+    """The exponent K3 carries through its epilogue (register accumulators, tensor-memory fallback, tail edges that belong to the
+    previous tile of the CTA): several passes per CTA, results compared in fp64 -- mantissa * 2^exponent must equal the oracle
+    whether or not the plain fp32 result would have survived."""
+    from bayescard_b200.synth import make_tree_model, pack_ranges_u16, random_range_queries
+
+    parent, cards = K3_SHAPES[shape]
+    tm = make_tree_model(len(cards), cards, seed=5, dtype=np.float32, parent=parent)
+    dm = DeviceModel(tm, device=0, specialize=False)
+    nq = 50000
+    lo, hi = random_range_queries(tm, nq, seed=9, kmax=len(cards))
+    narrow = np.random.default_rng(1).random(lo.shape) < 0.5       # half of the predicates collapse to one (often rare) state
+    hi = np.where(narrow, lo, hi)
+    ref = O.dense_tree(tm, O.range_weights(tm, lo, hi))
+    got = dm.run_host_scaled(pack_ranges_u16(lo, hi), L.DESC_RANGE_U16, None, L.KERNEL_FUSED)
+    err = rel_err(got, ref)
+    err[ref == 0] = 0
+    assert err.max() <= RTOL, (shape, float(err.max()), float(ref[err.argmax()]))
+    assert np.array_equal(got == 0, ref == 0)
     dm.close()
 
 
