@@ -221,8 +221,9 @@ BC_API int bc_pipe_wait(bc_model* m, uint64_t ticket);
  * flushes to zero.  The *_scaled entry points carry one power-of-two exponent per query: the kernels renormalise a
  * message row (exactly, by a power of two) every time an edge has been multiplied in, and return
  *     probability[q] = out_mantissa[q] * 2^out_exponent[q]          (combine in fp64: ldexp(mantissa, exponent)).
- * Served by the generic kernel (K1: every descriptor format, fan-out masks) and the batched large-domain path
- * (K2: RANGE_* rows); BC_KERNEL_AUTO picks between them the way bc_query_batch does for a model without an image.
+ * Served by the generic kernel (K1: every descriptor format, fan-out masks), the fused tensor-core kernel (K3: every
+ * format, fan-out masks, the models it plans) and the batched large-domain path (K2: RANGE_* rows); BC_KERNEL_AUTO picks
+ * between them the way bc_query_batch does for a model without an image.
  * DEVICE pointers, stream ordered. */
 BC_API int bc_query_batch_scaled(bc_model* m, const void* desc, size_t n_queries, int desc_format,
                                  const uint32_t* fanout_mask, float* out_mantissa, int32_t* out_exponent, int kernel,
