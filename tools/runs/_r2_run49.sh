@@ -1,7 +1,7 @@
 #!/bin/bash
 # round 2, run 49: final verification on one GPU: whole GPU suite, smoke(), both bench arms
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
+timeout 300 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
 timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2_49_ref.json 2>/dev/null; echo "ref rc=$?"; python -c "
 import json; d=json.loads(open('gpurun_out/r2_49_ref.json').read().strip().splitlines()[-1]); print('ref', d['value'], d['cpu_baseline']['kind'], d['cpu_baseline']['cores'], d.get('config'))"
