@@ -58,6 +58,7 @@ _SIGS = {
     "bc_model_specialize": (C.c_int, [C.c_void_p, C.c_char_p]),
     "bc_model_has_spec": (C.c_int, [C.c_void_p]),
     "bc_model_fused_plan": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "bc_model_fused_sequence": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int32)]),
     "bc_model_spec_source": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "bc_model_spec_hash": (C.c_uint64, [C.c_void_p]),
     "bc_model_load_cubin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),

@@ -1378,6 +1378,23 @@ extern "C" int bc_model_fused_plan(bc_model* m, int32_t* info, int32_t* edges, s
     return BC_OK;
 }
 
+extern "C" int bc_model_fused_sequence(bc_model* m, uint8_t* sequence, uint8_t* flags, size_t capacity, int32_t* n_tail) {
+    if (!m || !sequence || !flags || !n_tail) { bc_set_error("model/sequence/flags/n_tail is NULL"); return BC_EINVAL; }
+    {
+        std::lock_guard<std::mutex> g(m->k3_mu);
+        int rc = k3_prepare(m);
+        if (rc) return rc;
+    }
+    const BcK3Plan* k = m->k3;
+    if (capacity < k->edges.size() || k->seq.size() != k->edges.size()) { bc_set_error("sequence buffer too small"); return BC_EINVAL; }
+    for (size_t i = 0; i < k->edges.size(); ++i) {
+        sequence[i] = k->seq[i];
+        flags[i] = (uint8_t)k->edges[i].flags;
+    }
+    *n_tail = k->n_tail;
+    return BC_OK;
+}
+
 void bc_k3_free(bc_model* m) {
     if (!m->k3) return;
     cudaFree(m->k3->d_bimg);

@@ -137,6 +137,11 @@ BC_API int bc_model_has_spec(const bc_model* m);
  *               ring steps}; may be NULL.
  * BC_ELIMIT (with the reason in bc_last_error) when K3 does not serve the model. */
 BC_API int bc_model_fused_plan(bc_model* m, int32_t* info, int32_t* edges, size_t edges_capacity);
+/* ... and its step sequence: sequence[i] = edge index (position in the schedule above) | 128 for a TAIL edge, which a CTA runs for
+ * its PREVIOUS tile (the chain at the top of the tree is interleaved with the next tile's body); flags[e] per edge: bit 0 first /
+ * bit 1 last edge of a run of consecutive edges into one parent, bit 2 the parent's message stays in the epilogue warps' registers
+ * over the run.  *n_tail = number of tail edges (the last ones of the schedule).  Both arrays hold `edges` entries. */
+BC_API int bc_model_fused_sequence(bc_model* m, uint8_t* sequence, uint8_t* flags, size_t capacity, int32_t* n_tail);
 /* Write the generated CUDA source of the specialised kernel (host only, no GPU needed; used by the
  * ahead-of-time build and by tests).  Returns the number of bytes needed including the NUL. */
 BC_API int64_t bc_model_spec_source(const bc_model* m, char* buf, size_t buf_bytes);

@@ -5,6 +5,8 @@ import ctypes
 import os
 import re
 
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -470,6 +472,90 @@ def test_fused_kernel_plan_invariants(name):
     info, edges, why = _fused_plan(wide)
     assert info is not None and int(info[0]) == 99, why
     wide.close()
+
+
+K3_PLAN_SHAPES = {
+    "star_root_split": ([-1, 0, 0, 0, 0, 0, 0], [40, 50, 33, 64, 7, 50, 21]),
+    "chain": ([-1, 0, 1, 2, 3], [8, 40, 60, 50, 33]),
+    "root_two_internal": ([-1, 0, 0, 1, 1, 2, 2, 0], [30, 45, 52, 20, 61, 33, 17, 9]),
+    "hub_112_columns": ([-1, 0, 1, 1, 1, 1], [5, 110, 40, 50, 60, 70]),
+    "root_100_states": ([-1, 0, 0, 0, 3], [100, 20, 30, 40, 50]),
+    "deep_hub_tail": ([-1, 0, 1, 2, 3, 3, 3, 3], [3, 12, 70, 84, 80, 9, 77, 50]),
+    "two_hubs": ([-1, 0, 1, 1, 1, 0, 5, 5, 5], [6, 60, 30, 40, 50, 72, 20, 64, 33]),
+    "hub_two_runs_under_a_chain": ([-1, 0, 1, 2, 2, 3, 3, 4, 4], [4, 30, 110, 20, 25, 9, 9, 8, 8]),
+}
+
+
+@pytest.mark.parametrize("name", list(G.MODEL_NAMES) + sorted(K3_PLAN_SHAPES))
+def test_fused_kernel_step_sequence(name):
+    """K3's step sequence (bc_model_fused_sequence), checked without a GPU: every edge once; the tail = the maximal suffix of edges
+    that are the only message into their parent (at least one body edge stays); tail edges keep their order, never use the
+    register accumulator, and the first of them comes BEFORE the first body write into the message it reads -- the end of the
+    first run into that node when the node's message lives in registers, its first edge when it is updated in tensor memory
+    (the bug the GPU tree-shape tests found); the nodes a tail edge reads or writes own their tensor-memory columns outright."""
+    from bayescard_b200.synth import make_tree_model
+
+    if name in K3_PLAN_SHAPES:
+        parent, cards = K3_PLAN_SHAPES[name]
+        m = make_tree_model(len(cards), cards, seed=1, dtype=np.float32, parent=parent)
+    else:
+        m = G.model(name)
+    dm = DeviceModel(m, device=-1, specialize=False)
+    info, edges, why = _fused_plan(dm)
+    if info is None:
+        dm.close()
+        pytest.skip(f"K3 declines this model: {why}")
+    n_edges = int(info[0])
+    seq, flags = np.zeros(n_edges, dtype=np.uint8), np.zeros(n_edges, dtype=np.uint8)
+    n_tail = C.c_int32()
+    L.check(L.lib().bc_model_fused_sequence(dm._h, seq.ctypes.data, flags.ctypes.data, n_edges, C.byref(n_tail)))
+    n_tail = n_tail.value
+    n_body = n_edges - n_tail
+    child = edges[:, 0].tolist()
+    par = [int(m.parent[v]) for v in child]
+    n_msgs = {p: par.count(p) for p in set(par)}
+    assert sorted(int(x) & 127 for x in seq) == list(range(n_edges))
+    # the tail: maximal suffix of only-message edges, one body edge at least
+    want_tail = 0
+    while want_tail < n_edges - 1 and n_msgs[par[n_edges - 1 - want_tail]] == 1:
+        want_tail += 1
+    assert n_tail == want_tail and n_body >= 1
+    pos = {int(x) & 127: i for i, x in enumerate(seq)}
+    for e in range(n_edges):
+        assert bool(int(seq[pos[e]]) & 128) == (e >= n_body)
+        run_first = e == 0 or par[e - 1] != par[e]
+        run_last = e == n_edges - 1 or par[e + 1] != par[e]
+        assert bool(flags[e] & 1) == run_first and bool(flags[e] & 2) == run_last
+        if e >= n_body:
+            assert not flags[e] & 4                     # a tail edge never touches the register accumulator
+        else:
+            assert bool(flags[e] & 4) == (int(edges[e, 3]) <= 96)
+    body_order = [int(x) for x in seq if not int(x) & 128]
+    tail_order = [int(x) & 127 for x in seq if int(x) & 128]
+    assert body_order == list(range(n_body)) and tail_order == list(range(n_body, n_edges))
+    if n_tail:
+        hub = child[n_body]                             # the node whose message the first tail edge reads
+        into_hub = [e for e in range(n_body) if par[e] == hub]
+        assert into_hub, "the node below the chain has children (else it would be part of the chain)"
+        in_regs = bool(flags[into_hub[0]] & 4)
+        first_write = next(e for e in into_hub if flags[e] & 2) if in_regs else into_hub[0]
+        assert pos[n_body] < pos[first_write], (name, seq.tolist())
+        # pinned nodes own their columns: no other message overlaps them
+        pinned = {child[e] for e in range(n_body, n_edges)} | {par[e] for e in range(n_body, n_edges)}
+        col_of = {}
+        for e in range(n_edges):
+            if int(edges[e, 4]) >= 0:
+                col_of[child[e]] = int(edges[e, 4])
+            if int(edges[e, 5]) >= 0:
+                col_of[par[e]] = int(edges[e, 5])
+        width = lambda v: -(-int(m.card[v]) // 8) * 8
+        for v in pinned:
+            if v not in col_of:
+                continue                                # (the root in registers)
+            for u, c in col_of.items():
+                if u != v:
+                    assert col_of[v] + width(v) <= c or c + width(u) <= col_of[v], (name, v, u)
+    dm.close()
 
 
 def test_shard_split():
