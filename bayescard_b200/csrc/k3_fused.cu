@@ -37,8 +37,15 @@
 //   * warp 13          TMA WARP: T_v^T blocks (hi and lo, pre-split and pre-swizzled once per model into an "operand image",
 //     L2 resident) by ONE bulk copy per step, and the DENSE weight blocks; the step sequence is static, so both rings run
 //     ahead across edges and tiles.
-// Lambda_v of every live internal node sits in tensor memory (one fp32 column per state); the columns are assigned on the
-// host by first fit over the nodes' lifetimes in the edge schedule.
+// Lambda_v of every live internal node sits in tensor memory (one fp32 column per state) from the end of the run that
+// completes it; the columns are assigned on the host by first fit over the nodes' lifetimes in the edge schedule.
+//
+// Step sequence (K3Params::seq): the chain at the top of the tree -- edges that are each the only message into their parent --
+// is cut off a tile's own pass and interleaved with the body of the CTA's NEXT tile (every hop of it waits for the complete
+// result of the one before; alone it left the tensor pipe idle for 35-40 % of a tile).  Every role walks the same static
+// (edge, tile) sequence; k3_kernel<FMT, true> additionally carries a power-of-two exponent per query through the epilogue
+// (results beyond the fp32 range).  A CTA's timeline, measured with the clock stamps of BC_K3_TRACE_BUILD, and what bounds
+// the kernel now are in DESIGN.md section 4.
 //
 // Algorithmic work per query = flops_dense(model) (every CPT entry once); HBM traffic = descriptor row + 4 B.
 #include <cuda.h>
