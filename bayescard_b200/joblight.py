@@ -215,6 +215,9 @@ class NativeJobLight:
         if getattr(self, "_h", None):
             L.lib().bc_joblight_destroy(self._h)
             self._h = None
+        if getattr(self, "_dev_pool", None) is not None:
+            self._dev_pool.shutdown(wait=True)
+            self._dev_pool = None
         for c in getattr(self, "sqlc", []):
             c.close()
 
@@ -309,13 +312,12 @@ class NativeJobLight:
         nf = plan["factor_bn"].size
         prob = np.zeros(nf, dtype=np.float64)
         python_factors = []
-        rows = self.factor_rows(plan, wsparse=True)
-        t2 = time.perf_counter()
-        for b, (ids, kind, bits, ws, didx) in rows.items():
+
+        def device_part(b, ids, kind, bits, ws, didx):
+            """One BN's factors through the device (disjoint slots of ``prob``); returns the factors the mirror has to redo."""
             m = self.machines[b]
             mask = plan["factor_fan_mask"][ids].reshape(-1, 1)
-            n_bits = int(np.count_nonzero(kind == L.SQLC_BITS))
-            if n_bits:
+            if np.count_nonzero(kind == L.SQLC_BITS):
                 # every row of the BN goes through the kernel (rows of the other kinds hold arbitrary selection bits: finite
                 # results that are not used) -- cheaper than gathering the BITS rows on the host
                 p_all = m.dev.run_host(bits, L.DESC_BITS, mask, m.kernel)
@@ -323,11 +325,31 @@ class NativeJobLight:
                 prob[ids[sel]] = p_all[sel]
             if didx.size:   # fractional weights: weighted runs over PCIe (~100 B per factor), DENSE rows built on the device
                 prob[ids[didx]] = m.dev.run_wsparse_host(ws[0], ws[1], np.ascontiguousarray(mask[didx]), m.kernel)
-            bad = (kind == L.SQLC_PYTHON) | ((kind == L.SQLC_ZERO) & (mask[:, 0] != 0))
             # SQLC_ZERO: probability 0 (already) -- except on an EXPECTATION factor: Bayescard_BN.expectation has no guard for an
             # undecodable predicate and the reference fails there (Models/Bayescard_BN.py:581-583); the mirror raises the same
-            if bad.any():
-                python_factors.extend(ids[np.nonzero(bad)[0]].tolist())
+            bad = (kind == L.SQLC_PYTHON) | ((kind == L.SQLC_ZERO) & (mask[:, 0] != 0))
+            return ids[np.nonzero(bad)[0]].tolist() if bad.any() else []
+
+        # decode + pack of model b + 1 (host threads inside the library) runs while model b is on the device (one worker thread:
+        # the device calls block in CUDA with the GIL released)
+        if getattr(self, "_dev_pool", None) is None:
+            from concurrent.futures import ThreadPoolExecutor
+
+            self._dev_pool = ThreadPoolExecutor(max_workers=1)
+        t_dec = 0.0
+        futs = []
+        for b in range(self.n_bn):
+            td = time.perf_counter()
+            ids = np.nonzero(plan["factor_bn"] == b)[0].astype(np.uint32)
+            if ids.size == 0:
+                continue
+            rows_b = self.sqlc[b].compile_factors(ids, plan["pred_off"], plan["pred_col"], plan["pred_kind"], plan["pred_a"],
+                                                  plan["pred_b"], plan["factor_fan_mask"], True)
+            t_dec += time.perf_counter() - td
+            futs.append(self._dev_pool.submit(device_part, b, ids, *rows_b))
+        t2 = time.perf_counter()
+        for f in futs:
+            python_factors.extend(f.result())
         t3 = time.perf_counter()
         out = np.zeros(nq, dtype=np.float64)
         redo = set(np.nonzero(plan["status"])[0].tolist())
@@ -347,5 +369,6 @@ class NativeJobLight:
                 tq = self.ens.parse_query_all([plan_star_query(text_of(q), self.join_sizes)])[0]
                 out[q] = float(np.asarray(self.ens.cardinality(tq)).reshape(-1)[0])
         if timing is not None:
-            timing.update(plan=t1 - t0, decode_pack=t2 - t1, device=t3 - t2, combine=time.perf_counter() - t3, factors=int(nf))
+            timing.update(plan=t1 - t0, decode_pack=t_dec, decode_pack_with_device_overlapped=t2 - t1, device_tail=t3 - t2,
+                          combine=time.perf_counter() - t3, factors=int(nf))
         return out
