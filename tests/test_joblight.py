@@ -255,6 +255,15 @@ def test_native_planner_and_factor_rows_equal_the_python_mirror():
     for key, want in plan_c.items():
         assert np.array_equal(plan[key], want) and np.array_equal(plan_b[key], want), key
     assert (gf.value, gp.value) == (nf, npred)
+    # non-ASCII text: byte offsets, not character counts; such a text is simply not a job-light query
+    odd = ["SELECT COUNT(*) FROM title t WHERE t.kind_id=1 AND t.note='caf\u00e9 \u4e2d\u6587'", sqls[0], "\u00e9", sqls[1]]
+    blob2, off2 = nat.join_texts(odd)
+    assert [blob2[int(off2[i]):int(off2[i + 1])].decode("utf-8").rstrip("\n") for i in range(4)] == odd
+    p_odd = nat.plan(odd)
+    assert p_odd["status"].tolist() == [1, 0, 1, 0]
+    for key in ("factor_bn", "factor_inverse", "factor_fan_mask"):
+        assert np.array_equal(p_odd[key], np.concatenate([plan[key][int(plan["first_factor"][q]):int(plan["first_factor"][q + 1])] for q in (0, 1)]))
+    assert nat.plan([])["n_queries"] == 0 and nat.plan(b"", np.zeros(1, dtype=np.uint64))["factor_bn"].size == 0
     # combine: BN_ensemble.cardinality's rules
     first = np.asarray([0, 2, 4, 5], dtype=np.uint32)
     inv = np.asarray([0, 1, 0, 0, 0], dtype=np.uint8)
